@@ -1,0 +1,139 @@
+/*
+ * sodt_b200 -- C ABI of the B200-native (sm_100a) attention / Detect / NMS hot path of
+ * the cross-channel RGB+IR small-object detector.
+ *
+ * The reference (Bissmella/Small-object-detection-transformers) is pure Python/PyTorch and
+ * has no FFI layer; its only native hook is the dangling WindowProcess /
+ * WindowProcessReverse pair behind `fused_window_process` (basics/models/backbone_vit.py:1100,1120).
+ * Each entry point below therefore replaces a span of reference Python, cited per function.
+ * The binding a reference maintainer would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - the caller owns all memory (inputs, outputs, workspaces); nothing is allocated or freed here;
+ *   - every function returns a sodt_status (0 = ok, negative = error) and never throws;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no call synchronises the device;
+ *   - `dtype` selects the storage type of activations: SODT_F32 or SODT_BF16.  Softmax, LayerNorm
+ *     statistics, Detect decode and all NMS arithmetic are always fp32;
+ *   - entry points are re-entrant and keep no mutable global state.
+ */
+#ifndef SODT_B200_H_
+#define SODT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SODT_OK = 0,
+    SODT_ERR_INVALID_ARG = -1,   /* null pointer, non-positive extent, C % heads != 0 ... */
+    SODT_ERR_UNSUPPORTED = -2,   /* shape outside what the kernels implement (see each function) */
+    SODT_ERR_WORKSPACE = -3,     /* workspace pointer null or too small */
+    SODT_ERR_CUDA = -4,          /* a CUDA runtime call failed; see sodt_last_cuda_error() */
+    SODT_ERR_ALIGNMENT = -5      /* a pointer is not 16-byte aligned */
+} sodt_status;
+
+typedef enum { SODT_F32 = 0, SODT_BF16 = 1 } sodt_dtype;
+
+/* Library / build identification. */
+int sodt_version(void);                         /* e.g. 100 = 0.1.0 */
+const char* sodt_status_string(int status);     /* static string */
+const char* sodt_last_cuda_error(void);         /* static string of the last CUDA error seen by this thread */
+int sodt_built_for_sm(void);                    /* 100 (sm_100a) */
+
+/*
+ * Window multi-head self-attention on the projected token image.
+ * Replaces backbone_vit.py:1094-1123 (torch.roll, window_partition, WindowAttention's
+ * score/bias/mask/softmax/AV at :971-989, window_unpartition, reverse roll) -- everything
+ * between the qkv Linear (:968) and the proj Linear (:990).  No window tensor, score tensor,
+ * bias tensor or mask tensor is materialised.
+ *
+ *   qkv        [B, H, W, 3*C]  channel order (3, heads, C/heads), un-rolled, un-padded
+ *   bias_table [(2*ws-1)^2, heads] fp32 (relative_position_bias_table; the int64 index buffer is
+ *              not needed: index = (yi-yj+ws-1)*(2*ws-1) + (xi-xj+ws-1))
+ *   pad_qkv    [3*C] or NULL: q/k/v of tokens added by padding H, W up to multiples of ws
+ *              (the qkv bias; NULL = zeros).  Only read when H % ws or W % ws is non-zero.
+ *   out        [B, H, W, C]
+ *   shift      cyclic shift (0 <= shift < ws).  shift > 0 applies the shifted-window mask
+ *              (region ids of backbone_vit.py:1060-1072 evaluated in closed form) with
+ *              `mask_value` (-100.0 in the reference, finite on purpose).
+ *   scale      multiplies q (head_dim^-0.5 in the reference).
+ * Supported: C % heads == 0, head_dim <= 64, any ws >= 1 (tokens per window unbounded).
+ */
+int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
+                         int B, int H, int W, int C, int heads, int ws, int shift,
+                         int dtype, float scale, float mask_value, void* stream);
+
+/*
+ * Cross-channel attention block over the four token streams R, G, B, IR.
+ * Replaces CAttentionBlock.forward, backbone_vit.py:469-561 (and its general-window twin
+ * backbone_swinv2.py:429-469): four parameter-free multi-head cross attentions
+ * (R<-G, G<-B, B<-IR, IR<-G; CAttention.forward backbone_vit.py:589-616) each followed by
+ * LayerNorm_i(stream_i + attn_i).
+ *
+ *   r,g,b,ir   [B, h, w, C] each, addressed through element strides (sb, sy, sx, sc) shared by
+ *              the four streams, so both NHWC tensors and the NCHW outputs of the
+ *              channel-embedding convs (backbone_vit.py:196-199,772) are read in place
+ *   ln_w, ln_b [4, C] fp32 (norm1..norm4 weight / bias)
+ *   out        [B, h, w, 4*C] contiguous: the concatenation of backbone_vit.py:210
+ *   ws         window size (1 in the shipped model => attention is the identity on v and the
+ *              block is 4 fused add+LayerNorms); shift as for window attention, mask added
+ *              BEFORE the 1/sqrt(C/heads) scaling (backbone_vit.py:601-608)
+ * Supported: C % heads == 0, C <= 128, ws*ws <= 144.
+ */
+int sodt_cattn_block_fwd(const void* r, const void* g, const void* b, const void* ir,
+                         long long sb, long long sy, long long sx, long long sc,
+                         const float* ln_w, const float* ln_b, void* out,
+                         int B, int h, int w, int C, int heads, int ws, int shift,
+                         float eps, float mask_value, int dtype, void* stream);
+
+/*
+ * YOLOv5 Detect decode for one level.  Replaces model.py:55-64 (view/permute/contiguous,
+ * sigmoid, grid + anchor decode, view) for the output of the level's 1x1 conv (model.py:53).
+ *
+ *   raw        [B, na*no, ny, nx] addressed through element strides (sb, sc, sy, sx)
+ *              (NCHW or channels_last)
+ *   anchors_px [na, 2] fp32 (Detect.anchor_grid, pixels)
+ *   z          fp32 rows: z[(b*rows_total + row_offset + (a*ny + y)*nx + x)*no + o]; with one level
+ *              rows_total = na*ny*nx and row_offset = 0 (model.py:64-65 concatenates levels on rows)
+ *   x_perm     [B, na, ny, nx, no] in `dtype`, or NULL (the second return value of Detect.forward)
+ */
+int sodt_detect_decode(const void* raw, long long sb, long long sc, long long sy, long long sx,
+                       const float* anchors_px, float* z, void* x_perm,
+                       int B, int na, int no, int ny, int nx, float stride,
+                       long long rows_total, long long row_offset, int dtype, void* stream);
+
+/*
+ * Batched non_max_suppression.  Replaces basics/utils/general.py:425-512 including the
+ * torchvision.ops.nms call at :496 (class-offset boxes, greedy suppression in stable
+ * descending-score order, IoU = inter / (area_a + area_b - inter) in fp32, suppress iff IoU > thr),
+ * the max_det cut, merge-NMS and the `redundant` filter.  The 10 s watchdog (:508-510) is not
+ * reproduced.
+ *
+ *   pred       [B, R, 5+nc] fp32 decoded predictions (cx, cy, w, h, obj, cls...)
+ *   classes    [n_classes] int32 class filter or NULL
+ *   out        [B, max_det, 6] fp32 rows (x1, y1, x2, y2, conf, cls), descending conf; rows beyond
+ *              counts[b] are zero.  May point into an NCCL send buffer (no pack step).
+ *   counts     [B] int32
+ *   keep_idx   [B, max_det] int32 or NULL: kept candidate indices (reference candidate order after
+ *              the max_nms cut) -- the quantity that is bit-exact against the reference
+ *   workspace  sodt_nms_workspace_bytes(B, R, nc, multi_label) bytes, 16-byte aligned
+ */
+size_t sodt_nms_workspace_bytes(int B, int R, int nc, int multi_label);
+int sodt_nms(const float* pred, const int* classes, int n_classes, float* out, int* counts, int* keep_idx,
+             void* workspace, size_t workspace_bytes, int B, int R, int nc,
+             float conf_thres, double iou_thres, int multi_label, int agnostic, int merge, int redundant,
+             int max_det, int max_nms, float max_wh, void* stream);
+
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+long long sodt_launch_count(void);
+void sodt_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SODT_B200_H_ */

@@ -1,0 +1,65 @@
+"""ctypes binding of the C ABI declared in include/sodt_b200.h.
+
+The shared library is built in-tree by ``build.py`` (nvcc, sm_100a).  Loading is lazy and
+fails loudly: there is no fallback implementation of any entry point.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libsodt_b200.so")
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_ll = ctypes.c_longlong
+_f = ctypes.c_float
+_d = ctypes.c_double
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/sodt_b200.h
+SIGNATURES = {
+    "sodt_version": (_i, []),
+    "sodt_status_string": (ctypes.c_char_p, [_i]),
+    "sodt_last_cuda_error": (ctypes.c_char_p, []),
+    "sodt_built_for_sm": (_i, []),
+    "sodt_window_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p]),
+    "sodt_cattn_block_fwd": (_i, [_p, _p, _p, _p, _ll, _ll, _ll, _ll, _p, _p, _p,
+                                  _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p]),
+    "sodt_detect_decode": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _f, _ll, _ll, _i, _p]),
+    "sodt_nms_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "sodt_nms": (_i, [_p, _p, _i, _p, _p, _p, _p, _sz, _i, _i, _i, _f, _d, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "sodt_launch_count": (_ll, []),
+    "sodt_reset_launch_count": (None, []),
+}
+
+_lib = None
+
+
+class SodtError(RuntimeError):
+    pass
+
+
+def lib():
+    """Returns the loaded library; raises SodtError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SodtError(
+                f"{LIB_PATH} is missing: build it with `python small-object-detection-transformers_b200/build.py` "
+                "(or __graft_entry__.build()).  There is no CPU fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        L = lib()
+        msg = L.sodt_status_string(status).decode()
+        if status == -4:
+            msg += ": " + L.sodt_last_cuda_error().decode()
+        raise SodtError(f"{what} failed: {msg} (status {status})")

@@ -1,0 +1,383 @@
+"""Host-side mirror of the reference backbone (basics/models/backbone_vit.py) for the hot path.
+
+Same class names, constructor arguments, parameter / buffer names and shapes as the reference,
+so its state_dicts and pickled checkpoints resolve here.  The attention math does not run in
+torch: ``SwinTransformerBlock`` and ``CAttentionBlock`` call the sm_100a kernels through the
+C ABI (``ops.window_attention`` / ``ops.cattn_block``); LayerNorm, the Linear / conv GEMMs and
+GELU around them stay torch library calls (cuBLAS / cuDNN), as scoped in SURVEY.md section 8a.
+
+Differences from the reference, all deliberate:
+  * the token grid follows the input instead of the hard-coded 128x128
+    (reference backbone_vit.py:119,136,153,1087), so 1024^2 and 2048^2 inputs run;
+  * no window / rolled / score / bias / mask tensor is ever materialised;
+  * activations stay channels-last ([B,H,W,C]) end to end; 1x1 convs run as GEMMs on that layout.
+"""
+import math
+from functools import partial
+from typing import Optional, Tuple, Type
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import ops
+
+MASK_VALUE = -100.0
+
+
+def to_2tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+# ------------------------------------------------------------------ reference-compatible helpers
+def window_partition(x: torch.Tensor, window_size: int, top_padding: bool = False):
+    """[B,H,W,C] -> ([B*nW, ws, ws, C], (Hp, Wp)); API of reference backbone_vit.py:619.
+    Kept for callers of the reference API; the fused kernels never call it."""
+    B, H, W, C = x.shape
+    ph, pw = (-H) % window_size, (-W) % window_size
+    if ph or pw:
+        x = F.pad(x, (0, 0, pw, 0, ph, 0) if top_padding else (0, 0, 0, pw, 0, ph))
+    Hp, Wp = H + ph, W + pw
+    x = x.reshape(B, Hp // window_size, window_size, Wp // window_size, window_size, C)
+    return x.transpose(2, 3).reshape(-1, window_size, window_size, C), (Hp, Wp)
+
+
+def window_unpartition(windows: torch.Tensor, window_size: int, pad_hw: Tuple[int, int], hw: Tuple[int, int],
+                       top_padding: bool = False):
+    """Inverse of window_partition + crop; API of reference backbone_vit.py:646."""
+    Hp, Wp = pad_hw
+    H, W = hw
+    nh, nw = Hp // window_size, Wp // window_size
+    B = windows.shape[0] // (nh * nw)
+    x = windows.reshape(B, nh, nw, window_size, window_size, -1).transpose(2, 3).reshape(B, Hp, Wp, -1)
+    if Hp > H or Wp > W:
+        x = x[:, Hp - H:, Wp - W:] if top_padding else x[:, :H, :W]
+    return x.contiguous()
+
+
+def get_channels(x):
+    """Four single-channel views of a [B,4,H,W] tensor (reference backbone_vit.py:810)."""
+    return tuple(x[:, c:c + 1] for c in range(4))
+
+
+def _relative_position_index(wh: int, ww: int) -> torch.Tensor:
+    ys = torch.arange(wh).repeat_interleave(ww)
+    xs = torch.arange(ww).repeat(wh)
+    return (ys[:, None] - ys[None, :] + wh - 1) * (2 * ww - 1) + (xs[:, None] - xs[None, :] + ww - 1)
+
+
+def _shift_mask(H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """The reference's attn_mask buffer ([nW, N, N], 0 / -100) in closed form.  Registered only so
+    that state_dict keys and shapes match; the kernels evaluate the same region ids on the fly."""
+    def axis(n):
+        a = torch.arange(n)
+        return (a >= n - ws).long() + (a >= n - shift).long()
+    ids = (3 * axis(H)[:, None] + axis(W)[None, :]).float().reshape(1, H, W, 1)
+    win, _ = window_partition(ids, ws)
+    flat = win.reshape(-1, ws * ws)
+    diff = flat[:, None, :] - flat[:, :, None]
+    return torch.where(diff != 0, torch.full_like(diff, MASK_VALUE), torch.zeros_like(diff))
+
+
+# --------------------------------------------------------------------------------- small layers
+class PatchEmbed(nn.Module):
+    """Conv patch embedding returning channels-last tokens (reference backbone_vit.py:742).
+    Note the reference's default padding of (1, 1), which channel_embed_r inherits."""
+
+    def __init__(self, kernel_size=(16, 16), stride=(16, 16), padding=(1, 1), in_chans: int = 3, embed_dim: int = 768):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=kernel_size, stride=stride, padding=padding)
+
+    def forward(self, x):
+        return self.proj(x).permute(0, 2, 3, 1)
+
+    def forward_tokens(self, x):
+        """1x1 / stride-1 projection applied directly on [B,H,W,Cin] tokens as a GEMM."""
+        w = self.proj.weight
+        return F.linear(x, w.reshape(w.shape[0], w.shape[1]), self.proj.bias)
+
+
+class PatchMerging(nn.Module):
+    """2x2 neighbourhood gather + Linear(4C -> 2C) + LayerNorm (reference backbone_vit.py:823)."""
+
+    def __init__(self, input_resolution, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution = input_resolution
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(2 * dim)
+
+    def forward(self, x, input_resolution):
+        H, W = input_resolution
+        B, L, C = x.shape
+        if L != H * W or H % 2 or W % 2:
+            raise ValueError(f"PatchMerging: bad token grid {H}x{W} for {L} tokens")
+        g = x.view(B, H // 2, 2, W // 2, 2, C)
+        # channel order of the reference concat: (dy,dx) = (0,0), (1,0), (0,1), (1,1)
+        g = g.permute(0, 1, 3, 4, 2, 5).reshape(B, (H // 2) * (W // 2), 4 * C)
+        return self.norm(self.reduction(g))
+
+
+class Mlp(nn.Module):
+    """Linear MLP, or the conv-enhanced variant fc1 -> 2x2 conv -> GELU -> fc2
+    (reference backbone_vit.py:863).  Not part of the attention hot path: torch library calls."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, linear_mlp=True, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.linear = linear_mlp
+        self.bs = in_features
+        if linear_mlp:
+            self.fc1 = nn.Linear(in_features, hidden_features)
+            self.act = act_layer()
+            self.fc2 = nn.Linear(hidden_features, out_features)
+        else:
+            self.fc1 = nn.Linear(in_features, in_features)
+            self.act = act_layer()
+            self.conv1 = nn.Conv2d(in_features, in_features, 2)
+            self.fc2 = nn.Linear(in_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x, H, W):
+        if self.linear:
+            return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        B, L, C = x.shape
+        h = self.fc1(x).view(B, H, W, C).permute(0, 3, 1, 2)   # NCHW view of channels-last memory
+        h = F.pad(h, (0, 1, 0, 1))                              # zero column right, zero row below
+        h = self.conv1(h).permute(0, 2, 3, 1).reshape(B, L, C)
+        return self.drop(self.fc2(self.drop(self.act(h))))
+
+
+# ------------------------------------------------------------------------------- window attention
+class WindowAttention(nn.Module):
+    """W-MSA / SW-MSA with relative position bias (reference backbone_vit.py:913).
+
+    Parameters and buffers match the reference: qkv, proj, relative_position_bias_table and the
+    int64 relative_position_index buffer (kept for state_dict compatibility; the kernel computes
+    the index in closed form)."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        if attn_drop or proj_drop:
+            raise NotImplementedError("inference path: dropout must be 0 (the reference model uses 0)")
+        self.dim = dim
+        self.window_size = to_2tuple(window_size)
+        self.num_heads = num_heads
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        wh, ww = self.window_size
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * wh - 1) * (2 * ww - 1), num_heads))
+        self.register_buffer("relative_position_index", _relative_position_index(wh, ww))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def forward_image(self, x, ws, shift):
+        """x: [B,H,W,C] normalised, un-rolled tokens -> [B,H,W,C] (after proj).
+        roll / partition / bias / mask / softmax / AV / reverse all happen inside the kernel."""
+        if ws != self.window_size[0] or ws != self.window_size[1]:
+            raise ValueError("window size does not match the bias table")
+        qkv = self.qkv(x)
+        o = ops.window_attention(qkv, self.relative_position_bias_table, self.num_heads, ws, shift,
+                                 pad_qkv=self.qkv.bias, scale=self.scale, mask_value=MASK_VALUE)
+        return self.proj(o)
+
+    def forward(self, x, mask=None):
+        """Reference signature: x [num_windows*B, N, C] already partitioned (backbone_vit.py:961)."""
+        if mask is not None:
+            raise NotImplementedError(
+                "explicit mask tensors are not taken: SwinTransformerBlock passes the shift to the kernel, "
+                "which evaluates the shifted-window mask in closed form")
+        wh, ww = self.window_size
+        if wh != ww:
+            raise NotImplementedError("square windows only")
+        B_, N, C = x.shape
+        return self.forward_image(x.reshape(B_, wh, ww, C), wh, 0).reshape(B_, N, C)
+
+    def extra_repr(self):
+        return f"dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}"
+
+
+class SwinTransformerBlock(nn.Module):
+    """Swin block (reference backbone_vit.py:1011): x + Attn(LN(x)), then x + Mlp(LN(x))."""
+
+    def __init__(self, dim, input_resolution, num_heads, window_size=7, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm,
+                 fused_window_process=False, linear_mlp=True):
+        super().__init__()
+        if drop_path:
+            raise NotImplementedError("inference path: drop_path must be 0")
+        self.dim = dim
+        self.input_resolution = tuple(input_resolution)
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        if min(self.input_resolution) <= self.window_size:   # window covers the map: one global window, no shift
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        if not 0 <= self.shift_size < self.window_size:
+            raise ValueError("shift_size must be in [0, window_size)")
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, to_2tuple(self.window_size), num_heads, qkv_bias, qk_scale, attn_drop, drop)
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio), act_layer=act_layer, linear_mlp=linear_mlp)
+        mask = _shift_mask(*self.input_resolution, self.window_size, self.shift_size) if self.shift_size > 0 else None
+        self.register_buffer("attn_mask", mask)
+        self.fused_window_process = fused_window_process   # subsumed: windows are never materialised
+
+    def forward(self, x, hw: Optional[Tuple[int, int]] = None):
+        """x [B, H*W, C].  ``hw`` overrides the construction-time token grid (extension)."""
+        H, W = hw if hw is not None else self.input_resolution
+        B, L, C = x.shape
+        if L != H * W:
+            raise ValueError("input feature has wrong size")
+        if min(H, W) <= self.window_size and (H != W or H != self.window_size):
+            raise ValueError(f"token grid {H}x{W} is smaller than the window {self.window_size}")
+        y = self.attn.forward_image(self.norm1(x).view(B, H, W, C), self.window_size, self.shift_size)
+        x = x + y.view(B, L, C)
+        return x + self.mlp(self.norm2(x), H, W)
+
+    def extra_repr(self):
+        return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
+                f"window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
+
+
+# -------------------------------------------------------------------------- cross-channel attention
+class CAttention(nn.Module):
+    """Parameter-free multi-head cross attention over windows (reference backbone_vit.py:566).
+    Exists for state_dict / pickle compatibility; CAttentionBlock runs all four of them in one kernel."""
+
+    def __init__(self, embedding_dim: int, num_heads: int = 8, shift_size=0):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.num_heads = num_heads
+
+
+class CAttentionBlock(nn.Module):
+    """R<-G, G<-B, B<-IR, IR<-G cross attention + LayerNorm (reference backbone_vit.py:407).
+
+    ``forward`` returns the four streams like the reference; ``forward_fused`` returns their
+    concatenation [B,h,w,4C] straight from the kernel (what ImageEncoderViT consumes)."""
+
+    def __init__(self, embedding_dim: int, num_heads: int, out_dim: int = 192, activation: Type[nn.Module] = nn.ReLU,
+                 skip_pe: bool = True, shift_size=0):
+        super().__init__()
+        self.r2g_attn = CAttention(embedding_dim, num_heads, shift_size)
+        self.norm1 = nn.LayerNorm(embedding_dim)
+        self.rg2b_attn = CAttention(embedding_dim, num_heads, shift_size)
+        self.norm2 = nn.LayerNorm(embedding_dim)
+        self.rgb2ir_attn = CAttention(embedding_dim, num_heads, shift_size)
+        self.norm3 = nn.LayerNorm(embedding_dim)
+        self.ir2rgb_attn = CAttention(embedding_dim, num_heads, shift_size)
+        self.norm4 = nn.LayerNorm(embedding_dim)
+        self.num_heads = num_heads
+        self.window_size = 1
+        self.input_resolution = (128, 128)
+        self.shift_size = shift_size
+        mask = _shift_mask(*self.input_resolution, self.window_size, shift_size) if shift_size > 0 else None
+        self.register_buffer("attn_mask", mask)
+
+    def forward_fused(self, r, g, b, ir, window_size: Optional[int] = None):
+        ws = self.window_size if window_size is None else window_size
+        norms = (self.norm1, self.norm2, self.norm3, self.norm4)
+        ln_w = torch.stack([n.weight for n in norms])
+        ln_b = torch.stack([n.bias for n in norms])
+        return ops.cattn_block(r, g, b, ir, ln_w, ln_b, self.num_heads, ws, self.shift_size, self.norm1.eps, MASK_VALUE)
+
+    def forward(self, r, g, b, ir, window_size: int = 1):
+        # like the reference, the `window_size` argument is ignored in favour of self.window_size
+        C = r.shape[-1]
+        return torch.split(self.forward_fused(r, g, b, ir), C, dim=-1)
+
+
+# ---------------------------------------------------------------------------------------- backbone
+class ImageEncoderViT(nn.Module):
+    """Channel embedding -> cross-channel block -> 3 Swin-like stages -> 1x1 necks
+    (reference backbone_vit.py:11-272).  forward(x [B,4,H,W]) -> [y0, y1, y2] in NCHW shape
+    ([B,256,H/4,W/4], [B,256,H/8,W/8], [B,512,H/16,W/16]; channels-last memory)."""
+
+    STAGE_SHIFTS = (0, 2, 0, 2, 0, 2, 0, 2)
+
+    def __init__(self, img_size: int = 512, patch_size: int = 16, in_chans: int = 4, embed_dim: int = 768,
+                 depth: int = 11, num_heads: int = 12, mlp_ratio: float = 4.0, out_chans: int = 256,
+                 qkv_bias: bool = True, norm_layer: Type[nn.Module] = partial(nn.LayerNorm, eps=1e-6),
+                 act_layer: Type[nn.Module] = nn.GELU, use_abs_pos: bool = True, use_rel_pos: bool = True,
+                 rel_pos_zero_init: bool = True, window_size: int = 0, global_attn_indexes: Tuple[int, ...] = ()):
+        super().__init__()
+        self.img_size = img_size
+        grid = img_size // 4
+        self.patch_embed = PatchEmbed(kernel_size=(1, 1), stride=(1, 1), padding=(0, 0), in_chans=192, embed_dim=embed_dim)
+        self.pos_embed: Optional[nn.Parameter] = None
+        if use_abs_pos:
+            self.pos_embed = nn.Parameter(torch.zeros(1, grid, grid, embed_dim))
+        ks = (patch_size, patch_size)
+        self.channel_embed_r = PatchEmbed(kernel_size=ks, stride=(4, 4), in_chans=1, embed_dim=48)  # default padding (1,1)
+        self.channel_embed_g = PatchEmbed(kernel_size=ks, stride=(4, 4), padding=(0, 0), in_chans=1, embed_dim=48)
+        self.channel_embed_b = PatchEmbed(kernel_size=ks, stride=(4, 4), padding=(0, 0), in_chans=1, embed_dim=48)
+        self.channel_embed_i = PatchEmbed(kernel_size=ks, stride=(4, 4), padding=(0, 0), in_chans=1, embed_dim=48)
+        self.chan_block = CAttentionBlock(embedding_dim=48, num_heads=num_heads)
+
+        def stage(n, dim, res, ws, all_linear=False):
+            return nn.ModuleList(
+                SwinTransformerBlock(dim=dim, input_resolution=res, num_heads=num_heads, window_size=ws,
+                                     shift_size=self.STAGE_SHIFTS[i], mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                                     act_layer=act_layer, linear_mlp=all_linear or self.STAGE_SHIFTS[i] == 0)
+                for i in range(n))
+
+        # literal sizes of the reference: dims 192/384/768 -> embed_dim, 2x, 4x at embed_dim=192
+        self.stage1 = stage(6, embed_dim, (128, 128), 8)
+        self.pmerging1 = PatchMerging((128, 128), embed_dim)
+        self.stage2 = stage(4, 384, (64, 64), 8)
+        self.pmerging2 = PatchMerging((64, 64), 384)
+        self.stage3 = stage(1, 768, (32, 32), 32, all_linear=True)
+        self.neck3 = nn.Conv2d(768, 512, kernel_size=1, bias=False)
+        self.neck2 = nn.Conv2d(384, 256, kernel_size=1, bias=False)
+        self.neck1 = nn.Conv2d(384, 256, kernel_size=1, bias=False)
+
+    @staticmethod
+    def _neck(conv, tokens):
+        w = conv.weight
+        return F.linear(tokens, w.reshape(w.shape[0], w.shape[1])).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def _run_stage(blocks, x, hw):
+        for blk in blocks:
+            x = blk(x, hw)
+        return x
+
+    def forward(self, x: torch.Tensor):
+        r, g, b, i = get_channels(x)
+        r = self.channel_embed_r(r)
+        g = self.channel_embed_g(g)
+        b = self.channel_embed_b(b)
+        i = self.channel_embed_i(i)
+        x = self.chan_block.forward_fused(r, g, b, i)            # [B,h,w,192], the reference's concat
+        x = self.patch_embed.forward_tokens(x)
+        if self.pos_embed is not None and x.shape[1] == self.pos_embed.shape[1]:
+            x = x + self.pos_embed                               # silently skipped on a size mismatch, like the reference
+        B, h, w, C = x.shape
+        x = x.reshape(B, h * w, C)
+        kept = []
+        for n, blk in enumerate(self.stage1):
+            x = blk(x, (h, w))
+            if n in (4, 5):
+                kept.append(x.view(B, h, w, C))
+        y0 = torch.cat(kept, dim=-1)
+        x = self.pmerging1(x, (h, w))
+        h2, w2 = h // 2, w // 2
+        x = self._run_stage(self.stage2, x, (h2, w2))
+        y1 = x.view(B, h2, w2, -1)
+        x = self.pmerging2(x, (h2, w2))
+        h3, w3 = h2 // 2, w2 // 2
+        blk3 = self.stage3[0]
+        if min(h3, w3) <= blk3.window_size and (h3 != w3 or h3 != blk3.window_size):
+            raise ValueError(f"stage-3 token grid {h3}x{w3} does not match its {blk3.window_size}-token window; "
+                             "inputs must be multiples of 512 px (or exactly 16*window)")
+        x = self._run_stage(self.stage3, x, (h3, w3))
+        y2 = x.view(B, h3, w3, -1)
+        return [self._neck(self.neck1, y0), self._neck(self.neck2, y1), self._neck(self.neck3, y2)]

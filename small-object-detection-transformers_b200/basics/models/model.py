@@ -1,0 +1,230 @@
+"""Model assembly with the reference's surface: Detect, Model, parse_model
+(reference basics/models/model.py).  The yaml schema ([from, number, module, args] rows,
+depth / width multiples, anchors) and the resulting state_dict keys are unchanged.
+
+Detect's decode runs in one sm_100a kernel (ops.detect_decode); the backbone's attention runs in
+the window / cross-channel kernels (see backbone_vit.py); everything else is torch library code.
+"""
+import logging
+import math
+from copy import deepcopy
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..utils.general import make_divisible
+from .backbone_vit import ImageEncoderViT
+from .common import C3, SPP, Bottleneck, Concat, Conv, DWConv, Focus
+
+logger = logging.getLogger(__name__)
+
+
+class Detect(nn.Module):
+    """YOLOv5 detection layer (reference model.py:32-70)."""
+    stride = None   # set by Model
+    export = False
+
+    def __init__(self, nc=80, anchors=(), ch=()):
+        super().__init__()
+        self.nc = nc
+        self.no = nc + 5
+        self.nl = len(anchors)
+        self.na = len(anchors[0]) // 2
+        self.grid = [torch.zeros(1)] * self.nl   # kept for attribute compatibility; the kernel needs no grid tensor
+        a = torch.tensor(anchors).float().view(self.nl, -1, 2)
+        self.register_buffer("anchors", a)
+        self.register_buffer("anchor_grid", a.clone().view(self.nl, 1, -1, 1, 1, 2))
+        self.m = nn.ModuleList(nn.Conv2d(c, self.no * self.na, 1) for c in ch)
+
+    def forward(self, x):
+        self.training |= self.export
+        raws = [self.m[i](x[i]) for i in range(self.nl)]
+        if self.training:
+            for i, r in enumerate(raws):
+                bs, _, ny, nx = r.shape
+                x[i] = r.view(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+            return x
+        bs = raws[0].shape[0]
+        rows = [self.na * r.shape[2] * r.shape[3] for r in raws]
+        z = torch.empty((bs, sum(rows), self.no), dtype=torch.float32, device=raws[0].device)
+        off = 0
+        for i, r in enumerate(raws):
+            _, x[i] = ops.detect_decode(r, self.anchor_grid[i], float(self.stride[i]), want_perm=True, z=z,
+                                        rows_total=z.shape[1], row_offset=off)
+            off += rows[i]
+        return z, x
+
+
+_MODULES = {
+    "Conv": Conv, "DWConv": DWConv, "Bottleneck": Bottleneck, "C3": C3, "SPP": SPP, "Focus": Focus,
+    "Concat": Concat, "Detect": Detect, "ImageEncoderViT": ImageEncoderViT,
+    "nn.Upsample": nn.Upsample, "nn.BatchNorm2d": nn.BatchNorm2d,
+}
+_WIDTH_SCALED = (Conv, Bottleneck, SPP, DWConv, Focus, C3)
+
+
+def _resolve(token, names):
+    """yaml args are strings like 'nc', 'anchors', 'None', 'nearest'."""
+    if not isinstance(token, str):
+        return token
+    if token in names:
+        return names[token]
+    if token in ("None", "True", "False"):
+        return {"None": None, "True": True, "False": False}[token]
+    return token
+
+
+def parse_model(d, string, ch, config=None):
+    """Builds the 'backbone' module or the 'head' nn.Sequential from a model dict
+    (reference model.py:350-435).  ``ch`` is the running list of channel counts."""
+    anchors, nc, gd, gw = d["anchors"], d["nc"], d["depth_multiple"], d["width_multiple"]
+    na = len(anchors[0]) // 2 if isinstance(anchors, list) else anchors
+    no = na * (nc + 5)
+    names = {"nc": nc, "anchors": anchors}
+    parts = string.split("+")
+    rows = sum((d[p] for p in parts), []) if len(parts) == 2 else d[parts[-1]]
+    if string == "head":   # the three backbone outputs seed the head's channel list (reference model.py:367-370)
+        ch[0] = 256
+        ch += [256, 512]
+    layers, save, c2 = [], [], ch[-1]
+    for i, (f, n, m, args) in enumerate(rows):
+        if isinstance(m, str):
+            if m not in _MODULES:
+                raise KeyError(f"module {m!r} is outside the scope of this package")
+            m = _MODULES[m]
+        args = [_resolve(a, names) for a in args]
+        n = max(round(n * gd), 1) if n > 1 else n
+        if string == "backbone":
+            mod = m(img_size=args[0], patch_size=4, embed_dim=args[2], in_chans=args[3], out_chans=args[4],
+                    window_size=args[5])
+        else:
+            if m in _WIDTH_SCALED or m is DWConv:
+                c1, c2 = ch[f], args[0]
+                c2 = make_divisible(c2 * gw, 8) if c2 != no else c2
+                args = [c1, c2, *args[1:]]
+                if m is C3:
+                    args.insert(2, n)
+                    n = 1
+            elif m is nn.BatchNorm2d:
+                args = [ch[f]]
+            elif m is Concat:
+                c2 = sum(ch[j] for j in f)
+            elif m is Detect:
+                args.append([ch[j] for j in f])
+                if isinstance(args[1], int):
+                    args[1] = [list(range(args[1] * 2))] * len(f)
+            else:
+                c2 = ch[f if f < 0 else f + 1]
+            mod = nn.Sequential(*(m(*args) for _ in range(n))) if n > 1 else m(*args)
+        mod.i, mod.f = i, f
+        mod.type = f"{m.__module__}.{m.__name__}" if hasattr(m, "__name__") else str(m)
+        mod.np = sum(p.numel() for p in mod.parameters())
+        save.extend(j % (i + 0.00001) for j in ([f] if isinstance(f, int) else f) if j != -1)
+        layers.append(mod)
+        ch.append(c2)
+    if string == "backbone":
+        return layers[0], sorted(save)
+    return nn.Sequential(*layers), sorted(save)
+
+
+def fuse_conv_and_bn(conv, bn):
+    """Folds an eval-mode BatchNorm into the preceding conv (reference utils/torch_utils.py:182)."""
+    fused = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
+                      groups=conv.groups, bias=True).requires_grad_(False).to(conv.weight.device, conv.weight.dtype)
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    fused.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
+    b = conv.bias if conv.bias is not None else torch.zeros_like(bn.running_mean)
+    fused.bias.copy_((b - bn.running_mean) * scale + bn.bias)
+    return fused
+
+
+class Model(nn.Module):
+    """The RGB+IR detector: ImageEncoderViT backbone + YOLOv5 head (reference model.py:73-348)."""
+    export = False
+
+    def __init__(self, cfg="yolov5s.yaml", input_mode="RGB", ch_steam=3, ch=3, nc=None, anchors=None, config=None,
+                 sr=False, factor=2):
+        super().__init__()
+        self.init_params = dict(cfg=cfg, input_mode=input_mode, ch_steam=ch_steam, ch=ch, nc=nc, anchors=anchors,
+                                config=config, sr=sr, factor=factor)
+        if isinstance(cfg, dict):
+            self.yaml = cfg
+        else:
+            import yaml
+            self.yaml_file = Path(cfg).name
+            with open(cfg) as f:
+                self.yaml = yaml.safe_load(f)
+        if sr:
+            raise NotImplementedError("the super-resolution training branch is out of scope")
+        self.sr = False
+        ch = self.yaml["ch"] = self.yaml.get("ch", ch)
+        if nc and nc != self.yaml["nc"]:
+            self.yaml["nc"] = nc
+        if anchors:
+            self.yaml["anchors"] = round(anchors)
+        self.image_encoder, self.save1 = parse_model(deepcopy(self.yaml), "backbone", ch=[ch], config=config)
+        self.detect, self.save2 = parse_model(deepcopy(self.yaml), "head", ch=[ch], config=config)
+        det = self.detect[-1]
+        if isinstance(det, Detect):
+            det.stride = torch.tensor([4.0])             # hard-coded in the reference (model.py:130)
+            det.anchors /= det.stride.view(-1, 1, 1)
+            area = det.anchor_grid.prod(-1).view(-1)     # check_anchor_order (utils/autoanchor.py:13)
+            if (area[-1] - area[0]).sign() != (det.stride[-1] - det.stride[0]).sign():
+                det.anchors[:] = det.anchors.flip(0)
+                det.anchor_grid[:] = det.anchor_grid.flip(0)
+            self.stride = det.stride
+            self._initialize_biases()
+        for m in self.modules():                         # initialize_weights (utils/torch_utils.py:145)
+            if type(m) is nn.BatchNorm2d:
+                m.eps, m.momentum = 1e-3, 0.03
+
+    def _initialize_biases(self, cf=None):
+        det = self.detect[-1]
+        for conv, s in zip(det.m, det.stride):
+            b = conv.bias.view(det.na, -1)
+            b.data[:, 4] += math.log(8 / (640 / s) ** 2)
+            b.data[:, 5:] += math.log(0.6 / (det.nc - 0.99)) if cf is None else torch.log(cf / cf.sum())
+            conv.bias = nn.Parameter(b.view(-1), requires_grad=True)
+
+    def _stem(self, x, ir, input_mode):
+        if input_mode == "RGB+IR":
+            return torch.cat((x, ir[:, 0:1]), 1)
+        if input_mode == "RGB":
+            return x
+        if input_mode == "IR":
+            return ir
+        raise NotImplementedError(f"input_mode {input_mode!r} is out of scope")
+
+    def forward(self, x, ir=None, input_mode="RGB+IR", augment=False, profile=False):
+        if augment:
+            raise NotImplementedError("test-time augmentation is out of scope")
+        if ir is None:
+            ir = x
+        head_out, feats = self.forward_once(self._stem(x, ir, input_mode), "yolo", profile)
+        self.training |= self.export
+        if self.training:
+            return head_out, feats
+        return head_out[0], head_out[1], feats
+
+    def forward_once(self, x, string="yolo", profile=False):
+        y = list(self.image_encoder(x))
+        for m in self.detect:
+            if m.f != -1:
+                x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            x = m(x)
+            y.append(x)
+        return x, y
+
+    def fuse(self):
+        for m in self.modules():
+            if type(m) is Conv and hasattr(m, "bn"):
+                m.conv = fuse_conv_and_bn(m.conv, m.bn)
+                delattr(m, "bn")
+                m.forward = m.fuseforward
+        return self
+
+    def info(self, verbose=False, img_size=640):
+        n = sum(p.numel() for p in self.parameters())
+        logger.info("Model: %d layers, %d parameters", len(list(self.modules())), n)

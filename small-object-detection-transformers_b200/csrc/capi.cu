@@ -1,0 +1,45 @@
+// C-ABI entry points that only validate and dispatch (see include/sodt_b200.h), plus library bookkeeping.
+#include "common.cuh"
+
+namespace sodt {
+
+thread_local long long g_launches = 0;
+thread_local cudaError_t g_last_cuda_error = cudaSuccess;
+
+int window_attn_generic(const void* qkv, const float* table, const void* pad_qkv, void* out, int B, int H, int W,
+                        int C, int heads, int ws, int shift, int dtype, float scale, float mask_value,
+                        cudaStream_t stream);
+
+}  // namespace sodt
+
+extern "C" int sodt_version(void) { return 100; }
+extern "C" int sodt_built_for_sm(void) { return 100; }
+
+extern "C" const char* sodt_status_string(int status) {
+    switch (status) {
+        case SODT_OK: return "ok";
+        case SODT_ERR_INVALID_ARG: return "invalid argument";
+        case SODT_ERR_UNSUPPORTED: return "unsupported shape";
+        case SODT_ERR_WORKSPACE: return "workspace missing, misaligned or too small";
+        case SODT_ERR_CUDA: return "CUDA error";
+        case SODT_ERR_ALIGNMENT: return "pointer not 16-byte aligned";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char* sodt_last_cuda_error(void) { return cudaGetErrorString(sodt::g_last_cuda_error); }
+extern "C" long long sodt_launch_count(void) { return sodt::g_launches; }
+extern "C" void sodt_reset_launch_count(void) { sodt::g_launches = 0; }
+
+extern "C" int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
+                                    int B, int H, int W, int C, int heads, int ws, int shift,
+                                    int dtype, float scale, float mask_value, void* stream) {
+    using namespace sodt;
+    if (!qkv || !bias_table || !out) return SODT_ERR_INVALID_ARG;
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0) return SODT_ERR_INVALID_ARG;
+    if (shift < 0 || shift >= ws) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_F32 && dtype != SODT_BF16) return SODT_ERR_INVALID_ARG;
+    if (!aligned16(qkv) || !aligned16(out) || (pad_qkv && !aligned16(pad_qkv))) return SODT_ERR_ALIGNMENT;
+    return window_attn_generic(qkv, bias_table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value,
+                               static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,85 @@
+// YOLOv5 Detect decode: one HBM pass.  Reads the 1x1-conv output once (NCHW or channels_last,
+// through strides), transposes through shared memory and writes fully coalesced rows of the
+// decoded prediction tensor z (fp32) and, optionally, the permuted raw tensor.
+//
+// Reference: Detect.forward basics/models/model.py:55-64, _make_grid :67-70.
+// Decode is fp32 regardless of the activation dtype: box centres reach >1000 px and the
+// 1e-3 px-relative budget does not survive bf16.
+#include "common.cuh"
+
+namespace sodt {
+namespace {
+
+constexpr int XT = 64;
+constexpr int THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+detect_decode_kernel(const T* __restrict__ raw, long long sb, long long sc, long long sy, long long sx,
+                     const float* __restrict__ anchors_px, float* __restrict__ z, T* __restrict__ x_perm,
+                     int na, int no, int ny, int nx, float stride, long long rows_total, long long row_offset) {
+    extern __shared__ float tile[];  // [na*no][XT+1]
+    const int CH = na * no;
+    const int x0 = blockIdx.x * XT;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    const int xt = min(XT, nx - x0);
+    const T* src = raw + b * sb + y * sy;
+    if (sx == 1) {
+        for (int e = threadIdx.x; e < CH * XT; e += THREADS) {
+            const int c = e / XT, xl = e - c * XT;
+            if (xl < xt) tile[c * (XT + 1) + xl] = to_f32<T>(src[c * sc + (x0 + xl)]);
+        }
+    } else {
+        for (int e = threadIdx.x; e < CH * xt; e += THREADS) {
+            const int xl = e / CH, c = e - xl * CH;
+            tile[c * (XT + 1) + xl] = to_f32<T>(src[c * sc + (x0 + xl) * sx]);
+        }
+    }
+    __syncthreads();
+    const int run = xt * no;
+    for (int a = 0; a < na; ++a) {
+        const long long row0 = ((long long)a * ny + y) * nx + x0;
+        float* zdst = z + ((long long)b * rows_total + row_offset + row0) * no;
+        T* xdst = x_perm ? x_perm + (((long long)b * na + a) * ny * nx + (long long)y * nx + x0) * no : nullptr;
+        const float aw = anchors_px[2 * a], ah = anchors_px[2 * a + 1];
+        for (int e = threadIdx.x; e < run; e += THREADS) {
+            const int xl = e / no, o = e - xl * no;
+            const float v = tile[(a * no + o) * (XT + 1) + xl];
+            const float s = 1.f / (1.f + expf(-v));
+            float r;
+            if (o == 0) r = (s * 2.f - 0.5f + (float)(x0 + xl)) * stride;
+            else if (o == 1) r = (s * 2.f - 0.5f + (float)y) * stride;
+            else if (o == 2) { const float t = s * 2.f; r = t * t * aw; }
+            else if (o == 3) { const float t = s * 2.f; r = t * t * ah; }
+            else r = s;
+            zdst[e] = r;
+            if (xdst) xdst[e] = from_f32<T>(v);
+        }
+    }
+}
+
+}  // namespace
+}  // namespace sodt
+
+extern "C" int sodt_detect_decode(const void* raw, long long sb, long long sc, long long sy, long long sx,
+                                  const float* anchors_px, float* z, void* x_perm,
+                                  int B, int na, int no, int ny, int nx, float stride,
+                                  long long rows_total, long long row_offset, int dtype, void* stream) {
+    using namespace sodt;
+    if (!raw || !anchors_px || !z) return SODT_ERR_INVALID_ARG;
+    if (B <= 0 || na <= 0 || no < 5 || ny <= 0 || nx <= 0) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_F32 && dtype != SODT_BF16) return SODT_ERR_INVALID_ARG;
+    if (ny > 65535 || B > 65535) return SODT_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)na * no * (XT + 1) * sizeof(float);
+    if (smem > 48 * 1024) return SODT_ERR_UNSUPPORTED;
+    dim3 grid((nx + XT - 1) / XT, ny, B);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == SODT_F32)
+        detect_decode_kernel<float><<<grid, THREADS, smem, s>>>(static_cast<const float*>(raw), sb, sc, sy, sx, anchors_px, z,
+                                                               static_cast<float*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
+    else
+        detect_decode_kernel<__nv_bfloat16><<<grid, THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx, anchors_px, z,
+                                                                       static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
+    return check_launch();
+}

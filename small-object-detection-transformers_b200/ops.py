@@ -1,0 +1,210 @@
+"""Tensor-level wrappers around the C ABI (include/sodt_b200.h).
+
+Each function validates shapes / dtypes / devices, allocates the output with torch (the
+kernels never allocate), and enqueues the kernels on ``torch.cuda.current_stream()``.
+The same functions are registered as ``torch.ops.sodt.*`` custom ops (with fake-tensor
+shape functions) so that the modules stay traceable.  No CPU path exists.
+"""
+import math
+
+import torch
+
+from . import _capi
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _capi.SodtError("sodt_b200 ops run on CUDA tensors only (there is no CPU fallback)")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def launch_count():
+    return _capi.lib().sodt_launch_count()
+
+
+def reset_launch_count():
+    _capi.lib().sodt_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------ window attention
+def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=None, mask_value=-100.0):
+    """qkv [B,H,W,3C] (f32 / bf16) -> [B,H,W,C].  See sodt_window_attn_fwd."""
+    _require_cuda(qkv, bias_table, pad_qkv)
+    if qkv.dim() != 4 or qkv.shape[-1] % 3:
+        raise ValueError("qkv must be [B, H, W, 3*C]")
+    if qkv.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {qkv.dtype}")
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    if C % heads:
+        raise ValueError("C must be divisible by heads")
+    span = (2 * ws - 1) ** 2
+    if tuple(bias_table.shape) != (span, heads):
+        raise ValueError(f"bias_table must be [{span}, {heads}], got {tuple(bias_table.shape)}")
+    qkv = qkv.contiguous()
+    table = bias_table.detach().to(torch.float32).contiguous()
+    if pad_qkv is not None:
+        pad_qkv = pad_qkv.detach().to(qkv.dtype).contiguous()
+        if pad_qkv.numel() != C3:
+            raise ValueError("pad_qkv must have 3*C elements")
+    out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
+    if scale is None:
+        scale = (C // heads) ** -0.5
+    with torch.cuda.device(qkv.device):
+        st = _capi.lib().sodt_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), _ptr(pad_qkv), out.data_ptr(),
+                                              B, H, W, C, heads, ws, shift, _DT[qkv.dtype], float(scale),
+                                              float(mask_value), _stream())
+    _capi.check(st, "sodt_window_attn_fwd")
+    return out
+
+
+# ------------------------------------------------------------------------- cross-channel block
+def cattn_block(r, g, b, ir, ln_w, ln_b, heads, ws=1, shift=0, eps=1e-5, mask_value=-100.0):
+    """Four streams [B,h,w,C] (any common strides) -> [B,h,w,4C].  ln_w / ln_b: [4,C].
+    See sodt_cattn_block_fwd."""
+    _require_cuda(r, g, b, ir, ln_w, ln_b)
+    streams = [r, g, b, ir]
+    if any(t.shape != r.shape or t.dtype != r.dtype for t in streams) or r.dim() != 4:
+        raise ValueError("the four streams must share shape [B,h,w,C] and dtype")
+    if r.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {r.dtype}")
+    if any(t.stride() != r.stride() for t in streams):
+        streams = [t.contiguous() for t in streams]
+    B, h, w, C = r.shape
+    sb, sy, sx, sc = streams[0].stride()
+    ln_w = ln_w.detach().to(torch.float32).contiguous()
+    ln_b = ln_b.detach().to(torch.float32).contiguous()
+    if ln_w.numel() != 4 * C or ln_b.numel() != 4 * C:
+        raise ValueError("ln_w / ln_b must be [4, C]")
+    out = torch.empty((B, h, w, 4 * C), dtype=r.dtype, device=r.device)
+    with torch.cuda.device(r.device):
+        st = _capi.lib().sodt_cattn_block_fwd(streams[0].data_ptr(), streams[1].data_ptr(), streams[2].data_ptr(),
+                                              streams[3].data_ptr(), sb, sy, sx, sc, ln_w.data_ptr(), ln_b.data_ptr(),
+                                              out.data_ptr(), B, h, w, C, heads, ws, shift, float(eps),
+                                              float(mask_value), _DT[r.dtype], _stream())
+    _capi.check(st, "sodt_cattn_block_fwd")
+    return out
+
+
+# --------------------------------------------------------------------------------- Detect decode
+def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=None, row_offset=0):
+    """raw [B, na*no, ny, nx] (any strides) -> (z [B, na*ny*nx, no] fp32, x_perm [B,na,ny,nx,no] or None)."""
+    _require_cuda(raw, anchors_px, z)
+    if raw.dim() != 4 or raw.dtype not in _DT:
+        raise ValueError("raw must be a 4-D f32 / bf16 tensor")
+    B, ch, ny, nx = raw.shape
+    anchors_px = anchors_px.detach().to(torch.float32).reshape(-1, 2).contiguous()
+    na = anchors_px.shape[0]
+    if ch % na:
+        raise ValueError("channels must be divisible by the number of anchors")
+    no = ch // na
+    rows = na * ny * nx
+    if z is None:
+        rows_total = rows
+        z = torch.empty((B, rows, no), dtype=torch.float32, device=raw.device)
+    elif rows_total is None:
+        rows_total = z.shape[1]
+    xp = torch.empty((B, na, ny, nx, no), dtype=raw.dtype, device=raw.device) if want_perm else None
+    sb, sc, sy, sx = raw.stride()
+    with torch.cuda.device(raw.device):
+        st = _capi.lib().sodt_detect_decode(raw.data_ptr(), sb, sc, sy, sx, anchors_px.data_ptr(), z.data_ptr(), _ptr(xp),
+                                            B, na, no, ny, nx, float(stride), rows_total, row_offset, _DT[raw.dtype],
+                                            _stream())
+    _capi.check(st, "sodt_detect_decode")
+    return z, xp
+
+
+# ------------------------------------------------------------------------------------------- NMS
+_workspaces = {}
+
+
+def _nms_workspace(device, B, R, nc, multi_label):
+    need = _capi.lib().sodt_nms_workspace_bytes(B, R, nc, int(multi_label))
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def nms(pred, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, merge=True,
+        redundant=True, max_det=300, max_nms=30000, max_wh=4096.0, out=None, counts=None, want_keep_idx=False):
+    """pred [B,R,5+nc] fp32 -> (out [B,max_det,6] fp32, counts [B] int32, keep_idx [B,max_det] int32 | None).
+    ``out`` / ``counts`` may be caller-provided (e.g. slices of a communication buffer)."""
+    _require_cuda(pred, out, counts)
+    if pred.dim() != 3 or pred.shape[2] < 6 or pred.dtype != torch.float32:
+        raise ValueError("pred must be fp32 [B, R, 5+nc] with nc >= 1")
+    pred = pred.contiguous()
+    B, R, no = pred.shape
+    nc = no - 5
+    dev = pred.device
+    if out is None:
+        out = torch.empty((B, max_det, 6), dtype=torch.float32, device=dev)
+    if counts is None:
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+    if not (out.is_contiguous() and counts.is_contiguous()) or out.dtype != torch.float32 or counts.dtype != torch.int32:
+        raise ValueError("out must be contiguous fp32 [B,max_det,6] and counts contiguous int32 [B]")
+    keep = torch.empty((B, max_det), dtype=torch.int32, device=dev) if want_keep_idx else None
+    cls_t = None
+    if classes is not None:
+        cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=dev)
+    ws = _nms_workspace(dev, B, R, nc, multi_label)
+    with torch.cuda.device(dev):
+        st = _capi.lib().sodt_nms(pred.data_ptr(), _ptr(cls_t), 0 if cls_t is None else cls_t.numel(), out.data_ptr(),
+                                  counts.data_ptr(), _ptr(keep), ws.data_ptr(), ws.numel(), B, R, nc, float(conf_thres),
+                                  float(iou_thres), int(bool(multi_label)), int(bool(agnostic)), int(bool(merge)),
+                                  int(bool(redundant)), max_det, max_nms, float(max_wh), _stream())
+    _capi.check(st, "sodt_nms")
+    return out, counts, keep
+
+
+# ---------------------------------------------------------------------------- torch.ops.sodt.*
+def _register_custom_ops():
+    lib = torch.library
+
+    @lib.custom_op("sodt::window_attn_fwd", mutates_args=())
+    def window_attn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, pad_qkv: torch.Tensor, heads: int, ws: int,
+                        shift: int, scale: float, mask_value: float) -> torch.Tensor:
+        return window_attention(qkv, bias_table, heads, ws, shift, pad_qkv, scale, mask_value)
+
+    @window_attn_fwd.register_fake
+    def _(qkv, bias_table, pad_qkv, heads, ws, shift, scale, mask_value):
+        B, H, W, C3 = qkv.shape
+        return qkv.new_empty((B, H, W, C3 // 3))
+
+    @lib.custom_op("sodt::cattn_block_fwd", mutates_args=())
+    def cattn_block_fwd(r: torch.Tensor, g: torch.Tensor, b: torch.Tensor, ir: torch.Tensor, ln_w: torch.Tensor,
+                        ln_b: torch.Tensor, heads: int, ws: int, shift: int, eps: float) -> torch.Tensor:
+        return cattn_block(r, g, b, ir, ln_w, ln_b, heads, ws, shift, eps)
+
+    @cattn_block_fwd.register_fake
+    def _(r, g, b, ir, ln_w, ln_b, heads, ws, shift, eps):
+        B, h, w, C = r.shape
+        return r.new_empty((B, h, w, 4 * C))
+
+    @lib.custom_op("sodt::detect_decode", mutates_args=())
+    def detect_decode_op(raw: torch.Tensor, anchors_px: torch.Tensor, stride: float) -> torch.Tensor:
+        return detect_decode(raw, anchors_px, stride, want_perm=False)[0]
+
+    @detect_decode_op.register_fake
+    def _(raw, anchors_px, stride):
+        B, ch, ny, nx = raw.shape
+        na = anchors_px.numel() // 2
+        return raw.new_empty((B, na * ny * nx, ch // na), dtype=torch.float32)
+
+
+try:  # registration is idempotent per process; a second import of this module must not fail
+    _register_custom_ops()
+except RuntimeError:
+    pass

@@ -1,0 +1,371 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): attention / fusion outputs rel. error <= 1e-5 in fp32 mode,
+<= 2e-2 in bf16 mode (bf16 kernel vs the fp32/fp64 oracle); box coordinates <= 1e-3 px-relative;
+NMS kept-index sets bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_ref as A
+from oracle import fixtures as fx
+from oracle import model_ref, nms_ref
+from oracle.detect_ref import detect_decode as detect_oracle
+from tests.golden_cases import (CATTN_CASES, DETECT_ANCHORS, DETECT_FEATS, DETECT_STRIDES, NMS_CASES, SWIN_CASES,
+                                swin_state_shapes)
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+YAML = os.path.join(ROOT, "small-object-detection-transformers_b200", "models", "model.yaml")
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
+
+
+@pytest.fixture(scope="module", autouse=True)
+def exact_fp32_libraries():
+    """fp32 parity mode: cuBLAS / cuDNN must not silently use TF32."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def ops():
+    from sodt_b200 import ops as o
+    return o
+
+
+# --------------------------------------------------------------------------- window attention op
+# (B, H, W, C, heads, ws, shift, use_pad_bias)
+WINDOW_CASES = [
+    (2, 16, 16, 192, 12, 8, 0, False),    # stage-1 geometry, hd 16
+    (2, 16, 16, 192, 12, 8, 2, False),
+    (1, 32, 24, 384, 12, 8, 2, False),    # stage-2 geometry, hd 32, rectangular
+    (1, 32, 32, 128, 2, 32, 0, False),    # stage-3 geometry, hd 64, N = 1024
+    (2, 12, 12, 48, 3, 8, 2, True),       # padding + shift, pad tokens carry the qkv bias
+    (1, 10, 12, 48, 3, 8, 0, True),
+    (1, 14, 14, 48, 3, 7, 3, False),      # N = 49
+    (2, 8, 12, 32, 4, 4, 1, False),       # hd 8, N = 16
+    (1, 16, 16, 128, 2, 16, 5, False),    # N = 256 with a shift
+    (1, 9, 9, 40, 2, 3, 1, False),        # hd 20 (not a power of two), N = 9
+    (3, 8, 8, 24, 4, 8, 0, False),        # hd 6
+    (1, 64, 64, 192, 12, 8, 4, False),    # shift = ws/2 (swinv2-style)
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", WINDOW_CASES)
+def test_window_attention_vs_oracle(case, dtype):
+    B, H, W, C, heads, ws, shift, pad = case
+    qkv = fx.det_input(f"wa:{case}", (B, H, W, 3 * C))
+    table = 0.5 * fx.det_input(f"wa_table:{case}", ((2 * ws - 1) ** 2, heads))
+    pad_qkv = 0.3 * fx.det_input(f"wa_pad:{case}", (3 * C,)) if pad else None
+    q_dev = qkv.to("cuda", dtype)
+    pad_dev = None if pad_qkv is None else pad_qkv.to("cuda", dtype)
+    out = ops().window_attention(q_dev, table.cuda(), heads, ws, shift, pad_qkv=pad_dev)
+    assert out.shape == (B, H, W, C) and out.dtype == dtype
+    # the oracle sees exactly the values the kernel sees (bf16-rounded inputs in bf16 mode)
+    ref = A.attention_on_qkv_image(q_dev.float().cpu(), table, heads, ws, shift,
+                                   pad_qkv=None if pad_dev is None else pad_dev.float().cpu())
+    assert rel_err(out, ref) < TOL[dtype]
+    if dtype == torch.float32:
+        assert (out.double().cpu() - ref).abs().max() < 5e-5
+
+
+def test_window_attention_rejects_bad_arguments():
+    from sodt_b200._capi import SodtError
+    q = torch.zeros(1, 8, 8, 96, device="cuda")
+    with pytest.raises(ValueError):
+        ops().window_attention(q, torch.zeros(10, 2, device="cuda"), 2, 8)
+    with pytest.raises(SodtError):   # shift >= ws
+        ops().window_attention(q, torch.zeros(225, 2, device="cuda"), 2, 8, shift=8)
+    with pytest.raises(SodtError):   # head_dim 96 > 64 -> unsupported
+        ops().window_attention(torch.zeros(1, 8, 8, 288, device="cuda"), torch.zeros(225, 1, device="cuda"), 1, 8)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_window_attention_full_size_properties(dtype):
+    """BASELINE config-2 stage-1 geometry (256x256 tokens, C=192, 12 heads, ws 8, shift 2), batch 2:
+    size-independent properties instead of an oracle run."""
+    B, H, W, C, heads, ws, shift = 2, 256, 256, 192, 12, 8, 2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = torch.randn(B, H, W, 3 * C, device="cuda", generator=g).to(dtype)
+    table = (0.5 * torch.randn((2 * ws - 1) ** 2, heads, device="cuda", generator=g))
+    # (1) softmax rows sum to one: constant v gives constant output
+    q1 = qkv.clone()
+    q1[..., 2 * C:] = 0.75
+    o1 = ops().window_attention(q1, table, heads, ws, shift)
+    assert (o1.float() - 0.75).abs().max() < (1e-5 if dtype == torch.float32 else 8e-3)
+    # (2) linear in v
+    qa, qb = qkv.clone(), qkv.clone()
+    qb[..., 2 * C:] = torch.randn(B, H, W, C, device="cuda", generator=g).to(dtype)
+    qs = qkv.clone()
+    qs[..., 2 * C:] = (qa[..., 2 * C:].float() + qb[..., 2 * C:].float()).to(dtype)
+    oa, ob, os_ = (ops().window_attention(t, table, heads, ws, shift).float() for t in (qa, qb, qs))
+    assert ((oa + ob - os_).norm() / os_.norm()).item() < (1e-5 if dtype == torch.float32 else 2e-2)
+    # (3) translating the image by whole windows (cyclically) translates the output when shift == 0
+    o0 = ops().window_attention(qkv, table, heads, ws, 0)
+    o0r = ops().window_attention(torch.roll(qkv, (ws, 2 * ws), (1, 2)), table, heads, ws, 0)
+    assert torch.equal(torch.roll(o0, (ws, 2 * ws), (1, 2)), o0r)
+    # (4) a sampled window against the oracle: with shift == 0 windows are independent crops
+    crop = qkv[:1, 40:48, 80:88].float().cpu()
+    ref = A.attention_on_qkv_image(crop, table.cpu(), heads, ws, 0)
+    assert rel_err(o0[:1, 40:48, 80:88], ref) < TOL[dtype]
+
+
+# ------------------------------------------------------------------------------------ swin block
+def swin_params(name):
+    dim, res, heads, ws, shift, lin, B = SWIN_CASES[name]
+    return {k: fx.deterministic_tensor(k, s, seed=1) for k, s in swin_state_shapes(dim, ws, lin, heads, res).items()}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", list(SWIN_CASES))
+def test_swin_block_module_vs_reference_golden(golden, name, dtype):
+    from sodt_b200.basics.models.backbone_vit import SwinTransformerBlock
+    dim, res, heads, ws, shift, lin, B = SWIN_CASES[name]
+    blk = SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift, linear_mlp=lin).eval()
+    missing = blk.load_state_dict(swin_params(name), strict=False)
+    assert set(missing.missing_keys) <= {"attn_mask", "attn.relative_position_index"} and not missing.unexpected_keys
+    blk = blk.to("cuda", dtype)
+    x = fx.det_input("swin:" + name, (B, res[0] * res[1], dim)).to("cuda", dtype)
+    with torch.no_grad():
+        y = blk(x)
+    assert rel_err(y, golden("swin_blocks")[name + "/y"]) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+# ------------------------------------------------------------------------- cross-channel block
+@pytest.mark.parametrize("layout", ["nhwc", "nchw_view"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", list(CATTN_CASES))
+def test_cattn_block_vs_reference_golden(golden, name, dtype, layout):
+    variant, C, heads, hw, ws, B = CATTN_CASES[name]
+    g = golden("cattn")
+    streams = [fx.det_input(f"cattn:{name}:{i}", (B, hw[0], hw[1], C)).to("cuda", dtype) for i in range(4)]
+    if layout == "nchw_view":   # what PatchEmbed.forward hands over: a permuted view of NCHW memory
+        streams = [s.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1) for s in streams]
+    ln_w = torch.stack([fx.deterministic_tensor(f"norm{i}.weight", (C,), seed=2) for i in range(1, 5)]).cuda()
+    ln_b = torch.stack([fx.deterministic_tensor(f"norm{i}.bias", (C,), seed=2) for i in range(1, 5)]).cuda()
+    shift = 1 if variant == "vit_shift1" else 0
+    out = ops().cattn_block(*streams, ln_w, ln_b, heads, ws=ws, shift=shift)
+    assert out.shape == (B, hw[0], hw[1], 4 * C)
+    for i, y in enumerate(torch.split(out, C, dim=-1)):
+        ref = g[f"{name}/y{i}"]
+        if hw[0] > 64:
+            y = y[:, ::5, ::3]
+        assert rel_err(y, ref) < TOL[dtype], (name, i)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C,heads,ws,shift", [(48, 12, 4, 2), (24, 3, 2, 1), (96, 6, 8, 3), (48, 4, 3, 1), (40, 5, 1, 0)])
+def test_cattn_block_shifted_vs_oracle(C, heads, ws, shift, dtype):
+    """Masked / shifted general-window path (never exercised by the shipped model, part of the contract)."""
+    B, h, w = 2, 16, 12
+    streams = [fx.det_input(f"cattn_s:{C}:{ws}:{i}", (B, h, w, C)).to("cuda", dtype) for i in range(4)]
+    ln_w = 1.0 + 0.1 * fx.det_input("cattn_s:w", (4, C))
+    ln_b = 0.1 * fx.det_input("cattn_s:b", (4, C))
+    out = ops().cattn_block(*streams, ln_w.cuda(), ln_b.cuda(), heads, ws=ws, shift=shift)
+    ref = torch.cat(A.cattention_block([s.float().cpu() for s in streams], list(ln_w), list(ln_b), heads, ws, shift), -1)
+    assert rel_err(out, ref) < TOL[dtype]
+
+
+# ---------------------------------------------------------------------------------------- Detect
+@pytest.mark.parametrize("memory_format", ["nchw", "channels_last"])
+def test_detect_module_vs_reference_golden(golden, memory_format):
+    from sodt_b200.basics.models.model import Detect
+    g = golden("detect")
+    det = Detect(nc=8, anchors=DETECT_ANCHORS, ch=(16, 24)).eval()
+    det.stride = torch.tensor(DETECT_STRIDES)
+    sd = {k: fx.deterministic_tensor(k, v.shape, seed=3) for k, v in det.state_dict().items() if k.startswith("m.")}
+    det.load_state_dict(sd, strict=False)
+    det = det.cuda()
+    feats = [fx.det_input(f"detect:{i}", s).cuda() for i, s in enumerate(DETECT_FEATS)]
+    if memory_format == "channels_last":
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in feats]
+    with torch.no_grad():
+        z, xs = det(feats)
+    ref = torch.from_numpy(g["z"]).double()
+    zc = z.double().cpu()
+    assert ((zc[..., :4] - ref[..., :4]).abs() / ref[..., :4].abs().clamp_min(1.0)).max() < 1e-3 * 1e-2
+    assert (zc[..., 4:] - ref[..., 4:]).abs().max() < 1e-5
+    for i, x in enumerate(xs):
+        assert rel_err(x, g[f"x{i}"]) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_detect_decode_full_size_vs_oracle(dtype):
+    """BASELINE config 5 decode geometry: 256x256 cells, 3 anchors, 13 outputs."""
+    raw = fx.det_input("detect_big", (2, 39, 256, 256)).to("cuda", dtype)
+    anchors = torch.tensor(DETECT_ANCHORS[0], dtype=torch.float32).reshape(-1, 2)
+    z, xp = ops().detect_decode(raw, anchors.cuda(), 4.0)
+    zr, xr = detect_oracle(raw.float().cpu(), anchors, 4.0)
+    zc = z.double().cpu()
+    assert ((zc[..., :4] - zr[..., :4]).abs() / zr[..., :4].abs().clamp_min(1.0)).max() < 1e-5
+    assert (zc[..., 4:] - zr[..., 4:]).abs().max() < 1e-6
+    assert torch.equal(xp.float().cpu(), xr.float())
+
+
+# ------------------------------------------------------------------------------------------- NMS
+def run_cuda_nms(pred_np, kw):
+    pred = torch.from_numpy(pred_np).cuda()
+    det, counts, keep = ops().nms(pred, want_keep_idx=True, **kw)
+    torch.cuda.synchronize()
+    return det.cpu().numpy(), counts.cpu().numpy(), keep.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", list(NMS_CASES))
+def test_nms_vs_reference_golden_and_oracle(golden, name):
+    B, R, img, active, seed, kw = NMS_CASES[name]
+    g = golden("nms")
+    pred = fx.synthetic_predictions(B, R, 8, img, active, seed)
+    det, counts, keep = run_cuda_nms(pred, kw)
+    outs, idxs = nms_ref.non_max_suppression(pred, return_indices=True, early_stop=True, **kw)
+    assert np.array_equal(counts, g[name + "/count"])
+    for i in range(B):
+        n = int(counts[i])
+        assert np.array_equal(keep[i, :n], idxs[i]), "kept-index set must be bit-exact"
+        assert np.all(keep[i, n:] == -1)
+        ref = g[name + "/det"][i, :n]
+        assert np.array_equal(det[i, :n, 4:], ref[:, 4:])           # confidence and class: bit-exact
+        assert np.abs(det[i, :n, :4] - ref[:, :4]).max(initial=0.0) < 1e-3
+        assert np.all(det[i, n:] == 0)
+
+
+@pytest.mark.parametrize("seed,R,img,active,kw", [
+    (11, 20000, 512, 0.3, dict(conf_thres=0.25, iou_thres=0.45)),
+    (12, 20000, 160, 0.5, dict(conf_thres=0.3, iou_thres=0.5)),                       # heavy overlap, many chunks
+    (13, 6000, 512, 0.1, dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)),
+    (14, 3000, 64, 1.0, dict(conf_thres=0.5, iou_thres=0.2, agnostic=True)),          # extreme overlap
+    (15, 1000, 300, 1.0, dict(conf_thres=0.01, iou_thres=0.45, multi_label=True, classes=[0, 3, 7])),
+])
+def test_nms_random_vs_oracle(seed, R, img, active, kw):
+    pred = fx.synthetic_predictions(2, R, 8, img, active, seed)
+    det, counts, keep = run_cuda_nms(pred, kw)
+    outs, idxs = nms_ref.non_max_suppression(pred, return_indices=True, early_stop=True, **kw)
+    for i in range(2):
+        n = int(counts[i])
+        assert n == len(idxs[i])
+        assert np.array_equal(keep[i, :n], idxs[i])
+        assert np.array_equal(det[i, :n, 4:], outs[i][:, 4:])
+        assert np.abs(det[i, :n, :4] - outs[i][:, :4]).max(initial=0.0) < 1e-3
+
+
+def test_nms_ties_and_degenerate_boxes_vs_oracle():
+    """Equal scores (stable order), duplicate boxes, zero-area boxes (NaN IoU keeps both)."""
+    r = np.random.RandomState(5)
+    R = 1500
+    pred = np.zeros((1, R, 6), dtype=np.float32)   # nc = 1
+    pred[0, :, 0:2] = r.uniform(20, 80, size=(R, 2))
+    pred[0, :, 2:4] = r.uniform(0, 30, size=(R, 2))
+    pred[0, :, 4] = np.round(r.uniform(0.3, 1.0, size=R) * 16) / 16   # many exact ties
+    pred[0, :, 5] = 1.0
+    pred[0, ::9, :4] = pred[0, 1::9, :4][: pred[0, ::9].shape[0]]      # duplicates
+    pred[0, ::13, 2:4] = 0.0                                           # zero area
+    kw = dict(conf_thres=0.25, iou_thres=0.5)
+    det, counts, keep = run_cuda_nms(pred, kw)
+    outs, idxs = nms_ref.non_max_suppression(pred, return_indices=True, **kw)
+    n = int(counts[0])
+    assert n == len(idxs[0]) and np.array_equal(keep[0, :n], idxs[0])
+
+
+def test_nms_core_vs_torchvision_cuda():
+    """The suppression core against the third-party kernel the reference actually calls on a GPU
+    (torchvision.ops.nms, general.py:496), fed the same class-offset boxes and scores."""
+    tv = pytest.importorskip("torchvision")
+    pred = fx.synthetic_predictions(1, 8000, 8, 200, 0.6, 21)
+    kw = dict(conf_thres=0.25, iou_thres=0.45)
+    x = nms_ref.candidates(pred[0], 0.25, False)
+    boxes = torch.from_numpy(x[:, :4] + x[:, 5:6] * np.float32(4096)).cuda()
+    scores = torch.from_numpy(x[:, 4]).cuda()
+    ref_keep = tv.ops.nms(boxes, scores, 0.45)[:300].cpu().numpy()
+    pred_t = torch.from_numpy(pred).cuda()
+    det, counts, keep = ops().nms(pred_t, merge=False, want_keep_idx=True, **kw)
+    n = int(counts[0])
+    assert np.array_equal(keep[0, :n].cpu().numpy(), ref_keep)
+
+
+def test_nms_full_size_batch_consistency():
+    """BASELINE config 5: 196,608 rows per image.  Every image of a batch must equal the same
+    image run alone (batch-independence), at both operating points; first image vs the oracle."""
+    o = ops()
+    pred = fx.synthetic_predictions(4, 196608, 8, 1024, 0.02, 31)
+    pt = torch.from_numpy(pred).cuda()
+    for kw in (dict(conf_thres=0.25, iou_thres=0.45), dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)):
+        det, counts, keep = o.nms(pt, want_keep_idx=True, **kw)
+        for i in range(4):
+            d1, c1, k1 = o.nms(pt[i:i + 1], want_keep_idx=True, **kw)
+            assert torch.equal(d1[0], det[i]) and torch.equal(c1[0], counts[i]) and torch.equal(k1[0], keep[i])
+        outs, idxs = nms_ref.non_max_suppression(pred[:1], return_indices=True, early_stop=True, **kw)
+        n = int(counts[0])
+        assert n == len(idxs[0]) and np.array_equal(keep[0, :n].cpu().numpy(), idxs[0])
+
+
+# ------------------------------------------------------------------------------------ whole model
+def load_det_weights(model):
+    sd = model.state_dict()
+    new = {}
+    for k, v in sd.items():
+        if torch.is_floating_point(v) and not any(s in k for s in ("attn_mask", "anchors", "anchor_grid")):
+            new[k] = fx.deterministic_tensor(k, v.shape, seed=0)
+    model.load_state_dict(new, strict=False)
+    return model
+
+
+def test_model_512_fp32_vs_reference_golden(golden):
+    from sodt_b200.basics.models.model import Model
+    g = golden("model_512")
+    m = load_det_weights(Model(YAML, input_mode="RGB+IR", ch_steam=3, ch=128, nc=8)).eval().cuda()
+    rgb = fx.det_input("model:rgb", (1, 3, 512, 512), kind="uniform").cuda()
+    ir = fx.det_input("model:ir", (1, 3, 512, 512), kind="uniform").cuda()
+    with torch.no_grad():
+        pred, raw, feats = m(rgb, ir, "RGB+IR")
+    for i in range(3):
+        assert rel_err(feats[i][0, ::7, ::5, ::3], g[f"feat{i}_sub"]) < 1e-4, i
+    assert rel_err(raw[0][0].reshape(-1, 13)[::61], g["raw_rows"]) < 1e-4
+    ref = torch.from_numpy(g["pred_rows"]).double()
+    got = pred[0, ::61].double().cpu()
+    assert ((got[:, :4] - ref[:, :4]).abs() / ref[:, :4].abs().clamp_min(1.0)).max() < 1e-3
+    assert (got[:, 4:] - ref[:, 4:]).abs().max() < 1e-4
+
+
+def test_model_512_bf16_vs_reference_golden(golden):
+    from sodt_b200.basics.models.model import Model
+    g = golden("model_512")
+    m = load_det_weights(Model(YAML, input_mode="RGB+IR", ch_steam=3, ch=128, nc=8)).eval().cuda().to(torch.bfloat16)
+    rgb = fx.det_input("model:rgb", (1, 3, 512, 512), kind="uniform").cuda().to(torch.bfloat16)
+    ir = fx.det_input("model:ir", (1, 3, 512, 512), kind="uniform").cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        pred, raw, feats = m(rgb, ir, "RGB+IR")
+    assert pred.dtype == torch.float32            # decode is fp32 in every mode
+    for i in range(3):
+        assert rel_err(feats[i][0, ::7, ::5, ::3], g[f"feat{i}_sub"]) < 3e-2, i
+
+
+def test_model_1024_runs_and_matches_oracle_adapter():
+    """1024x1024 is beyond the reference's hard-coded grid; the oracle adapter (reference classes'
+    math at a scaled token grid, oracle/model_ref.py) is the checker.  Batch 1 keeps the CPU oracle short."""
+    from sodt_b200.basics.models.model import Model
+    m = load_det_weights(Model(YAML, input_mode="RGB+IR", ch_steam=3, ch=128, nc=8)).eval()
+    p = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    rgb = fx.det_input("model1024:rgb", (1, 3, 1024, 1024), kind="uniform")
+    ir = fx.det_input("model1024:ir", (1, 3, 1024, 1024), kind="uniform")
+    with torch.no_grad():
+        pred, raw, feats = m(rgb.cuda(), ir.cuda(), "RGB+IR")
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        pred_ref, raw_ref = model_ref.model_forward(rgb, ir, p)
+    assert pred.shape == (1, 3 * 256 * 256, 13)
+    assert rel_err(raw[0], raw_ref[0]) < 1e-4
+    got, ref = pred.double().cpu(), pred_ref.double()
+    assert ((got[..., :4] - ref[..., :4]).abs() / ref[..., :4].abs().clamp_min(1.0)).max() < 1e-3
