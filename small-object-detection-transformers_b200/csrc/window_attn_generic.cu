@@ -103,7 +103,8 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
     for (int d = 0; d < HDP; ++d) q[d] = ks[i * LD + d] * scale;  // reference scales q first (:971)
     int yq = 0, xq = 0;
     const bool q_real = tq < N && g.rolled(win, tq, yq, xq);
-    const int tyq = tq / ws, txq = tq - tyq * ws;
+    const int tq_c = tq < N ? tq : N - 1;   // rows past the window only pad the tile; keep their bias index in range
+    const int tyq = tq_c / ws, txq = tq_c - tyq * ws;
     const int rq = shift > 0 ? g.region(yq, xq) : 0;
     __syncthreads();
 
