@@ -61,11 +61,17 @@ int sodt_built_for_sm(void);                    /* 100 (sm_100a) */
  *              (region ids of backbone_vit.py:1060-1072 evaluated in closed form) with
  *              `mask_value` (-100.0 in the reference, finite on purpose).
  *   scale      multiplies q (head_dim^-0.5 in the reference).
+ *   workspace  sodt_window_attn_workspace_bytes(C, heads, ws) bytes of device scratch (16-byte aligned)
+ *              used by the tensor-core kernels for a transposed, log2(e)-scaled copy of the bias table.
  * Supported: C % heads == 0, head_dim <= 64, any ws >= 1 (tokens per window unbounded).
+ * Kernel selection (by shape, one code path per shape): bf16 with head_dim 64, ws 32, no shift ->
+ * tcgen05 flash kernel; everything else (and all of SODT_F32) -> the exact fp32 CUDA-core kernel.
  */
+size_t sodt_window_attn_workspace_bytes(int C, int heads, int ws);
 int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
                          int B, int H, int W, int C, int heads, int ws, int shift,
-                         int dtype, float scale, float mask_value, void* stream);
+                         int dtype, float scale, float mask_value,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Cross-channel attention block over the four token streams R, G, B, IR.

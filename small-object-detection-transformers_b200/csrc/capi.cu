@@ -10,7 +10,17 @@ int window_attn_generic(const void* qkv, const float* table, const void* pad_qkv
                         int C, int heads, int ws, int shift, int dtype, float scale, float mask_value,
                         cudaStream_t stream);
 
+size_t window_attn_flash_workspace(int heads, int ws);
+bool window_attn_flash_supported(int H, int W, int C, int heads, int ws, int shift, int dtype);
+int window_attn_flash(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
+                      int heads, int ws, float scale, cudaStream_t stream);
+
 }  // namespace sodt
+
+extern "C" size_t sodt_window_attn_workspace_bytes(int C, int heads, int ws) {
+    if (C <= 0 || heads <= 0 || ws <= 0) return 0;
+    return sodt::window_attn_flash_workspace(heads, ws);
+}
 
 extern "C" int sodt_version(void) { return 100; }
 extern "C" int sodt_built_for_sm(void) { return 100; }
@@ -33,13 +43,20 @@ extern "C" void sodt_reset_launch_count(void) { sodt::g_launches = 0; }
 
 extern "C" int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
                                     int B, int H, int W, int C, int heads, int ws, int shift,
-                                    int dtype, float scale, float mask_value, void* stream) {
+                                    int dtype, float scale, float mask_value,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
     using namespace sodt;
     if (!qkv || !bias_table || !out) return SODT_ERR_INVALID_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0) return SODT_ERR_INVALID_ARG;
     if (shift < 0 || shift >= ws) return SODT_ERR_INVALID_ARG;
     if (dtype != SODT_F32 && dtype != SODT_BF16) return SODT_ERR_INVALID_ARG;
     if (!aligned16(qkv) || !aligned16(out) || (pad_qkv && !aligned16(pad_qkv))) return SODT_ERR_ALIGNMENT;
+    if (window_attn_flash_supported(H, W, C, heads, ws, shift, dtype)) {
+        if (!workspace || !aligned16(workspace) || workspace_bytes < window_attn_flash_workspace(heads, ws))
+            return SODT_ERR_WORKSPACE;
+        return window_attn_flash(qkv, bias_table, out, workspace, B, H, W, C, heads, ws, scale,
+                                 static_cast<cudaStream_t>(stream));
+    }
     return window_attn_generic(qkv, bias_table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value,
                                static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,297 @@
+// Global-window attention on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).
+//
+// Serves the "window covers a large map" case of the backbone's last stage: windows of WS x WS
+// tokens with N = WS*WS a multiple of 128 and head_dim 64 (stage 3: WS = 32, N = 1024,
+// basics/models/backbone_vit.py:151-160), no shift.  Flash-style: one CTA owns 128 query rows of
+// one (window, head) and streams the keys / values in tiles of 128 through shared memory.
+//
+//   S = Q K^T          tcgen05.mma SS, M=128 N=128 K=64, both operands K-major (SWIZZLE_NONE canonical
+//                      layout [8-element chunk][row][16 B]), accumulator in TMEM columns [0,128)
+//   softmax            one thread per query row reads its S row from TMEM (tcgen05.ld 32x32b), adds the
+//                      relative-position bias (closed-form index into the shared-memory table,
+//                      conflict free: the 32 lanes of a warp are 32 consecutive tokens of one window row),
+//                      exp2 with a lazily updated running maximum, writes P as packed bf16 pairs back to
+//                      TMEM columns [128,192)
+//   O += P V           tcgen05.mma TS (A = P from TMEM, B = V MN-major from shared memory), accumulator in
+//                      TMEM columns [192,256); rescaled in TMEM only when a row maximum grew by > 2^8
+//
+// Warp roles: warps 0-3 softmax + epilogue (128 threads = 128 rows), warp 4 cp.async producer,
+// warp 5 MMA issuer (one elected lane).  Two CTAs per SM (256 TMEM columns, ~97 KB smem each) so that one
+// CTA's softmax overlaps the other's MMAs.  No score, probability, bias or window tensor reaches HBM.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace sodt {
+namespace {
+
+using namespace tc;
+
+constexpr int TM = 128;            // query rows per CTA
+constexpr int TN = 128;            // keys per tile
+constexpr int HD = 64;             // head dim
+constexpr int NTHREADS = 192;
+constexpr int TILE_BYTES = TM * HD * 2;   // 16 KB
+constexpr int CHUNK_STRIDE = TM * 16;     // bytes between 8-element chunks of the canonical layout
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct SmemLayout {
+    static constexpr int Q = 0;
+    static constexpr int K = Q + TILE_BYTES;            // 2 stages
+    static constexpr int V = K + 2 * TILE_BYTES;        // 2 stages
+    static constexpr int TAB = V + 2 * TILE_BYTES;      // (2*WS-1)^2 floats
+};
+
+// Transposes the bias table to [heads][(2ws-1)^2] and scales it by log2(e).
+__global__ void prep_table_kernel(const float* __restrict__ table, float* __restrict__ out, int entries, int heads) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < entries * heads) {
+        const int h = e / entries, i = e - h * entries;
+        out[e] = table[(long long)i * heads + h] * LOG2E;
+    }
+}
+
+// 128 tokens x 64 dims of q / k / v of one head -> canonical tile.  One warp; lane = (chunk quad, token octet).
+template <int WS>
+__device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* __restrict__ qkv, long long win_base,
+                                          int W, int C3, int t0, int col0, int lane) {
+    const int tsub = lane & 7, csub = lane >> 3;
+#pragma unroll 4
+    for (int oct = 0; oct < TM / 8; ++oct) {
+        const int t = t0 + oct * 8 + tsub;
+        const int ty = t / WS, tx = t - ty * WS;
+        const __nv_bfloat16* src = qkv + (win_base + (long long)ty * W + tx) * C3 + col0;
+        const uint32_t d = dst + (oct * 8 + tsub) * 16;
+        cp_async16(d + csub * CHUNK_STRIDE, src + csub * 8);
+        cp_async16(d + (csub + 4) * CHUNK_STRIDE, src + (csub + 4) * 8);
+    }
+}
+
+template <int WS>
+__global__ void __launch_bounds__(NTHREADS, 2)
+window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table_t,
+                         __nv_bfloat16* __restrict__ out, int H, int W, int C, int heads, float scale) {
+    constexpr int N = WS * WS;
+    constexpr int T = N / TN;
+    constexpr int SPAN = 2 * WS - 1;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t bar_k_full[2], bar_v_full[2], bar_kv_empty[2], bar_q_full, bar_s_full, bar_s_free, bar_p_full, bar_pv_done;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qtile = blockIdx.x, head = blockIdx.y;
+    const int nww = W / WS, nW = (H / WS) * nww;
+    const int b = blockIdx.z / nW, win = blockIdx.z - b * nW;
+    const int wy = win / nww, wx = win - wy * nww;
+    const long long win_base = ((long long)b * H + wy * WS) * W + wx * WS;   // token index of the window's corner
+    const int C3 = 3 * C;
+    const uint32_t sbase = smem_u32(smem);
+    float* tab = reinterpret_cast<float*>(smem + SmemLayout::TAB);
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_k_full[s], 32); mbar_init(&bar_v_full[s], 32); mbar_init(&bar_kv_empty[s], 1); }
+        mbar_init(&bar_q_full, 32);
+        mbar_init(&bar_s_full, 1);
+        mbar_init(&bar_s_free, TM);
+        mbar_init(&bar_p_full, TM);
+        mbar_init(&bar_pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) { tmem_alloc(&tmem_slot, 256); tmem_relinquish(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm_S = tmem_slot, tm_P = tmem_slot + 128, tm_O = tmem_slot + 192;
+
+    if (warp == 4) {
+        // ===================================================================== producer
+        load_tile<WS>(sbase + SmemLayout::Q, qkv, win_base, W, C3, qtile * TM, head * HD, lane);
+        cp_async_commit();
+        uint64_t* pending = &bar_q_full;          // barrier of the most recently committed group
+        for (int t = 0; t < T; ++t) {
+            const int s = t & 1;
+            if (t >= 2) mbar_wait(&bar_kv_empty[s], ((t >> 1) - 1) & 1);
+            load_tile<WS>(sbase + SmemLayout::K + s * TILE_BYTES, qkv, win_base, W, C3, t * TN, C + head * HD, lane);
+            cp_async_commit();
+            cp_async_wait<1>();                  // everything but the group just committed has landed
+            fence_proxy_async();
+            mbar_arrive(pending);
+            pending = &bar_k_full[s];
+            load_tile<WS>(sbase + SmemLayout::V + s * TILE_BYTES, qkv, win_base, W, C3, t * TN, 2 * C + head * HD, lane);
+            cp_async_commit();
+            cp_async_wait<1>();
+            fence_proxy_async();
+            mbar_arrive(pending);
+            pending = &bar_v_full[s];
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(pending);
+    } else if (warp == 5) {
+        // =================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = idesc_bf16(TM, TN, false, false);
+            constexpr uint32_t idesc_o = idesc_bf16(TM, HD, false, true);
+            auto issue_s = [&](int t) {
+                const int s = t & 1;
+                mbar_wait(&bar_k_full[s], (t >> 1) & 1);
+                if (t > 0) mbar_wait(&bar_s_free, (t - 1) & 1);
+                fence_proxy_async();
+                fence_after_sync();
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) {
+                    const uint64_t a = smem_desc(sbase + SmemLayout::Q + k * 2 * CHUNK_STRIDE, CHUNK_STRIDE, 128);
+                    const uint64_t bd = smem_desc(sbase + SmemLayout::K + s * TILE_BYTES + k * 2 * CHUNK_STRIDE, CHUNK_STRIDE, 128);
+                    mma_ss(tm_S, a, bd, idesc_s, k > 0);
+                }
+                mma_commit(&bar_s_full);
+            };
+            mbar_wait(&bar_q_full, 0);
+            issue_s(0);
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1;
+                if (t + 1 < T) issue_s(t + 1);
+                mbar_wait(&bar_v_full[s], (t >> 1) & 1);
+                mbar_wait(&bar_p_full, t & 1);
+                fence_proxy_async();
+                fence_after_sync();
+#pragma unroll
+                for (int k = 0; k < TN / 16; ++k) {
+                    // V tile [dim chunk][key][16 B]: 8-key groups 128 B apart, dim chunks CHUNK_STRIDE apart
+                    const uint64_t bd = smem_desc(sbase + SmemLayout::V + s * TILE_BYTES + k * 256, 128, CHUNK_STRIDE);
+                    mma_ts(tm_O, tm_P + k * 8, bd, idesc_o, (t > 0) || (k > 0));
+                }
+                mma_commit(&bar_pv_done);
+                mma_commit(&bar_kv_empty[s]);
+            }
+        }
+    } else {
+        // ============================================================ softmax + epilogue
+        const int row = tid;                                  // 0..127, TMEM lane == row
+        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+        for (int e = tid; e < SPAN * SPAN; e += TM) tab[e] = table_t[(long long)head * SPAN * SPAN + e];
+        asm volatile("bar.sync 1, 128;" ::: "memory");        // table visible to the 4 softmax warps
+        const int tq = qtile * TM + row;
+        const int yq = tq / WS, xq = tq - yq * WS;
+        const float* tab_q = tab + (yq + WS - 1) * SPAN + (xq + WS - 1);
+        const float c = scale * LOG2E;
+        float m_used = -INFINITY, l_run = 0.f;
+        for (int t = 0; t < T; ++t) {
+            mbar_wait(&bar_s_full, t & 1);
+            fence_after_sync();
+            float s2[TN];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                uint32_t r[32];
+                tmem_ld32(tm_S + lane_addr + q4 * 32, r);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s2[q4 * 32 + j] = __uint_as_float(r[j]);
+            }
+            fence_before_sync();
+            mbar_arrive(&bar_s_free);
+            // key j of this tile sits at window row t*(TN/WS) + j/WS, column j%WS
+            const float* tb = tab_q - (t * (TN / WS)) * SPAN;
+            float m_tile = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                s2[j] = fmaf(s2[j], c, tb[-((j / WS) * SPAN + (j % WS))]);
+                m_tile = fmaxf(m_tile, s2[j]);
+            }
+            float alpha = 1.f;
+            if (m_tile > m_used + RESCALE_THRESHOLD) {
+                alpha = fast_exp2(m_used - m_tile);   // 0 on the first tile (m_used = -inf)
+                m_used = m_tile;
+            }
+            float sum = 0.f;
+            uint32_t pk[TN / 2];
+#pragma unroll
+            for (int j = 0; j < TN; j += 2) {
+                const float p0 = fast_exp2(s2[j] - m_used), p1 = fast_exp2(s2[j + 1] - m_used);
+                sum += p0 + p1;
+                pk[j / 2] = pack_bf16(p0, p1);
+            }
+            l_run = l_run * alpha + sum;
+            if (t > 0) {
+                mbar_wait(&bar_pv_done, (t - 1) & 1);          // P and O are free again
+                fence_after_sync();
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        uint32_t o[32];
+                        tmem_ld32(tm_O + lane_addr + h2 * 32, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+                        tmem_st32(tm_O + lane_addr + h2 * 32, o);
+                    }
+                }
+            }
+            {
+                uint32_t half[32];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) half[j] = pk[h2 * 32 + j];
+                    tmem_st32(tm_P + lane_addr + h2 * 32, half);
+                }
+            }
+            tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive(&bar_p_full);
+        }
+        mbar_wait(&bar_pv_done, (T - 1) & 1);
+        fence_after_sync();
+        const float inv = 1.f / l_run;
+        const int ty = tq / WS, tx = tq - ty * WS;
+        __nv_bfloat16* dst = out + (win_base + (long long)ty * W + tx) * C + head * HD;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            uint32_t o[32];
+            tmem_ld32(tm_O + lane_addr + h2 * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint4 v;
+                v.x = pack_bf16(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
+                v.y = pack_bf16(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
+                v.z = pack_bf16(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
+                v.w = pack_bf16(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
+                *reinterpret_cast<uint4*>(dst + h2 * 32 + j) = v;
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_slot, 256);
+}
+
+}  // namespace
+
+size_t window_attn_flash_workspace(int heads, int ws) { return (size_t)heads * (2 * ws - 1) * (2 * ws - 1) * sizeof(float); }
+
+bool window_attn_flash_supported(int H, int W, int C, int heads, int ws, int shift, int dtype) {
+    return dtype == SODT_BF16 && shift == 0 && ws == 32 && C == heads * HD && H % ws == 0 && W % ws == 0 && C % 8 == 0;
+}
+
+int window_attn_flash(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
+                      int heads, int ws, float scale, cudaStream_t stream) {
+    constexpr int WS = 32;
+    const int entries = (2 * ws - 1) * (2 * ws - 1);
+    float* table_t = static_cast<float*>(workspace);
+    prep_table_kernel<<<(entries * heads + 255) / 256, 256, 0, stream>>>(table, table_t, entries, heads);
+    int st = check_launch();
+    if (st != SODT_OK) return st;
+    const size_t smem = SmemLayout::TAB + (size_t)entries * sizeof(float);
+    auto kern = window_attn_flash_kernel<WS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    const long long nwin = (long long)B * (H / ws) * (W / ws);
+    if (nwin > 65535 * 32LL) return SODT_ERR_UNSUPPORTED;
+    dim3 grid(ws * ws / TM, heads, (unsigned)nwin);
+    kern<<<grid, NTHREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), table_t,
+                                           static_cast<__nv_bfloat16*>(out), H, W, C, heads, scale);
+    return check_launch();
+}
+
+}  // namespace sodt

@@ -28,12 +28,61 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+# Optional per-call CUDA-event timing on the launching stream (bench.py's roofline leg).
+_timing = None
+
+
+def enable_kernel_timing(on=True):
+    """Start (or stop) recording a CUDA-event pair around every sodt kernel sequence."""
+    global _timing
+    _timing = {} if on else None
+
+
+def kernel_timings():
+    """{label: [ms, ...]} of everything recorded since enable_kernel_timing(); synchronises."""
+    if _timing is None:
+        return {}
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in _timing.items()}
+
+
+class _Timed:
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if _timing is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timing is not None:
+            self.b.record()
+            _timing.setdefault(self.label, []).append((self.a, self.b))
+        return False
+
+
 def launch_count():
     return _capi.lib().sodt_launch_count()
 
 
 def reset_launch_count():
     _capi.lib().sodt_reset_launch_count()
+
+
+_scratch_bufs = {}
+
+
+def _scratch(tag, device, nbytes):
+    """Per (device, stream) scratch buffer owned by torch's allocator; the kernels never allocate."""
+    key = (tag, device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch_bufs.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _scratch_bufs[key] = buf
+    return buf
 
 
 # ------------------------------------------------------------------------------ window attention
@@ -60,10 +109,11 @@ def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=No
     out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
     if scale is None:
         scale = (C // heads) ** -0.5
-    with torch.cuda.device(qkv.device):
+    wsp = _scratch("wattn", qkv.device, _capi.lib().sodt_window_attn_workspace_bytes(C, heads, ws))
+    with torch.cuda.device(qkv.device), _Timed(f"window_attn[B={B},H={H},W={W},C={C},heads={heads},ws={ws},shift={shift}]"):
         st = _capi.lib().sodt_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), _ptr(pad_qkv), out.data_ptr(),
                                               B, H, W, C, heads, ws, shift, _DT[qkv.dtype], float(scale),
-                                              float(mask_value), _stream())
+                                              float(mask_value), wsp.data_ptr(), wsp.numel(), _stream())
     _capi.check(st, "sodt_window_attn_fwd")
     return out
 
@@ -87,7 +137,7 @@ def cattn_block(r, g, b, ir, ln_w, ln_b, heads, ws=1, shift=0, eps=1e-5, mask_va
     if ln_w.numel() != 4 * C or ln_b.numel() != 4 * C:
         raise ValueError("ln_w / ln_b must be [4, C]")
     out = torch.empty((B, h, w, 4 * C), dtype=r.dtype, device=r.device)
-    with torch.cuda.device(r.device):
+    with torch.cuda.device(r.device), _Timed(f"cattn_block[B={B},h={h},w={w},C={C},ws={ws}]"):
         st = _capi.lib().sodt_cattn_block_fwd(streams[0].data_ptr(), streams[1].data_ptr(), streams[2].data_ptr(),
                                               streams[3].data_ptr(), sb, sy, sx, sc, ln_w.data_ptr(), ln_b.data_ptr(),
                                               out.data_ptr(), B, h, w, C, heads, ws, shift, float(eps),
@@ -116,7 +166,7 @@ def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=No
         rows_total = z.shape[1]
     xp = torch.empty((B, na, ny, nx, no), dtype=raw.dtype, device=raw.device) if want_perm else None
     sb, sc, sy, sx = raw.stride()
-    with torch.cuda.device(raw.device):
+    with torch.cuda.device(raw.device), _Timed(f"detect_decode[B={B},ny={ny},nx={nx}]"):
         st = _capi.lib().sodt_detect_decode(raw.data_ptr(), sb, sc, sy, sx, anchors_px.data_ptr(), z.data_ptr(), _ptr(xp),
                                             B, na, no, ny, nx, float(stride), rows_total, row_offset, _DT[raw.dtype],
                                             _stream())
@@ -160,7 +210,7 @@ def nms(pred, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, mul
     if classes is not None:
         cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=dev)
     ws = _nms_workspace(dev, B, R, nc, multi_label)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed(f"nms[B={B},R={R},nc={nc}]"):
         st = _capi.lib().sodt_nms(pred.data_ptr(), _ptr(cls_t), 0 if cls_t is None else cls_t.numel(), out.data_ptr(),
                                   counts.data_ptr(), _ptr(keep), ws.data_ptr(), ws.numel(), B, R, nc, float(conf_thres),
                                   float(iou_thres), int(bool(multi_label)), int(bool(agnostic)), int(bool(merge)),

@@ -1,0 +1,129 @@
+"""Inference runtime: the call a user makes.
+
+``Detector``         one GPU: uint8 RGB + IR images (host or device) -> padded detections.
+                     Mirrors the reference's evaluation loop (basics/test.py:124-152): /255,
+                     ``model(img, ir, input_mode)``, ``non_max_suppression``.
+``ShardedDetector``  one process per GPU: images are sharded by index across ranks, weights are
+                     replicated, the forward has no collective; the only exchange is one
+                     all-gather of the fixed-shape padded detections ([B_local, 300, 6] fp32 +
+                     [B_local] int32, 7.2 KB per image).  The NMS kernel writes straight into the
+                     all-gather send buffer, so there is no pack step.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .basics.models.model import Model
+
+MAX_DET = 300
+DEFAULT_CFG = os.path.join(os.path.dirname(os.path.abspath(__file__)), "models", "model.yaml")
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous split of ``n_items`` image indices over ``world`` ranks (first ranks get the remainder)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+class DetectionBuffer:
+    """Flat fp32 communication buffer: [B*max_det*6 detection floats | B int32 counts (bit-cast)].
+    ``det`` and ``counts`` are views into it; NMS writes them in place."""
+
+    def __init__(self, batch, device, max_det=MAX_DET):
+        self.batch, self.max_det = batch, max_det
+        self.flat = torch.zeros(batch * max_det * 6 + batch, dtype=torch.float32, device=device)
+        self.det = self.flat[: batch * max_det * 6].view(batch, max_det, 6)
+        self.counts = self.flat[batch * max_det * 6:].view(torch.int32)
+
+    @staticmethod
+    def split(flat, batch, max_det=MAX_DET):
+        n = batch * max_det * 6
+        return flat[:n].view(batch, max_det, 6), flat[n:n + batch].view(torch.int32)
+
+
+def allgather_detections(buf, group=None):
+    """All-gathers every rank's DetectionBuffer (equal local batch).  Returns (det [world*B,300,6],
+    counts [world*B]) in rank order == global image order for contiguous sharding."""
+    world = dist.get_world_size(group)
+    recv = torch.empty(world * buf.flat.numel(), dtype=buf.flat.dtype, device=buf.flat.device)
+    dist.all_gather_into_tensor(recv, buf.flat, group=group)
+    dets, counts = [], []
+    for r in range(world):
+        d, c = DetectionBuffer.split(recv[r * buf.flat.numel():(r + 1) * buf.flat.numel()], buf.batch, buf.max_det)
+        dets.append(d)
+        counts.append(c)
+    return torch.cat(dets), torch.cat(counts)
+
+
+class Detector:
+    """RGB+IR detector on one GPU.  ``dtype`` is the storage / tensor-core operand type of the
+    backbone and head (bf16 by default); softmax, LayerNorm statistics, Detect decode and NMS are fp32."""
+
+    def __init__(self, cfg=DEFAULT_CFG, state_dict=None, device="cuda", dtype=torch.bfloat16, conf_thres=0.25,
+                 iou_thres=0.45, multi_label=False, agnostic=False, classes=None, nc=8, seed=0):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.nms_args = dict(conf_thres=conf_thres, iou_thres=iou_thres, multi_label=multi_label, agnostic=agnostic,
+                             classes=classes)
+        torch.manual_seed(seed)
+        model = Model(cfg, input_mode="RGB+IR", ch_steam=3, ch=128, nc=nc)
+        if state_dict is not None:
+            model.load_state_dict(state_dict, strict=False)
+        self.model = model.eval().to(self.device, dtype)
+        self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
+        self._bufs = {}
+
+    def buffer(self, batch):
+        if batch not in self._bufs:
+            self._bufs[batch] = DetectionBuffer(batch, self.device)
+        return self._bufs[batch]
+
+    @torch.no_grad()
+    def predict(self, rgb_u8, ir_u8):
+        """Device uint8 [B,3,H,W] x2 -> decoded predictions [B, R, 5+nc] fp32 (the reference's ``out``)."""
+        x = rgb_u8.to(self.dtype).div_(255.0)
+        ir = ir_u8[:, 0:1].to(self.dtype).div_(255.0)     # the detector reads IR channel 0 only (model.py:192)
+        pred, _, _ = self.model(x, ir, "RGB+IR")
+        return pred
+
+    @torch.no_grad()
+    def detect_device(self, rgb_u8, ir_u8, buf=None):
+        """Device uint8 inputs -> DetectionBuffer (device resident, no host sync)."""
+        buf = buf or self.buffer(rgb_u8.shape[0])
+        pred = self.predict(rgb_u8, ir_u8)
+        ops.nms(pred, out=buf.det, counts=buf.counts, **self.nms_args)
+        return buf
+
+    def detect(self, rgb_u8_host, ir_u8_host):
+        """Host uint8 images (pinned for async copies) -> (det [B,300,6], counts [B]) on the host."""
+        rgb = rgb_u8_host.to(self.device, non_blocking=True)
+        ir = ir_u8_host.to(self.device, non_blocking=True)
+        buf = self.detect_device(rgb, ir)
+        flat = buf.flat.to("cpu")
+        return DetectionBuffer.split(flat, buf.batch, buf.max_det)
+
+    def __call__(self, rgb_u8_host, ir_u8_host):
+        det, counts = self.detect(rgb_u8_host, ir_u8_host)
+        return [det[i, :n] for i, n in enumerate(counts.tolist())]
+
+
+class ShardedDetector:
+    """Data-parallel inference over the ranks of an initialised process group (one process per GPU)."""
+
+    def __init__(self, detector, group=None):
+        self.detector = detector
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def local_slice(self, n_images):
+        return shard_range(n_images, self.rank, self.world)
+
+    @torch.no_grad()
+    def detect_device(self, rgb_u8_local, ir_u8_local):
+        """Each rank passes ITS shard (equal sizes); returns the gathered detections of all ranks."""
+        buf = self.detector.detect_device(rgb_u8_local, ir_u8_local)
+        return allgather_detections(buf, self.group)

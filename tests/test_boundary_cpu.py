@@ -42,7 +42,7 @@ def test_library_identity_without_gpu():
     assert L.sodt_status_string(-2) == b"unsupported shape"
     assert L.sodt_nms_workspace_bytes(2, 4096, 8, 1) > L.sodt_nms_workspace_bytes(2, 4096, 8, 0) > 0
     # argument validation happens before any CUDA call
-    assert L.sodt_window_attn_fwd(None, None, None, None, 1, 8, 8, 16, 1, 8, 0, 0, 1.0, -100.0, None) == -1
+    assert L.sodt_window_attn_fwd(None, None, None, None, 1, 8, 8, 16, 1, 8, 0, 0, 1.0, -100.0, None, 0, None) == -1
     assert L.sodt_nms(None, None, 0, None, None, None, None, 0, 1, 1, 1, 0.25, 0.45, 0, 0, 1, 1, 300, 30000, 4096.0, None) == -1
 
 

@@ -61,6 +61,8 @@ WINDOW_CASES = [
     (1, 9, 9, 40, 2, 3, 1, False),        # hd 20 (not a power of two), N = 9
     (3, 8, 8, 24, 4, 8, 0, False),        # hd 6
     (1, 64, 64, 192, 12, 8, 4, False),    # shift = ws/2 (swinv2-style)
+    (1, 64, 64, 192, 3, 32, 0, False),    # 4 global windows of 1024 tokens, hd 64 (1024^2-input stage 3)
+    (2, 32, 64, 128, 2, 32, 0, False),    # rectangular grid of 1024-token windows
 ]
 
 
