@@ -64,8 +64,9 @@ int sodt_built_for_sm(void);                    /* 100 (sm_100a) */
  *   workspace  sodt_window_attn_workspace_bytes(C, heads, ws) bytes of device scratch (16-byte aligned)
  *              used by the tensor-core kernels for a transposed, log2(e)-scaled copy of the bias table.
  * Supported: C % heads == 0, head_dim <= 64, any ws >= 1 (tokens per window unbounded).
- * Kernel selection (by shape, one code path per shape): bf16 with head_dim 64, ws 32, no shift ->
- * tcgen05 flash kernel; everything else (and all of SODT_F32) -> the exact fp32 CUDA-core kernel.
+ * Kernel selection (by shape, one code path per shape): bf16, head_dim 64, ws 32, no shift -> tcgen05
+ * flash kernel; bf16, ws 8, head_dim 16 / 32, H and W multiples of 8 -> tcgen05 window-pair kernel;
+ * everything else (and all of SODT_F32) -> the exact fp32 CUDA-core kernel.
  */
 size_t sodt_window_attn_workspace_bytes(int C, int heads, int ws);
 int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,

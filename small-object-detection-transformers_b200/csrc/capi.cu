@@ -15,11 +15,24 @@ bool window_attn_flash_supported(int H, int W, int C, int heads, int ws, int shi
 int window_attn_flash(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
                       int heads, int ws, float scale, cudaStream_t stream);
 
+size_t window_attn_win8_workspace(int heads);
+bool window_attn_win8_supported(int H, int W, int C, int heads, int ws, int shift, int dtype);
+int window_attn_win8(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
+                     int heads, int shift, float scale, float mask_value, int num_sms, cudaStream_t stream);
+
+static int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    return n;
+}
+
 }  // namespace sodt
 
 extern "C" size_t sodt_window_attn_workspace_bytes(int C, int heads, int ws) {
     if (C <= 0 || heads <= 0 || ws <= 0) return 0;
-    return sodt::window_attn_flash_workspace(heads, ws);
+    const size_t a = sodt::window_attn_flash_workspace(heads, ws), b = sodt::window_attn_win8_workspace(heads);
+    return a > b ? a : b;
 }
 
 extern "C" int sodt_version(void) { return 100; }
@@ -56,6 +69,12 @@ extern "C" int sodt_window_attn_fwd(const void* qkv, const float* bias_table, co
             return SODT_ERR_WORKSPACE;
         return window_attn_flash(qkv, bias_table, out, workspace, B, H, W, C, heads, ws, scale,
                                  static_cast<cudaStream_t>(stream));
+    }
+    if (window_attn_win8_supported(H, W, C, heads, ws, shift, dtype)) {
+        if (!workspace || !aligned16(workspace) || workspace_bytes < window_attn_win8_workspace(heads))
+            return SODT_ERR_WORKSPACE;
+        return window_attn_win8(qkv, bias_table, out, workspace, B, H, W, C, heads, shift, scale, mask_value, sm_count(),
+                                static_cast<cudaStream_t>(stream));
     }
     return window_attn_generic(qkv, bias_table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value,
                                static_cast<cudaStream_t>(stream));

@@ -63,6 +63,9 @@ WINDOW_CASES = [
     (1, 64, 64, 192, 12, 8, 4, False),    # shift = ws/2 (swinv2-style)
     (1, 64, 64, 192, 3, 32, 0, False),    # 4 global windows of 1024 tokens, hd 64 (1024^2-input stage 3)
     (2, 32, 64, 128, 2, 32, 0, False),    # rectangular grid of 1024-token windows
+    (1, 8, 24, 64, 4, 8, 2, False),       # odd number of windows (pair kernel tail), hd 16
+    (3, 8, 8, 64, 2, 8, 0, False),        # odd number of windows, hd 32
+    (2, 40, 24, 192, 12, 8, 7, False),    # largest shift
 ]
 
 
