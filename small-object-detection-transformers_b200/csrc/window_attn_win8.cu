@@ -156,6 +156,9 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                 const int p = (int)(n & 1);
                 const long long k = n >> 1, gq = n / G;
                 const int hg = (int)(n - gq * G), s = (int)(gq % STAGES);
+                // S[p] is free as soon as softmax(n) has copied it to registers (early in its work), so the
+                // scores of the group's next head are computed while softmax(n) is still running
+                if (n + 2 < n_total) issue_qk(n + 2);
                 mbar_wait(&p_full[p], (uint32_t)(k & 1));
                 fence_after_sync();
                 const uint32_t vt = sbase + s * STAGE_BYTES + (2 * G + hg) * TILE_BYTES;
@@ -164,7 +167,6 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                     mma_ts(tm + 384 + p * 32, tm + 256 + p * 64 + ks * 8, smem_desc(vt + ks * 256, 128, CHUNK_STRIDE), idesc_o, ks > 0);
                 mma_commit(&pv_done[p]);
                 if (hg == G - 1) mma_commit(&stage_empty[s]);
-                if (n + 2 < n_total) issue_qk(n + 2);
             }
         }
     } else {
