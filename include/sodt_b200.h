@@ -75,6 +75,22 @@ int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* p
                          void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Fused (residual add +) LayerNorm over the channels of token rows.
+ * Replaces the norm1 / norm2 LayerNorms and the residual adds of SwinTransformerBlock.forward
+ * (backbone_vit.py:1089-1090,1125,1128) and PatchMerging.norm (backbone_vit.py:858); eps as given, biased variance,
+ * statistics in fp32.
+ *
+ *   a, r       [rows, C]; r may be NULL.  s = a (+ r)
+ *   w, b       [C] fp32 LayerNorm weight / bias
+ *   y          [rows, C] = LayerNorm(s)
+ *   sum_out    [rows, C] or NULL: s (+ extra_bias).  extra_bias [C] fp32 or NULL is the bias of the NEXT projection,
+ *              pre-added to the residual stream so that the projection GEMM can add the residual in its epilogue.
+ * Supported: C even, C <= 1024.
+ */
+int sodt_add_layernorm_fwd(const void* a, const void* r, const float* w, const float* b, const float* extra_bias,
+                           void* sum_out, void* y, long long rows, int C, float eps, int dtype, void* stream);
+
+/*
  * Cross-channel attention block over the four token streams R, G, B, IR.
  * Replaces CAttentionBlock.forward, backbone_vit.py:469-561 (and its general-window twin
  * backbone_swinv2.py:429-469): four parameter-free multi-head cross attentions

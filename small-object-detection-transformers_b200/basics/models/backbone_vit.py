@@ -115,7 +115,7 @@ class PatchMerging(nn.Module):
         g = x.view(B, H // 2, 2, W // 2, 2, C)
         # channel order of the reference concat: (dy,dx) = (0,0), (1,0), (0,1), (1,1)
         g = g.permute(0, 1, 3, 4, 2, 5).reshape(B, (H // 2) * (W // 2), 4 * C)
-        return self.norm(self.reduction(g))
+        return ops.add_layernorm(self.reduction(g), None, self.norm.weight, self.norm.bias, self.norm.eps)[0]
 
 
 class Mlp(nn.Module):
@@ -139,14 +139,18 @@ class Mlp(nn.Module):
             self.fc2 = nn.Linear(in_features, out_features)
         self.drop = nn.Dropout(drop)
 
-    def forward(self, x, H, W):
+    def hidden(self, x, H, W):
+        """Everything before fc2: fc1 -> GELU, or fc1 -> zero-pad -> 2x2 conv -> GELU.  [B, L, hidden]."""
         if self.linear:
-            return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+            return self.act(self.fc1(x))
         B, L, C = x.shape
         h = self.fc1(x).view(B, H, W, C).permute(0, 3, 1, 2)   # NCHW view of channels-last memory
         h = F.pad(h, (0, 1, 0, 1))                              # zero column right, zero row below
         h = self.conv1(h).permute(0, 2, 3, 1).reshape(B, L, C)
-        return self.drop(self.fc2(self.drop(self.act(h))))
+        return self.act(h)
+
+    def forward(self, x, H, W):
+        return self.drop(self.fc2(self.drop(self.hidden(x, H, W))))
 
 
 # ------------------------------------------------------------------------------- window attention
@@ -238,9 +242,19 @@ class SwinTransformerBlock(nn.Module):
             raise ValueError("input feature has wrong size")
         if min(H, W) <= self.window_size and (H != W or H != self.window_size):
             raise ValueError(f"token grid {H}x{W} is smaller than the window {self.window_size}")
-        y = self.attn.forward_image(self.norm1(x).view(B, H, W, C), self.window_size, self.shift_size)
-        x = x + y.view(B, L, C)
-        return x + self.mlp(self.norm2(x), H, W)
+        attn, mlp = self.attn, self.mlp
+        # LN1 (sm_100a kernel); its second output is the residual stream with proj.bias pre-added, so that the proj
+        # GEMM adds the residual in its epilogue (addmm) and no elementwise add pass is left.
+        y, xb = ops.add_layernorm(x, None, self.norm1.weight, self.norm1.bias, self.norm1.eps,
+                                  extra_bias=attn.proj.bias, want_sum=True)
+        o = ops.window_attention(attn.qkv(y.view(B, H, W, C)), attn.relative_position_bias_table, attn.num_heads,
+                                 self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
+                                 mask_value=MASK_VALUE)
+        x = torch.addmm(xb.view(B * L, C), o.view(B * L, C), attn.proj.weight.t()).view(B, L, C)
+        z, xb = ops.add_layernorm(x, None, self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                  extra_bias=mlp.fc2.bias, want_sum=True)
+        h = mlp.hidden(z, H, W)
+        return torch.addmm(xb.view(B * L, C), h.view(B * L, h.shape[-1]), mlp.fc2.weight.t()).view(B, L, C)
 
     def extra_repr(self):
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "

@@ -6,6 +6,7 @@ The same functions are registered as ``torch.ops.sodt.*`` custom ops (with fake-
 shape functions) so that the modules stay traceable.  No CPU path exists.
 """
 import math
+import weakref
 
 import torch
 
@@ -116,6 +117,54 @@ def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=No
                                               float(mask_value), wsp.data_ptr(), wsp.numel(), _stream())
     _capi.check(st, "sodt_window_attn_fwd")
     return out
+
+
+# ------------------------------------------------------------------------------------ LayerNorm
+_f32_cache = {}
+
+
+def _as_f32(t):
+    """fp32 contiguous copy of a small parameter.  Cached per tensor OBJECT (weak reference) and validated
+    against its version counter and storage address, so bf16 models do not re-convert their LayerNorm
+    weights on every call and a recycled allocation can never alias a stale copy."""
+    if t is None:
+        return None
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t.detach()
+    key = id(t)
+    hit = _f32_cache.get(key)
+    if hit is not None:
+        ref, version, ptr, val = hit
+        if ref() is t and version == t._version and ptr == t.data_ptr():
+            return val
+    if len(_f32_cache) > 4096:
+        _f32_cache.clear()
+    val = t.detach().to(torch.float32).contiguous()
+    _f32_cache[key] = (weakref.ref(t), t._version, t.data_ptr(), val)
+    return val
+
+
+def add_layernorm(a, r, weight, bias, eps=1e-5, extra_bias=None, want_sum=False):
+    """y = LayerNorm(a (+ r)) over the last dim; optionally also returns a (+ r) (+ extra_bias).
+    See sodt_add_layernorm_fwd.  Returns (y, sum_or_None)."""
+    _require_cuda(a, r, weight, bias, extra_bias)
+    if a.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {a.dtype}")
+    C = a.shape[-1]
+    a = a.contiguous()
+    if r is not None:
+        if r.shape != a.shape or r.dtype != a.dtype:
+            raise ValueError("residual must match the input")
+        r = r.contiguous()
+    rows = a.numel() // C
+    y = torch.empty_like(a)
+    s = torch.empty_like(a) if want_sum else None
+    w32, b32, e32 = _as_f32(weight), _as_f32(bias), _as_f32(extra_bias)
+    with torch.cuda.device(a.device), _Timed(f"add_layernorm[rows={rows},C={C}]"):
+        st = _capi.lib().sodt_add_layernorm_fwd(a.data_ptr(), _ptr(r), w32.data_ptr(), b32.data_ptr(), _ptr(e32), _ptr(s),
+                                                y.data_ptr(), rows, C, float(eps), _DT[a.dtype], _stream())
+    _capi.check(st, "sodt_add_layernorm_fwd")
+    return y, s
 
 
 # ------------------------------------------------------------------------- cross-channel block

@@ -129,6 +129,24 @@ def test_window_attention_full_size_properties(dtype):
     assert rel_err(o0[:1, 40:48, 80:88], ref) < TOL[dtype]
 
 
+# ------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,C,with_r,with_e", [(1000, 192, False, True), (257, 384, True, True), (64, 768, True, False),
+                                                  (33, 48, False, False), (7, 1024, True, True), (5, 250, False, True),
+                                                  (4099, 192, True, True), (1001, 384, False, False), (515, 768, False, True)])
+def test_add_layernorm_vs_torch(rows, C, with_r, with_e, dtype):
+    a = fx.det_input(f"ln_a:{rows}:{C}", (rows, C)).to("cuda", dtype)
+    r = fx.det_input(f"ln_r:{rows}:{C}", (rows, C)).to("cuda", dtype) if with_r else None
+    w = 1.0 + 0.1 * fx.det_input("ln_w", (C,))
+    b = 0.1 * fx.det_input("ln_b", (C,))
+    e = 0.2 * fx.det_input("ln_e", (C,)) if with_e else None
+    y, s = ops().add_layernorm(a, r, w.cuda(), b.cuda(), 1e-5, extra_bias=None if e is None else e.cuda(), want_sum=True)
+    sd = a.double().cpu() + (r.double().cpu() if with_r else 0.0)
+    ref = torch.nn.functional.layer_norm(sd, (C,), w.double(), b.double(), 1e-5)
+    assert rel_err(y, ref) < (2e-6 if dtype == torch.float32 else 5e-3)
+    assert rel_err(s, sd + (e.double() if with_e else 0.0)) < (1e-6 if dtype == torch.float32 else 5e-3)
+
+
 # ------------------------------------------------------------------------------------ swin block
 def swin_params(name):
     dim, res, heads, ws, shift, lin, B = SWIN_CASES[name]
