@@ -151,6 +151,14 @@ int sodt_nms(const float* pred, const int* classes, int n_classes, float* out, i
              float conf_thres, double iou_thres, int multi_label, int agnostic, int merge, int redundant,
              int max_det, int max_nms, float max_wh, void* stream);
 
+/*
+ * Head glue: nearest-neighbour 2x upsample of `low` [B,H,W,C1] concatenated with `skip` [B,2H,2W,C2] on the
+ * channel axis, channels-last memory, one pass.  Replaces nn.Upsample(None, 2, 'nearest') + Concat(1) of the
+ * detector head (models/model.yaml head rows 1-2 and 5-6).  C1*elem_bytes and C2*elem_bytes multiples of 16.
+ */
+int sodt_upsample2x_concat_nhwc(const void* low, const void* skip, void* out, int B, int H, int W, int C1, int C2,
+                                int elem_bytes, void* stream);
+
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 long long sodt_launch_count(void);

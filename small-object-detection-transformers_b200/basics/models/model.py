@@ -182,11 +182,11 @@ class Model(nn.Module):
 
     def _initialize_biases(self, cf=None):
         det = self.detect[-1]
-        for conv, s in zip(det.m, det.stride):
-            b = conv.bias.view(det.na, -1)
-            b.data[:, 4] += math.log(8 / (640 / s) ** 2)
-            b.data[:, 5:] += math.log(0.6 / (det.nc - 0.99)) if cf is None else torch.log(cf / cf.sum())
-            conv.bias = nn.Parameter(b.view(-1), requires_grad=True)
+        with torch.no_grad():
+            for conv, s in zip(det.m, det.stride):
+                b = conv.bias.view(det.na, -1)        # in-place view: objectness and class priors (arXiv 1708.02002, 3.3)
+                b[:, 4] += math.log(8 / (640 / float(s)) ** 2)
+                b[:, 5:] += math.log(0.6 / (det.nc - 0.99)) if cf is None else torch.log(cf / cf.sum())
 
     def _stem(self, x, ir, input_mode):
         if input_mode == "RGB+IR":
@@ -210,11 +210,26 @@ class Model(nn.Module):
 
     def forward_once(self, x, string="yolo", profile=False):
         y = list(self.image_encoder(x))
-        for m in self.detect:
+        mods = list(self.detect)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            if (isinstance(m, nn.Upsample) and m.f == -1 and isinstance(nxt, Concat) and nxt.d == 1 and m.mode == "nearest"
+                    and m.scale_factor in (2, 2.0) and isinstance(nxt.f, list) and len(nxt.f) == 2 and nxt.f[0] == -1
+                    and x.is_cuda and (x.shape[1] * x.element_size()) % 16 == 0
+                    and (y[nxt.f[1]].shape[1] * x.element_size()) % 16 == 0):
+                # nn.Upsample(2, nearest) + Concat([-1, k]) in one pass; the upsampled tensor itself is not kept
+                x = ops.upsample2x_concat(x, y[nxt.f[1]])
+                y.append(None)
+                y.append(x)
+                i += 2
+                continue
             if m.f != -1:
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
             x = m(x)
             y.append(x)
+            i += 1
         return x, y
 
     def fuse(self):

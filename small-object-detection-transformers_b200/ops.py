@@ -223,6 +223,25 @@ def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=No
     return z, xp
 
 
+# ------------------------------------------------------------------- head glue: upsample + concat
+def upsample2x_concat(low, skip):
+    """cat([nearest_upsample_2x(low), skip], dim=1) for NCHW-shaped tensors in channels-last memory.
+    Returns an NCHW-shaped channels-last tensor.  See sodt_upsample2x_concat_nhwc."""
+    _require_cuda(low, skip)
+    B, C1, H, W = low.shape
+    B2, C2, H2, W2 = skip.shape
+    if (B2, H2, W2) != (B, 2 * H, 2 * W) or low.dtype != skip.dtype:
+        raise ValueError("skip must be [B, C2, 2H, 2W] with the dtype of low")
+    lo = low.permute(0, 2, 3, 1).contiguous()     # no copy when already channels-last
+    sk = skip.permute(0, 2, 3, 1).contiguous()
+    out = torch.empty((B, H2, W2, C1 + C2), dtype=low.dtype, device=low.device)
+    with torch.cuda.device(low.device), _Timed(f"upsample2x_concat[B={B},H={H},W={W},C1={C1},C2={C2}]"):
+        st = _capi.lib().sodt_upsample2x_concat_nhwc(lo.data_ptr(), sk.data_ptr(), out.data_ptr(), B, H, W, C1, C2,
+                                                     low.element_size(), _stream())
+    _capi.check(st, "sodt_upsample2x_concat_nhwc")
+    return out.permute(0, 3, 1, 2)
+
+
 # ------------------------------------------------------------------------------------------- NMS
 _workspaces = {}
 

@@ -72,7 +72,8 @@ class Detector:
         model = Model(cfg, input_mode="RGB+IR", ch_steam=3, ch=128, nc=nc)
         if state_dict is not None:
             model.load_state_dict(state_dict, strict=False)
-        self.model = model.eval().to(self.device, dtype)
+        # like the reference's inference loader (models/experimental.py:118-120): fold BatchNorm into the convs
+        self.model = model.eval().fuse().to(self.device, dtype)
         self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._bufs = {}
 

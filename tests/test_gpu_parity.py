@@ -203,6 +203,28 @@ def test_cattn_block_shifted_vs_oracle(C, heads, ws, shift, dtype):
     assert rel_err(out, ref) < TOL[dtype]
 
 
+# ------------------------------------------------------------------------ head glue
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_upsample2x_concat_vs_torch(dtype):
+    low = fx.det_input("up:low", (2, 16, 5, 7)).to("cuda", dtype).contiguous(memory_format=torch.channels_last)
+    skip = fx.det_input("up:skip", (2, 24, 10, 14)).to("cuda", dtype)
+    out = ops().upsample2x_concat(low, skip)
+    ref = torch.cat((torch.nn.functional.interpolate(low, scale_factor=2, mode="nearest"), skip), 1)
+    assert out.shape == ref.shape and torch.equal(out, ref)
+
+
+def test_fused_model_matches_unfused():
+    """Model.fuse() (Conv+BN folding, reference model.py:317-325) must not change the predictions."""
+    from sodt_b200.basics.models.model import Model
+    m = load_det_weights(Model(YAML, input_mode="RGB+IR", ch_steam=3, ch=128, nc=8)).eval().cuda()
+    rgb = fx.det_input("model:rgb", (1, 3, 512, 512), kind="uniform").cuda()
+    ir = fx.det_input("model:ir", (1, 3, 512, 512), kind="uniform").cuda()
+    with torch.no_grad():
+        p0 = m(rgb, ir, "RGB+IR")[0]
+        p1 = m.fuse()(rgb, ir, "RGB+IR")[0]
+    assert rel_err(p1, p0) < 1e-5
+
+
 # ---------------------------------------------------------------------------------------- Detect
 @pytest.mark.parametrize("memory_format", ["nchw", "channels_last"])
 def test_detect_module_vs_reference_golden(golden, memory_format):
