@@ -152,6 +152,16 @@ int sodt_nms(const float* pred, const int* classes, int n_classes, float* out, i
              int max_det, int max_nms, float max_wh, void* stream);
 
 /*
+ * Fused bias + activation (+ crop) on channels-last activations: out[b,y,x,c] = act(in[b, y+off_y, x+off_x, c] + bias[c]),
+ * act: 0 identity, 1 exact (erf) GELU, 2 SiLU.  in is [B, in_H, in_W, C], out [B, H, W, C], bias [C] fp32.
+ * Replaces, after the 2x2 conv of the conv-enhanced MLP (backbone_vit.py:896-902), the F.pad copy, the conv's separate
+ * bias-add pass and the GELU pass (the conv runs with padding 1 and no bias; row / column 0 are cropped here); also the
+ * bias + SiLU of the head's fused Conv (common.py:38-50).  C multiple of 8 (bf16) / 4 (fp32).
+ */
+int sodt_bias_act_crop_nhwc(const void* in, const float* bias, void* out, int B, int H, int W, int C,
+                            int in_H, int in_W, int off_y, int off_x, int act, int dtype, void* stream);
+
+/*
  * Head glue: nearest-neighbour 2x upsample of `low` [B,H,W,C1] concatenated with `skip` [B,2H,2W,C2] on the
  * channel axis, channels-last memory, one pass.  Replaces nn.Upsample(None, 2, 'nearest') + Concat(1) of the
  * detector head (models/model.yaml head rows 1-2 and 5-6).  C1*elem_bytes and C2*elem_bytes multiples of 16.

@@ -8,6 +8,7 @@ import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 
 def autopad(k, p=None):
@@ -30,7 +31,13 @@ class Conv(nn.Module):
         return self.act(self.bn(self.conv(x)))
 
     def fuseforward(self, x):
-        return self.act(self.conv(x))
+        conv = self.conv
+        if (x.is_cuda and isinstance(self.act, nn.SiLU) and conv.bias is not None and conv.out_channels % 8 == 0
+                and x.dtype in (torch.float32, torch.bfloat16)):
+            from ... import ops
+            y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+            return ops.bias_act_crop(y, conv.bias, "silu").permute(0, 3, 1, 2)   # bias + SiLU in one pass
+        return self.act(conv(x))
 
 
 def DWConv(c1, c2, k=1, s=1, act=True):

@@ -232,6 +232,7 @@ class Model(nn.Module):
             i += 1
         return x, y
 
+    @torch.no_grad()
     def fuse(self):
         for m in self.modules():
             if type(m) is Conv and hasattr(m, "bn"):

@@ -153,6 +153,23 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// Same, with a 128-bit "disable output lane" mask: TMEM lanes (accumulator rows) whose bit is set keep their old value.
+__device__ __forceinline__ void mma_ss_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate,
+                                              uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts_masked(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, bool accumulate,
+                                              uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+        : "memory");
+}
 // Arrives on the mbarrier when all tcgen05.mma issued so far by this thread have completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

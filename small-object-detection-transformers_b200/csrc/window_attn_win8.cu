@@ -1,20 +1,23 @@
 // 8x8-window attention (N = 64 tokens, head_dim 16 or 32) on tcgen05 tensor cores: the kernel of the
 // backbone's stage 1 and stage 2 (basics/models/backbone_vit.py:114-145; shift 0 or any 0 < shift < 8).
 //
-// A tile is a PAIR of windows (128 query rows): per head
-//   S[128x128] = Q_pair K_pair^T   tcgen05.mma SS (K-major operands) -> TMEM; only the two diagonal 64x64
-//                                  blocks are meaningful and only they are read back
-//   softmax                        one thread per query row: tcgen05.ld of its 64 useful scores, relative
-//                                  position bias (closed-form index, bank-conflict-free padded table in shared
-//                                  memory), shifted-window mask evaluated from region bit masks, exp2, row sum;
-//                                  P written to TMEM as packed bf16 (off-diagonal blocks stay zero)
-//   O[128xhd] = P V_pair           tcgen05.mma TS (A = P from TMEM, B = V MN-major), K = 128 keys
+// A tile is a PAIR of windows (128 query rows = 128 TMEM lanes).  Per head
+//   S[128x64]                      rows 0-63 = Q_w0 K_w0^T, rows 64-127 = Q_w1 K_w1^T: two tcgen05.mma (M=128, N=64) whose
+//                                  "disable output lane" masks let each write only its window's 64 lanes, so the score
+//                                  buffer holds no wasted off-diagonal block (64 TMEM columns per head in flight)
+//   softmax                        one thread per query row: tcgen05.ld of its 64 scores, relative position bias
+//                                  (closed-form index, bank-conflict-free padded table in shared memory), shifted-window
+//                                  mask from two 64-bit region masks (border windows only), exp2, row sum; P written
+//                                  back to TMEM as packed bf16 (32 columns)
+//   O[128xhd]                      = P V, again two lane-masked MMAs (TS: A = P from TMEM, B = V MN-major), K = 64 keys
 //   epilogue                       O / rowsum -> bf16 -> straight to the un-rolled, un-partitioned output image
 // Roll, partition, reverse partition and reverse roll are address arithmetic in the producer / epilogue.
 //
-// Persistent CTAs (one per SM), 10 warps: warps 0-3 and 4-7 are two softmax groups that take even / odd heads
-// (each with its own S, P and O buffers in TMEM, so one group's softmax overlaps the other's MMAs), warp 8
-// streams q/k/v of G heads at a time through a 3-stage cp.async ring, warp 9 issues the MMAs.
+// Persistent CTAs (one per SM), 12 warps: NG = 2 softmax groups of 4 warps take heads round-robin, each with its own
+// S / P / O columns in TMEM (64 + 32 + 32 columns per group), so one group's TMEM / shared-memory / MUFU latencies
+// are covered by the other (measured: NG = 3 or 4 is not faster, the per-head barrier hand-offs dominate); three producer warps (q, k, v) stream 64 channels
+// (4 or 2 heads) per stage through a 4-stage cp.async ring; one warp issues the MMAs (a tcgen05.mma of these shapes
+// occupies the tensor pipe ~64 cycles whatever N is: ten MMAs per head make the issue stream a first-order cost).
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -26,13 +29,17 @@ using namespace tc;
 constexpr int WS = 8;
 constexpr int NTOK = 64;                 // tokens per window
 constexpr int ROWS = 128;                // rows per tile = 2 windows
-constexpr int NTHREADS = 320;
-constexpr int STAGES = 3;
+constexpr int NG = 2;                    // softmax groups (heads in flight)
+constexpr int NPROD = 3;                 // producer warps: one each for q, k, v
+constexpr int NTHREADS = (NG * 4 + 1 + NPROD) * 32;
+constexpr int MMA_WARP = NG * 4, PRODUCER_WARP0 = NG * 4 + 1;
+constexpr int STAGES = 4;
 constexpr int STAGE_BYTES = 3 * ROWS * 128;   // q,k,v x 128 tokens x 128 B (= G heads x hd x 2 B)
 constexpr int CHUNK_STRIDE = ROWS * 16;       // bytes between 8-element chunks of a canonical tile
 constexpr int TAB_LD = 40;                    // padded row stride of the bias table (bank-conflict free)
 constexpr int TAB_ENTRIES = (2 * WS - 1) * TAB_LD;   // 600 floats per head
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint32_t TM_S = 0, TM_P = 256, TM_O = 384;   // TMEM column bases: S[g] = g*64, P[g] = 256+g*32, O[g] = 384+g*32
 
 // [heads][15][40] bias table, scaled by log2(e):  tab[h][(dy+7)*40 + (dx+7)]
 __global__ void prep_table_win8_kernel(const float* __restrict__ table, float* __restrict__ out, int heads) {
@@ -66,7 +73,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     constexpr int CPH = HD / 8;               // 16-byte chunks per head row
     constexpr int TILE_BYTES = ROWS * HD * 2; // one (q|k|v, head) tile
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ uint64_t stage_full[STAGES], stage_empty[STAGES], s_full[2], s_free[2], p_full[2], pv_done[2];
+    __shared__ uint64_t stage_full[STAGES], stage_empty[STAGES], s_full[NG], s_free[NG], p_full[NG], pv_done[NG];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -74,24 +81,27 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     float* tab = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
     const int C3 = 3 * C;
     const int groups = heads / G;
+    long long my_tiles = 0;
+    if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const long long n_total = my_tiles * heads;      // heads this CTA processes, in order n = tile_iter*heads + h
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&stage_full[s], 32); mbar_init(&stage_empty[s], 1); }
-        for (int p = 0; p < 2; ++p) { mbar_init(&s_full[p], 1); mbar_init(&s_free[p], ROWS); mbar_init(&p_full[p], ROWS); mbar_init(&pv_done[p], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&stage_full[s], 32 * NPROD); mbar_init(&stage_empty[s], 1); }
+        for (int g = 0; g < NG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], ROWS); mbar_init(&p_full[g], ROWS); mbar_init(&pv_done[g], 1); }
         fence_barrier_init();
     }
-    if (warp == 9) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+    if (warp == MMA_WARP) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
     for (int e = tid; e < heads * TAB_ENTRIES; e += NTHREADS) tab[e] = table_p[e];
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tm = tmem_slot;
-    // TMEM columns: S[p] = p*128 (128 cols), P[p] = 256 + p*64 (64 cols), O[p] = 384 + p*32 (HD cols)
-
-    if (warp == 8) {
-        // ================================================================ producer
+    if (warp >= PRODUCER_WARP0) {
+        // ===================================== producers: warp `which` streams q (0), k (1) or v (2) of every stage
+        // (one cp.async warp sustains only ~8 B/clk; three keep the ring ahead of the MMAs)
+        const int which = warp - PRODUCER_WARP0;
         const int tsub = lane & 7, csub = lane >> 3;
-        long long gseq = 0;
+        int stage = 0, round = 0;
         uint64_t* pending = nullptr;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             long long tok[16];
@@ -99,105 +109,105 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
             for (int oct = 0; oct < 16; ++oct) {
                 long long wdx = 2 * tile + (oct >> 3);
                 if (wdx >= geo.total_windows) wdx = 2 * tile;      // odd tail: duplicate the first window
-                tok[oct] = geo.token(wdx, oct & 7, tsub) * C3;
+                tok[oct] = geo.token(wdx, oct & 7, tsub) * C3 + which * C;
             }
-            for (int gi = 0; gi < groups; ++gi, ++gseq) {
-                const int s = (int)(gseq % STAGES);
-                if (gseq >= STAGES) mbar_wait(&stage_empty[s], (uint32_t)((gseq / STAGES - 1) & 1));
-                const uint32_t st = sbase + s * STAGE_BYTES;
+            for (int gi = 0; gi < groups; ++gi) {
+                if (round > 0) mbar_wait(&stage_empty[stage], (uint32_t)((round - 1) & 1));
+                const uint32_t st = sbase + stage * STAGE_BYTES + which * G * TILE_BYTES + tsub * 16;
 #pragma unroll
-                for (int which = 0; which < 3; ++which) {
-                    const int col = which * C + gi * 64;
+                for (int oct = 0; oct < 16; ++oct) {
+                    const __nv_bfloat16* src = qkv + tok[oct] + gi * 64;
 #pragma unroll
-                    for (int oct = 0; oct < 16; ++oct) {
-                        const __nv_bfloat16* src = qkv + tok[oct] + col;
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const int j = csub + 4 * half;          // chunk 0..7 of the 128-byte segment
-                            const int g = j / CPH, c = j % CPH;     // head in group, chunk in head
-                            cp_async16(st + (which * G + g) * TILE_BYTES + c * CHUNK_STRIDE + (oct * 8 + tsub) * 16, src + j * 8);
-                        }
+                    for (int half = 0; half < 2; ++half) {
+                        const int j = csub + 4 * half;              // chunk 0..7 of the 128-byte segment
+                        const int g = j / CPH, c = j % CPH;         // head in group, chunk in head
+                        cp_async16(st + g * TILE_BYTES + c * CHUNK_STRIDE + oct * 128, src + j * 8);
                     }
                 }
                 cp_async_commit();
                 if (pending) { cp_async_wait<1>(); fence_proxy_async(); mbar_arrive(pending); }
-                pending = &stage_full[s];
+                pending = &stage_full[stage];
+                if (++stage == STAGES) { stage = 0; ++round; }
             }
         }
         if (pending) { cp_async_wait<0>(); fence_proxy_async(); mbar_arrive(pending); }
-    } else if (warp == 9) {
+    } else if (warp == MMA_WARP) {
         // =============================================================== MMA issuer
+        // One thread; its instruction stream is kept short: all counters are 32-bit and incremental (no divisions),
+        // descriptors are a per-tile base plus compile-time constants.
         if (lane == 0) {
-            constexpr uint32_t idesc_s = idesc_bf16(ROWS, ROWS, false, false);
+            constexpr uint32_t idesc_s = idesc_bf16(ROWS, NTOK, false, false);
             constexpr uint32_t idesc_o = idesc_bf16(ROWS, HD, false, true);
-            long long my_tiles = 0;
-            for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++my_tiles;
-            const long long n_total = my_tiles * heads;
-            auto issue_qk = [&](long long n) {
-                const long long gq = n / G;
-                const int hg = (int)(n - gq * G), s = (int)(gq % STAGES);
-                if (hg == 0) mbar_wait(&stage_full[s], (uint32_t)((gq / STAGES) & 1));
-                const int p = (int)(n & 1);
-                const long long k = n >> 1;
-                if (k > 0) mbar_wait(&s_free[p], (uint32_t)((k - 1) & 1));
-                fence_proxy_async();
+            constexpr uint32_t ALL = 0xFFFFFFFFu;
+            const uint64_t kdesc0 = smem_desc(sbase, CHUNK_STRIDE, 128);      // K-major tiles (Q, K)
+            const uint64_t vdesc0 = smem_desc(sbase, 128, CHUNK_STRIDE);      // MN-major tile (V)
+            const int nt = (int)n_total;
+            // ---- cursor of the next QK to issue
+            int qn = 0, q_hg = 0, q_stage = 0, q_stage_par = 0, q_g = 0, q_k = 0;
+            auto issue_qk = [&]() {
+                if (q_hg == 0) mbar_wait(&stage_full[q_stage], (uint32_t)q_stage_par);
+                if (q_k > 0) mbar_wait(&s_free[q_g], (uint32_t)((q_k - 1) & 1));
                 fence_after_sync();
-                const uint32_t qt = sbase + s * STAGE_BYTES + (0 * G + hg) * TILE_BYTES;
-                const uint32_t kt = sbase + s * STAGE_BYTES + (1 * G + hg) * TILE_BYTES;
+                const uint32_t toff = (uint32_t)(q_stage * STAGE_BYTES + q_hg * TILE_BYTES) >> 4;
+                const uint64_t qd = kdesc0 + toff, kd = kdesc0 + toff + ((G * TILE_BYTES) >> 4);
+                const uint32_t d = tm + TM_S + q_g * 64;
 #pragma unroll
                 for (int ks = 0; ks < HD / 16; ++ks)
-                    mma_ss(tm + p * 128, smem_desc(qt + ks * 2 * CHUNK_STRIDE, CHUNK_STRIDE, 128),
-                           smem_desc(kt + ks * 2 * CHUNK_STRIDE, CHUNK_STRIDE, 128), idesc_s, ks > 0);
-                mma_commit(&s_full[p]);
-            };
-            if (n_total > 0) issue_qk(0);
-            if (n_total > 1) issue_qk(1);
-            for (long long n = 0; n < n_total; ++n) {
-                const int p = (int)(n & 1);
-                const long long k = n >> 1, gq = n / G;
-                const int hg = (int)(n - gq * G), s = (int)(gq % STAGES);
-                // S[p] is free as soon as softmax(n) has copied it to registers (early in its work), so the
-                // scores of the group's next head are computed while softmax(n) is still running
-                if (n + 2 < n_total) issue_qk(n + 2);
-                mbar_wait(&p_full[p], (uint32_t)(k & 1));
-                fence_after_sync();
-                const uint32_t vt = sbase + s * STAGE_BYTES + (2 * G + hg) * TILE_BYTES;
+                    mma_ss_masked(d, qd + ((ks * 2 * CHUNK_STRIDE) >> 4), kd + ((ks * 2 * CHUNK_STRIDE) >> 4), idesc_s, ks > 0, 0u, 0u, ALL, ALL);
 #pragma unroll
-                for (int ks = 0; ks < ROWS / 16; ++ks)
-                    mma_ts(tm + 384 + p * 32, tm + 256 + p * 64 + ks * 8, smem_desc(vt + ks * 256, 128, CHUNK_STRIDE), idesc_o, ks > 0);
-                mma_commit(&pv_done[p]);
-                if (hg == G - 1) mma_commit(&stage_empty[s]);
+                for (int ks = 0; ks < HD / 16; ++ks)
+                    mma_ss_masked(d, qd + ((ks * 2 * CHUNK_STRIDE) >> 4), kd + ((NTOK * 16 + ks * 2 * CHUNK_STRIDE) >> 4), idesc_s, ks > 0,
+                                  ALL, ALL, 0u, 0u);
+                mma_commit(&s_full[q_g]);
+                ++qn;
+                if (++q_hg == G) { q_hg = 0; if (++q_stage == STAGES) { q_stage = 0; q_stage_par ^= 1; } }
+                if (++q_g == NG) { q_g = 0; ++q_k; }
+            };
+            for (int i = 0; i < NG && i < nt; ++i) issue_qk();
+            int hg = 0, stage = 0, g = 0, k = 0;
+            for (int n = 0; n < nt; ++n) {
+                // S[g] is free as soon as softmax(n) has copied it to registers, so the group's next scores are
+                // computed while softmax(n) is still running
+                if (qn < nt) issue_qk();
+                mbar_wait(&p_full[g], (uint32_t)(k & 1));
+                fence_after_sync();
+                const uint64_t vd = vdesc0 + ((uint32_t)(stage * STAGE_BYTES + (2 * G + hg) * TILE_BYTES) >> 4);
+                const uint32_t d = tm + TM_O + g * 32, a = tm + TM_P + g * 32;
+#pragma unroll
+                for (int ks = 0; ks < NTOK / 16; ++ks)
+                    mma_ts_masked(d, a + ks * 8, vd + ((ks * 256) >> 4), idesc_o, ks > 0, 0u, 0u, ALL, ALL);
+#pragma unroll
+                for (int ks = 0; ks < NTOK / 16; ++ks)
+                    mma_ts_masked(d, a + ks * 8, vd + ((NTOK * 16 + ks * 256) >> 4), idesc_o, ks > 0, ALL, ALL, 0u, 0u);
+                mma_commit(&pv_done[g]);
+                if (++hg == G) { hg = 0; mma_commit(&stage_empty[stage]); if (++stage == STAGES) stage = 0; }
+                if (++g == NG) { g = 0; ++k; }
             }
         }
     } else {
         // ====================================================== softmax + epilogue groups
-        const int p = warp >> 2;                       // group 0: even heads, group 1: odd heads
+        const int g = warp >> 2;                       // group g takes heads n = g, g + NG, ...
         const int row = tid & 127;                     // TMEM lane == query row of the pair
         const int wh = row >> 6, ti = row & 63, ty = ti >> 3, tx = ti & 7;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tS = tm + p * 128 + wh * 64 + lane_addr;
-        const uint32_t tP = tm + 256 + p * 64 + wh * 32 + lane_addr;
-        const uint32_t tO = tm + 384 + p * 32 + lane_addr;
-        {   // the off-diagonal half of P stays zero for the whole kernel
-            uint32_t z[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) z[j] = 0u;
-            tmem_st32(tm + 256 + p * 64 + (wh ^ 1) * 32 + lane_addr, z);
-            tmem_wait_st();
-        }
+        const uint32_t tS = tm + TM_S + g * 64 + lane_addr;
+        const uint32_t tP = tm + TM_P + g * 32 + lane_addr;
+        const uint32_t tO = tm + TM_O + g * 32 + lane_addr;
         const float c = scale * LOG2E, mv2 = mask_value * LOG2E;
         const float* tab_row = tab + (ty + WS - 1) * TAB_LD + (tx + WS - 1);
         const int s_ = geo.shift;
         const uint64_t yhi = s_ > 0 ? (~0ull << (8 * (WS - s_))) : 0ull;                       // keys with ty >= ws - shift
         const uint64_t xhi = s_ > 0 ? 0x0101010101010101ull * (uint64_t)((0xFFu << (WS - s_)) & 0xFFu) : 0ull;  // tx >= ws - shift
         const int nwh = geo.nW / geo.nww;
-        long long k = 0;
+        long long k = 0, cur_iter = -1;
+        __nv_bfloat16* out_tok = nullptr;
+        uint64_t mbits = 0;
+        bool any_mask = false;
         __nv_bfloat16* prev_dst = nullptr;
         float prev_inv = 0.f;
         auto epilogue = [&](__nv_bfloat16* dst, float inv) {
             uint32_t o[HD];
-            if constexpr (HD == 16) { uint32_t (&o16)[16] = reinterpret_cast<uint32_t (&)[16]>(o); tmem_ld16(tO, o16); }
-            else { uint32_t (&o32)[32] = reinterpret_cast<uint32_t (&)[32]>(o); tmem_ld32(tO, o32); }
+            if constexpr (HD == 16) tmem_ld16(tO, o); else tmem_ld32(tO, o);
             tmem_wait_ld();
             if (dst != nullptr) {
 #pragma unroll
@@ -211,74 +221,83 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                 }
             }
         };
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long long wdx = 2 * tile + wh;
-            const bool valid = wdx < geo.total_windows;
-            __nv_bfloat16* out_tok = nullptr;
-            uint64_t mbits = 0;
-            if (valid) {
-                out_tok = out + geo.token(wdx, ty, tx) * C;
-                if (s_ > 0) {
-                    const int win = (int)(wdx % geo.nW);
-                    const int wy = win / geo.nww, wx = win - wy * geo.nww;
-                    if (wy == nwh - 1) mbits |= (ty >= WS - s_) ? ~yhi : yhi;
-                    if (wx == geo.nww - 1) mbits |= (tx >= WS - s_) ? ~xhi : xhi;
+        int h = g;                                      // head of the current pair; (it, h) advance without divisions
+        long long it = 0;
+        while (h >= heads) { h -= heads; ++it; }
+        for (long long n = g; n < n_total; n += NG, ++k) {
+            if (it != cur_iter) {                      // new window pair: output row pointer and shifted-window mask bits
+                cur_iter = it;
+                const long long wdx = 2 * ((long long)blockIdx.x + it * gridDim.x) + wh;
+                out_tok = nullptr;
+                mbits = 0;
+                if (wdx < geo.total_windows) {
+                    out_tok = out + geo.token(wdx, ty, tx) * C;
+                    if (s_ > 0) {
+                        const int win = (int)(wdx % geo.nW);
+                        const int wy = win / geo.nww, wx = win - wy * geo.nww;
+                        if (wy == nwh - 1) mbits |= (ty >= WS - s_) ? ~yhi : yhi;
+                        if (wx == geo.nww - 1) mbits |= (tx >= WS - s_) ? ~xhi : xhi;
+                    }
                 }
+                any_mask = __any_sync(0xffffffffu, mbits != 0);
             }
-            const bool any_mask = __any_sync(0xffffffffu, mbits != 0);
-            for (int h = p; h < heads; h += 2, ++k) {
-                mbar_wait(&s_full[p], (uint32_t)(k & 1));
+            mbar_wait(&s_full[g], (uint32_t)(k & 1));
+            fence_after_sync();
+            float s2[NTOK];
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(tS, r0);
+                tmem_ld32(tS + 32, r1);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { s2[j] = __uint_as_float(r0[j]); s2[32 + j] = __uint_as_float(r1[j]); }
+            }
+            fence_before_sync();
+            mbar_arrive(&s_free[g]);
+            const float* tb = tab_row + h * TAB_ENTRIES;
+#pragma unroll
+            for (int j = 0; j < NTOK; ++j) s2[j] = fmaf(s2[j], c, tb[-((j >> 3) * TAB_LD + (j & 7))]);
+            if (any_mask) {                            // warp-uniform: only windows of the last window row / column
+#pragma unroll
+                for (int j = 0; j < NTOK; ++j)
+                    if ((mbits >> j) & 1ull) s2[j] += mv2;
+            }
+            float mx = s2[0];
+#pragma unroll
+            for (int j = 1; j < NTOK; ++j) mx = fmaxf(mx, s2[j]);
+            float sum = 0.f;
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < NTOK; j += 2) {
+                const float p0 = fast_exp2(s2[j] - mx), p1 = fast_exp2(s2[j + 1] - mx);
+                sum += p0 + p1;
+                pk[j >> 1] = pack_bf16(p0, p1);
+            }
+            if (k > 0) {                               // previous head of this group: its P / O columns are free again
+                mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
                 fence_after_sync();
-                float s2[NTOK];
-                {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tS, r0);
-                    tmem_ld32(tS + 32, r1);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) { s2[j] = __uint_as_float(r0[j]); s2[32 + j] = __uint_as_float(r1[j]); }
-                }
-                fence_before_sync();
-                mbar_arrive(&s_free[p]);
-                const float* tb = tab_row + h * TAB_ENTRIES;
-                float mx = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < NTOK; ++j) {
-                    s2[j] = fmaf(s2[j], c, tb[-((j >> 3) * TAB_LD + (j & 7))]);
-                    if (any_mask && ((mbits >> j) & 1ull)) s2[j] += mv2;
-                    mx = fmaxf(mx, s2[j]);
-                }
-                float sum = 0.f;
-                uint32_t pk[32];
-#pragma unroll
-                for (int j = 0; j < NTOK; j += 2) {
-                    const float p0 = fast_exp2(s2[j] - mx), p1 = fast_exp2(s2[j + 1] - mx);
-                    sum += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
-                }
-                if (k > 0) {                                   // previous head of this group: P / O buffers free again
-                    mbar_wait(&pv_done[p], (uint32_t)((k - 1) & 1));
-                    fence_after_sync();
-                    epilogue(prev_dst, prev_inv);
-                }
-                tmem_st32(tP, pk);
-                tmem_wait_st();
-                fence_before_sync();
-                mbar_arrive(&p_full[p]);
-                prev_dst = valid ? out_tok + h * HD : nullptr;
-                prev_inv = 1.f / sum;
+                epilogue(prev_dst, prev_inv);
             }
+            tmem_st32(tP, pk);
+            tmem_wait_st();
+            fence_before_sync();
+            mbar_arrive(&p_full[g]);
+            prev_dst = out_tok ? out_tok + h * HD : nullptr;
+            prev_inv = 1.f / sum;
+            h += NG;
+            while (h >= heads) { h -= heads; ++it; }
         }
         if (k > 0) {
-            mbar_wait(&pv_done[p], (uint32_t)((k - 1) & 1));
+            mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
             fence_after_sync();
             epilogue(prev_dst, prev_inv);
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_slot, 512);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_slot, 512);
 }
+
 
 }  // namespace
 
@@ -289,8 +308,8 @@ bool window_attn_win8_supported(int H, int W, int C, int heads, int ws, int shif
     const int hd = C / heads;
     if (hd != 16 && hd != 32) return false;
     const int G = 64 / hd;
-    if (heads % G || heads % 2) return false;
-    return STAGES * STAGE_BYTES + (size_t)heads * TAB_ENTRIES * sizeof(float) <= 220 * 1024;
+    if (heads % G) return false;
+    return STAGES * STAGE_BYTES + (size_t)heads * TAB_ENTRIES * sizeof(float) <= 227 * 1024 - 2048;
 }
 
 int window_attn_win8(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,

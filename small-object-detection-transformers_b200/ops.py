@@ -223,6 +223,28 @@ def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=No
     return z, xp
 
 
+# ------------------------------------------------------------------- fused bias + activation (+ crop)
+_ACT = {None: 0, "none": 0, "gelu": 1, "silu": 2}
+
+
+def bias_act_crop(x_nchw, bias, act, out_hw=None, offset=(0, 0)):
+    """x: NCHW-shaped tensor in channels-last memory.  Returns act(x[:, :, oy:oy+H, ox:ox+W] + bias) as a contiguous
+    [B, H, W, C] tensor.  See sodt_bias_act_crop_nhwc."""
+    _require_cuda(x_nchw, bias)
+    if x_nchw.dtype not in _DT:
+        raise TypeError(f"unsupported dtype {x_nchw.dtype}")
+    B, C, inH, inW = x_nchw.shape
+    H, W = out_hw if out_hw is not None else (inH - offset[0], inW - offset[1])
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()        # no copy when the tensor is channels-last
+    out = torch.empty((B, H, W, C), dtype=x.dtype, device=x.device)
+    b32 = _as_f32(bias)
+    with torch.cuda.device(x.device), _Timed(f"bias_act_crop[B={B},H={H},W={W},C={C},act={act}]"):
+        st = _capi.lib().sodt_bias_act_crop_nhwc(x.data_ptr(), b32.data_ptr(), out.data_ptr(), B, H, W, C, inH, inW,
+                                                 offset[0], offset[1], _ACT[act], _DT[x.dtype], _stream())
+    _capi.check(st, "sodt_bias_act_crop_nhwc")
+    return out
+
+
 # ------------------------------------------------------------------- head glue: upsample + concat
 def upsample2x_concat(low, skip):
     """cat([nearest_upsample_2x(low), skip], dim=1) for NCHW-shaped tensors in channels-last memory.

@@ -63,6 +63,156 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* Q, const __nv_
     }
     for (int j = 0; j < 128; ++j) S_out[tid * 128 + j] = srow[j];
     if (variant == 1) goto done;
+    if (variant == 7) {
+        // T7: TMEM load / store throughput, all 4 warps (128 lanes) concurrently
+        __syncthreads();
+        long long t0 = clock64();
+        uint32_t acc = 0;
+        for (int i = 0; i < 64; ++i) {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(tm + lane_base + ((i & 1) * 64), r0);
+            tmem_ld32(tm + lane_base + ((i & 1) * 64) + 32, r1);
+            tmem_wait_ld();
+            for (int j = 0; j < 32; ++j) acc ^= r0[j] ^ r1[j];
+        }
+        long long t1 = clock64();
+        if (tid == 0) printf("LDTM: 128 lanes x 64 cols (32 KB) per iteration: %6.1f cycles  -> %5.1f B/cycle/SM (acc %u)\n",
+                             (double)(t1 - t0) / 64, 32768.0 * 64 / (double)(t1 - t0), acc & 1);
+        __syncthreads();
+        t0 = clock64();
+        for (int i = 0; i < 64; ++i) {
+            uint32_t r0[32];
+            for (int j = 0; j < 32; ++j) r0[j] = acc + j + i;
+            tmem_st32(tm + lane_base + 256 + ((i & 1) * 32), r0);
+            tmem_wait_st();
+        }
+        t1 = clock64();
+        if (tid == 0) printf("STTM: 128 lanes x 32 cols (16 KB) per iteration: %6.1f cycles  -> %5.1f B/cycle/SM\n",
+                             (double)(t1 - t0) / 64, 16384.0 * 64 / (double)(t1 - t0));
+        // one warp only
+        __syncthreads();
+        if (warp == 0) {
+            t0 = clock64();
+            for (int i = 0; i < 64; ++i) {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(tm + ((i & 1) * 64), r0);
+                tmem_ld32(tm + ((i & 1) * 64) + 32, r1);
+                tmem_wait_ld();
+                for (int j = 0; j < 32; ++j) acc ^= r0[j] ^ r1[j];
+            }
+            t1 = clock64();
+            if (tid == 0) printf("LDTM one warp: 32 lanes x 64 cols (8 KB): %6.1f cycles -> %5.1f B/cycle (acc %u)\n",
+                                 (double)(t1 - t0) / 64, 8192.0 * 64 / (double)(t1 - t0), acc & 1);
+        }
+        __syncthreads();
+        goto done;
+    }
+    if (variant == 6) {
+        // T6: issue-rate microbenchmark: cycles per tcgen05.mma for the shapes the window kernel uses
+        __syncthreads();
+        if (tid == 0) {
+            const int REP = 512;
+            long long t0, t1;
+            const uint32_t ids = idesc_bf16(128, 64, false, false), ido16 = idesc_bf16(128, 16, false, true),
+                           ido32 = idesc_bf16(128, 32, false, true), ids128 = idesc_bf16(128, 128, false, false);
+            uint64_t a = smem_desc(smem_u32(sQ), M * 16, 128), b = smem_desc(smem_u32(sK), NK * 16, 128);
+            uint64_t bv = smem_desc(smem_u32(sV), 128, NK * 16);
+            t0 = clock64();
+            for (int i = 0; i < REP; ++i) mma_ss(tm, a, b, ids128, i > 0);
+            mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+            printf("SS M128 N128 K16        : %6.1f cycles per MMA\n", (double)(t1 - t0) / REP);
+            t0 = clock64();
+            for (int i = 0; i < REP; ++i) mma_ss_masked(tm, a, b, ids, i > 0, 0u, 0u, ~0u, ~0u);
+            mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+            printf("SS M128 N64  K16 masked : %6.1f cycles per MMA\n", (double)(t1 - t0) / REP);
+            t0 = clock64();
+            for (int i = 0; i < REP; ++i) mma_ts(tm + 128, tm + 256, bv, ido16, i > 0);
+            mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+            printf("TS M128 N16  K16        : %6.1f cycles per MMA\n", (double)(t1 - t0) / REP);
+            t0 = clock64();
+            for (int i = 0; i < REP; ++i) mma_ts_masked(tm + 128, tm + 256, bv, ido16, i > 0, 0u, 0u, ~0u, ~0u);
+            mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+            printf("TS M128 N16  K16 masked : %6.1f cycles per MMA\n", (double)(t1 - t0) / REP);
+            t0 = clock64();
+            for (int i = 0; i < REP; ++i) mma_ts(tm + 128, tm + 256, bv, ido32, i > 0);
+            mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+            printf("TS M128 N32  K16        : %6.1f cycles per MMA\n", (double)(t1 - t0) / REP);
+            uint64_t bv64 = smem_desc(smem_u32(sV), 128, NK * 16);
+            const uint32_t ido64 = idesc_bf16(128, 64, false, true);
+            t0 = clock64();
+            for (int i = 0; i < REP; ++i) mma_ts(tm + 128, tm + 256, bv64, ido64, i > 0);
+            mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+            printf("TS M128 N64  K16        : %6.1f cycles per MMA\n", (double)(t1 - t0) / REP);
+            {   // the window kernel's per-head issue stream: 2 masked SS (N=64) + commit, 8 masked TS (N=16) + 2 commits
+                const uint32_t A = 0xFFFFFFFFu;
+                t0 = clock64();
+                for (int i = 0; i < 128; ++i) {
+                    mma_ss_masked(tm, a, b, ids, false, 0u, 0u, A, A);
+                    mma_ss_masked(tm, a, b, ids, false, A, A, 0u, 0u);
+                    mma_commit(&bar);
+                    for (int h = 0; h < 2; ++h)
+                        for (int ks = 0; ks < 4; ++ks)
+                            mma_ts_masked(tm + 128, tm + 256 + ks * 8, smem_desc(smem_u32(sV) + h * 64 * 16 + ks * 256, 128, NK * 16), ido16, ks > 0,
+                                          h ? A : 0u, h ? A : 0u, h ? 0u : A, h ? 0u : A);
+                    mma_commit(&bar);
+                    mma_commit(&bar);
+                }
+                t1 = clock64();
+                printf("win8 per-head stream (10 MMA + 3 commits), issue only : %6.1f cycles per head\n", (double)(t1 - t0) / 128);
+                // drain: 384 arrivals on a count-1 barrier = 384 phases; just wait long enough
+                for (volatile int w = 0; w < 200000; ++w) {}
+                mbar_init(&bar, 1); phase = 0;
+                // unmasked alternative: 1 SS N=128 + commit, 8 TS N=16 K over 128 keys + 2 commits
+                t0 = clock64();
+                for (int i = 0; i < 128; ++i) {
+                    mma_ss(tm, a, b, ids128, false);
+                    mma_commit(&bar);
+                    for (int ks = 0; ks < 8; ++ks)
+                        mma_ts(tm + 128, tm + 256 + ks * 8, smem_desc(smem_u32(sV) + ks * 256, 128, NK * 16), ido16, ks > 0);
+                    mma_commit(&bar);
+                    mma_commit(&bar);
+                }
+                t1 = clock64();
+                printf("unmasked per-head stream (9 MMA + 3 commits)          : %6.1f cycles per head\n", (double)(t1 - t0) / 128);
+                for (volatile int w = 0; w < 200000; ++w) {}
+                mbar_init(&bar, 1); phase = 0;
+            }
+            // latency of one dependent commit round trip
+            t0 = clock64();
+            for (int i = 0; i < 64; ++i) { mma_ss(tm, a, b, ids128, false); mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; }
+            t1 = clock64();
+            printf("SS N128 issue+commit+wait round trip: %6.1f cycles\n", (double)(t1 - t0) / 64);
+        }
+        __syncthreads();
+        goto done;
+    }
+    if (variant >= 4) {
+        // T4: S2[128 x 64]: rows 0-63 = Q K[0:64]^T, rows 64-127 = Q K[64:128]^T via two N=64 MMAs with lane masks
+        // (variant 4: bit set = lane disabled; variant 5: inverted polarity)
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t idesc = idesc_bf16(128, 64, false, false);
+            const uint32_t lo = variant == 4 ? 0u : 0xFFFFFFFFu, hi = ~lo;
+            for (int half = 0; half < 2; ++half)
+                for (int k = 0; k < HD / 16; ++k) {
+                    uint64_t a = smem_desc(smem_u32(sQ) + k * 2 * (M * 16), M * 16, 128);
+                    uint64_t b = smem_desc(smem_u32(sK) + half * 64 * 16 + k * 2 * (NK * 16), NK * 16, 128);
+                    // half 0 writes rows 0-63 (disable lanes 64-127), half 1 writes rows 64-127
+                    if (half == 0) mma_ss_masked(tm + 320, a, b, idesc, k > 0, lo, lo, hi, hi);
+                    else mma_ss_masked(tm + 320, a, b, idesc, k > 0, hi, hi, lo, lo);
+                }
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase); phase ^= 1;
+        fence_after_sync();
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tm + lane_base + 320 + c * 32, r);
+            tmem_wait_ld();
+            for (int j = 0; j < 32; ++j) O_out[tid * 64 + c * 32 + j] = __uint_as_float(r[j]);
+        }
+        goto done;
+    }
     // P = bf16(0.05 * S)
     if (variant == 2) {
         for (int c = 0; c < 16; ++c) {
@@ -158,6 +308,14 @@ int main(int argc, char** argv) {
             float acc = 0; for (int j = 0; j < NK; ++j) acc += P[i * NK + j] * fV[j * HD + d];
             eo = fmax(eo, fabs(acc - O[i * HD + d]));
         }
+    if (variant == 6 || variant == 7) return 0;
+    if (variant >= 4) {
+        double e4 = 0;
+        for (int i = 0; i < M; ++i)
+            for (int j = 0; j < 64; ++j) e4 = fmax(e4, fabs(S[i * NK + (i / 64) * 64 + j] - O[i * HD + j]));
+        printf("variant %d: masked two-half S max err vs block-diagonal of S: %.3e\n", variant, e4);
+        return 0;
+    }
     printf("variant %d: S max err %.3e   O max err %.3e   (S[0][0..3] = %.4f %.4f %.4f %.4f)\n", variant, es, eo, S[0], S[1], S[2], S[3]);
     return 0;
 }

@@ -213,6 +213,21 @@ def test_upsample2x_concat_vs_torch(dtype):
     assert out.shape == ref.shape and torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", ["gelu", "silu", None])
+def test_bias_act_crop_vs_torch(act, dtype):
+    x = fx.det_input(f"bac:{act}", (2, 48, 9, 11)).to("cuda", dtype).contiguous(memory_format=torch.channels_last)
+    b = 0.3 * fx.det_input("bac:b", (48,))
+    out = ops().bias_act_crop(x, b.cuda(), act, (8, 10), (1, 1))
+    ref = x.double().cpu()[:, :, 1:, 1:] + b.double().view(1, -1, 1, 1)
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    elif act == "silu":
+        ref = torch.nn.functional.silu(ref)
+    assert out.shape == (2, 8, 10, 48)
+    assert rel_err(out, ref.permute(0, 2, 3, 1)) < (2e-6 if dtype == torch.float32 else 5e-3)
+
+
 def test_fused_model_matches_unfused():
     """Model.fuse() (Conv+BN folding, reference model.py:317-325) must not change the predictions."""
     from sodt_b200.basics.models.model import Model
