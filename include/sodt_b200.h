@@ -152,6 +152,18 @@ int sodt_nms(const float* pred, const int* classes, int n_classes, float* out, i
              int max_det, int max_nms, float max_wh, void* stream);
 
 /*
+ * bf16 Linear with fused epilogue on tcgen05 tensor cores (TMA-fed, TMEM accumulators):
+ *   out[M, N] = act(x[M, K] . w[N, K]^T + bias[N]) (+ residual[M, N]),  act: 0 identity, 1 exact GELU.
+ * Replaces nn.Linear + the separate GELU pass of Mlp (backbone_vit.py:885-890) and nn.Linear + the separate residual add
+ * of SwinTransformerBlock (backbone_vit.py:968,990,1125,1128).  x, w, residual, out bf16 row-major, bias fp32 or NULL.
+ * Supported: SODT_BF16, K % 64 == 0, N % 192 == 0 or N % 256 == 0 (sodt_linear_supported); others -> SODT_ERR_UNSUPPORTED
+ * (the host wrapper then uses cuBLAS).
+ */
+int sodt_linear_supported(int M, int N, int K, int dtype);
+int sodt_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* out,
+                    int M, int N, int K, int act, int dtype, void* stream);
+
+/*
  * Fused bias + activation (+ crop) on channels-last activations: out[b,y,x,c] = act(in[b, y+off_y, x+off_x, c] + bias[c]),
  * act: 0 identity, 1 exact (erf) GELU, 2 SiLU.  in is [B, in_H, in_W, C], out [B, H, W, C], bias [C] fp32.
  * Replaces, after the 2x2 conv of the conv-enhanced MLP (backbone_vit.py:896-902), the F.pad copy, the conv's separate

@@ -30,6 +30,8 @@ SIGNATURES = {
     "sodt_detect_decode": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _f, _ll, _ll, _i, _p]),
     "sodt_nms_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sodt_nms": (_i, [_p, _p, _i, _p, _p, _p, _p, _sz, _i, _i, _i, _f, _d, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "sodt_linear_supported": (_i, [_i, _i, _i, _i]),
+    "sodt_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sodt_bias_act_crop_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_upsample2x_concat_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_launch_count": (_ll, []),

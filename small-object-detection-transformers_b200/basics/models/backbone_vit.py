@@ -141,10 +141,14 @@ class Mlp(nn.Module):
 
     def hidden(self, x, H, W):
         """Everything before fc2: fc1 -> GELU, or fc1 -> zero-pad -> 2x2 conv -> GELU.  [B, L, hidden]."""
+        exact_gelu = isinstance(self.act, nn.GELU) and self.act.approximate == "none"
         if self.linear:
+            if exact_gelu and x.is_cuda:
+                return ops.linear(x, self.fc1.weight, self.fc1.bias, act="gelu")    # GELU fused into the GEMM epilogue (bf16)
             return self.act(self.fc1(x))
         B, L, C = x.shape
-        h = self.fc1(x).view(B, H, W, C).permute(0, 3, 1, 2)   # NCHW view of channels-last memory
+        h = ops.linear(x, self.fc1.weight, self.fc1.bias) if x.is_cuda else self.fc1(x)
+        h = h.view(B, H, W, C).permute(0, 3, 1, 2)             # NCHW view of channels-last memory
         conv = self.conv1
         if isinstance(self.act, nn.GELU) and self.act.approximate == "none" and C % 8 == 0:
             # pad(0,1,0,1) + valid 2x2 conv == rows/cols 1.. of the same conv with symmetric padding 1; the crop, the
@@ -249,8 +253,19 @@ class SwinTransformerBlock(nn.Module):
         if min(H, W) <= self.window_size and (H != W or H != self.window_size):
             raise ValueError(f"token grid {H}x{W} is smaller than the window {self.window_size}")
         attn, mlp = self.attn, self.mlp
-        # LN1 (sm_100a kernel); its second output is the residual stream with proj.bias pre-added, so that the proj
-        # GEMM adds the residual in its epilogue (addmm) and no elementwise add pass is left.
+        if x.dtype == torch.bfloat16 and ops.USE_TC_LINEAR:
+            # bf16: every Linear runs on the tcgen05 GEMM with its bias / GELU / residual fused into the epilogue
+            y, _ = ops.add_layernorm(x, None, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            qkv = ops.linear(y, attn.qkv.weight, attn.qkv.bias)
+            o = ops.window_attention(qkv.view(B, H, W, 3 * C), attn.relative_position_bias_table, attn.num_heads,
+                                     self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
+                                     mask_value=MASK_VALUE)
+            x = ops.linear(o.view(B, L, C), attn.proj.weight, attn.proj.bias, residual=x)
+            z, _ = ops.add_layernorm(x, None, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+            h = mlp.hidden(z, H, W)
+            return ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x)
+        # fp32 (exact) mode: cuBLAS GEMMs; LN1's second output is the residual stream with proj.bias pre-added, so that the
+        # proj GEMM adds the residual in its epilogue (addmm) and no elementwise add pass is left.
         y, xb = ops.add_layernorm(x, None, self.norm1.weight, self.norm1.bias, self.norm1.eps,
                                   extra_bias=attn.proj.bias, want_sum=True)
         o = ops.window_attention(attn.qkv(y.view(B, H, W, C)), attn.relative_position_bias_table, attn.num_heads,

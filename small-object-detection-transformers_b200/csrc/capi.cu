@@ -20,6 +20,10 @@ bool window_attn_win8_supported(int H, int W, int C, int heads, int ws, int shif
 int window_attn_win8(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
                      int heads, int shift, float scale, float mask_value, int num_sms, cudaStream_t stream);
 
+int linear_tc(const void* x, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K, int act,
+              int num_sms, cudaStream_t stream);
+bool linear_tc_supported(int M, int N, int K);
+
 static int sm_count() {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -33,6 +37,20 @@ extern "C" size_t sodt_window_attn_workspace_bytes(int C, int heads, int ws) {
     if (C <= 0 || heads <= 0 || ws <= 0) return 0;
     const size_t a = sodt::window_attn_flash_workspace(heads, ws), b = sodt::window_attn_win8_workspace(heads);
     return a > b ? a : b;
+}
+
+extern "C" int sodt_linear_supported(int M, int N, int K, int dtype) {
+    return dtype == SODT_BF16 && sodt::linear_tc_supported(M, N, K) ? 1 : 0;
+}
+
+extern "C" int sodt_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* out,
+                               int M, int N, int K, int act, int dtype, void* stream) {
+    using namespace sodt;
+    if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0 || act < 0 || act > 1) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_BF16 || !linear_tc_supported(M, N, K)) return SODT_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)))
+        return SODT_ERR_ALIGNMENT;
+    return linear_tc(x, w, bias, residual, out, M, N, K, act, sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sodt_version(void) { return 100; }

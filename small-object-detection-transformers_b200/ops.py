@@ -223,6 +223,43 @@ def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=No
     return z, xp
 
 
+# ----------------------------------------------------------------------- Linear with fused epilogue
+USE_TC_LINEAR = False   # bf16 Linear layers on the tcgen05 kernel (False: cuBLAS + separate elementwise passes)
+
+
+def linear(x, weight, bias=None, act=None, residual=None):
+    """act(x @ weight.T + bias) (+ residual) over the last dim of x.  bf16 shapes the tcgen05 kernel supports run there
+    with the activation / residual fused into the epilogue; fp32 and other shapes use cuBLAS (torch) plus elementwise ops."""
+    _require_cuda(x, weight, bias, residual)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    M = x.numel() // K
+    if (USE_TC_LINEAR and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and act in (None, "gelu")
+            and _capi.lib().sodt_linear_supported(M, N, K, 1)):
+        x2 = x.contiguous()
+        w = weight.detach().contiguous()
+        res = None
+        if residual is not None:
+            res = residual.contiguous()
+            if res.numel() != M * N or res.dtype != torch.bfloat16:
+                raise ValueError("residual must be bf16 with the shape of the output")
+        out = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)
+        b32 = _as_f32(bias)
+        with torch.cuda.device(x.device), _Timed(f"linear[M={M},N={N},K={K},act={act},res={residual is not None}]"):
+            st = _capi.lib().sodt_linear_fwd(x2.data_ptr(), w.data_ptr(), _ptr(b32), _ptr(res), out.data_ptr(), M, N, K,
+                                             1 if act == "gelu" else 0, 1, _stream())
+        _capi.check(st, "sodt_linear_fwd")
+        return out
+    y = torch.nn.functional.linear(x, weight, bias)
+    if act == "gelu":
+        y = torch.nn.functional.gelu(y)
+    elif act is not None:
+        raise ValueError(f"unsupported activation {act!r}")
+    if residual is not None:
+        y = y + residual.view_as(y)
+    return y
+
+
 # ------------------------------------------------------------------- fused bias + activation (+ crop)
 _ACT = {None: 0, "none": 0, "gelu": 1, "silu": 2}
 

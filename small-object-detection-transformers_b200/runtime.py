@@ -106,6 +106,61 @@ class Detector:
         flat = buf.flat.to("cpu")
         return DetectionBuffer.split(flat, buf.batch, buf.max_det)
 
+    def _rings(self, batch, depth=3):
+        key = ("ring", batch)
+        if key not in self._bufs:
+            dev = [DetectionBuffer(batch, self.device) for _ in range(depth)]
+            host = [torch.empty(dev[0].flat.shape, dtype=dev[0].flat.dtype).pin_memory() for _ in range(depth)]
+            self._bufs[key] = (dev, host)
+        return self._bufs[key]
+
+    def detect_stream(self, batches):
+        """Pipelined inference over an iterable of (rgb_u8_host, ir_u8_host) pinned batches: the host->device copy of
+        batch i+1 runs on a copy stream while batch i is computed, and the detections of batch i are read back while
+        batch i+1 is computed.  Device / pinned host result buffers come from small preallocated rings (a yielded result
+        stays valid until two more results have been taken).  Yields (det [B,300,6], counts [B]) host tensors in order."""
+        compute = torch.cuda.current_stream(self.device)
+        copy = self.copy_stream
+
+        def upload(pair):
+            with torch.cuda.stream(copy):
+                rgb = pair[0].to(self.device, non_blocking=True)
+                ir = pair[1].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return rgb, ir, ev
+
+        it = iter(batches)
+        nxt = next(it, None)
+        staged = upload(nxt) if nxt is not None else None
+        pending = None                                   # (host flat buffer, event, batch) of the previous batch
+        i = 0
+        while staged is not None:
+            rgb, ir, ev = staged
+            nxt = next(it, None)
+            staged = upload(nxt) if nxt is not None else None      # overlaps with the compute below
+            dev_ring, host_ring = self._rings(rgb.shape[0])
+            buf, host = dev_ring[i % len(dev_ring)], host_ring[i % len(host_ring)]
+            compute.wait_event(ev)
+            self.detect_device(rgb, ir, buf)
+            rgb.record_stream(compute)
+            ir.record_stream(compute)
+            done = torch.cuda.Event()
+            done.record(compute)
+            with torch.cuda.stream(copy):
+                copy.wait_event(done)
+                host.copy_(buf.flat, non_blocking=True)
+                hev = torch.cuda.Event()
+                hev.record(copy)
+            if pending is not None:
+                pending[1].synchronize()
+                yield DetectionBuffer.split(pending[0], pending[2], MAX_DET)
+            pending = (host, hev, buf.batch)
+            i += 1
+        if pending is not None:
+            pending[1].synchronize()
+            yield DetectionBuffer.split(pending[0], pending[2], MAX_DET)
+
     def __call__(self, rgb_u8_host, ir_u8_host):
         det, counts = self.detect(rgb_u8_host, ir_u8_host)
         return [det[i, :n] for i, n in enumerate(counts.tolist())]

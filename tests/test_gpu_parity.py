@@ -129,6 +129,28 @@ def test_window_attention_full_size_properties(dtype):
     assert rel_err(o0[:1, 40:48, 80:88], ref) < TOL[dtype]
 
 
+# ------------------------------------------------------------------------------------ fused Linear
+@pytest.mark.parametrize("M,N,K,act,res", [(1000, 576, 192, None, False), (777, 768, 192, "gelu", False), (4096, 192, 768, None, True),
+                                           (300, 192, 192, None, True), (129, 1152, 384, None, False), (2048, 1536, 384, "gelu", False),
+                                           (513, 384, 1536, None, True), (640, 3072, 768, "gelu", False), (100, 768, 3072, None, True),
+                                           (50000, 768, 192, "gelu", False)])
+def test_linear_tc_vs_torch(M, N, K, act, res):
+    x = fx.det_input(f"lin_x:{M}:{K}", (M, K)).to("cuda", torch.bfloat16)
+    w = (fx.det_input(f"lin_w:{N}:{K}", (N, K)) / K ** 0.5).to("cuda", torch.bfloat16)
+    b = 0.2 * fx.det_input(f"lin_b:{N}", (N,))
+    r = fx.det_input(f"lin_r:{M}:{N}", (M, N)).to("cuda", torch.bfloat16) if res else None
+    assert ops()._capi.lib().sodt_linear_supported(M, N, K, 1) == 1
+    out = ops().linear(x, w, b.cuda(), act=act, residual=r)
+    ref = x.double().cpu() @ w.double().cpu().t() + b.double()
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+    if res:
+        ref = ref + r.double().cpu()
+    assert out.shape == (M, N) and out.dtype == torch.bfloat16
+    assert rel_err(out, ref) < 4e-3
+    assert (out.double().cpu() - ref).abs().max() < 0.06 * max(1.0, ref.abs().max().item() / 8)
+
+
 # ------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,C,with_r,with_e", [(1000, 192, False, True), (257, 384, True, True), (64, 768, True, False),
