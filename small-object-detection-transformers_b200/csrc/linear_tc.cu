@@ -7,10 +7,11 @@
 // token rows), so removing the extra elementwise passes over the 4C-wide hidden tensor is worth more than MMA efficiency.
 //
 // Persistent CTAs (one per SM), tile 128 x BN (BN = 256 or 192), k-block 64:
-//   warp 8      TMA producer: cp.async.bulk.tensor 2-D boxes of x and W, SWIZZLE_128B, 4-stage mbarrier ring
-//   warp 9      MMA issuer:   tcgen05.mma kind::f16, M=128, N=BN, K-major SWIZZLE_128B operands, fp32 accumulators in TMEM,
+//   warp 16     TMA producer: cp.async.bulk.tensor 2-D boxes of x and W, SWIZZLE_128B, 4-stage mbarrier ring
+//   warp 17     MMA issuer:   tcgen05.mma kind::f16, M=128, N=BN, K-major SWIZZLE_128B operands, fp32 accumulators in TMEM,
 //                             two accumulator buffers (2 x BN columns) so the epilogue of tile t overlaps the MMAs of t+1
-//   warps 0-7   epilogue:     two groups of 4 warps alternate over the tile's 64-column boxes: tcgen05.ld (warp w: TMEM lanes
+//   warps 0-15  epilogue:     four groups of 4 warps take the tile's 64-column boxes (residual box TMA-loaded into the group's
+//                             staging buffer first): tcgen05.ld (warp w: TMEM lanes
 //                             32*(w%4)..), bias, GELU (erf by A&S 7.1.26, |error| < 2e-7, far below bf16), residual, bf16
 //                             pack into a SWIZZLE_128B staging box in shared memory, one TMA store per box (full 128-byte
 //                             lines; per-thread 16-byte row stores capped the kernel at ~1.9 TB/s)
@@ -27,7 +28,10 @@ using namespace tc;
 constexpr int BM = 128, BK = 64;
 constexpr int BOX_BYTES = BM * 64 * 2;      // one 128-row x 64-column bf16 output box
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NTHREADS = 320;
+constexpr int EPI_GROUPS = 4;                  // epilogue groups of 4 warps (one 64-column box each at a time)
+constexpr int EPI_WARPS = EPI_GROUPS * 4;
+constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -50,7 +54,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 // exact-GELU with erf from Abramowitz & Stegun 7.1.26 (max abs error 1.5e-7): one MUFU.RCP, one MUFU.EX2, ~10 FMA
 __device__ __forceinline__ float gelu_erf(float x) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
@@ -63,12 +67,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_o, const float* __restrict__ bias,
-                 const __nv_bfloat16* __restrict__ residual, int M, int N, int K, int act, int num_n_tiles, int num_tiles) {
+                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
+                 const float* __restrict__ bias, int has_residual, int M, int N, int K, int act, int num_n_tiles, int num_tiles) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], res_full[EPI_GROUPS];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -76,16 +80,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 256); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32); }
+        for (int g = 0; g < EPI_GROUPS; ++g) mbar_init(&res_full[g], 1);
         fence_barrier_init();
     }
-    if (warp == 9) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+    if (warp == MMA_WARP) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tm = tmem_slot;
 
-    if (warp == 8) {
+    if (warp == PRODUCER_WARP) {
         if (lane == 0) {
             int stage = 0, round = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -100,7 +105,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == MMA_WARP) {
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16(BM, BN, false, false);
             int stage = 0, round = 0, it = 0;
@@ -121,7 +126,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         }
     } else {
-        // epilogue group eg = warp/4 takes the tile's 64-column boxes eg, eg+2, ...; thread = one row of the box
+        // epilogue group eg = warp/4 takes the tile's 64-column boxes eg, eg + EPI_GROUPS, ...; thread = one row of the box
         const int quarter = warp & 3, eg = warp >> 2;
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -131,22 +136,28 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const bool issuer = quarter == 0 && lane == 0;
         constexpr int NBOX = BN / 64;
         int it = 0;
+        uint32_t res_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int a = it & 1;
             const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
-            const int row = mt * BM + row_in_tile;
             mbar_wait(&acc_full[a], (uint32_t)((it >> 1) & 1));
             fence_after_sync();
 #pragma unroll 1
-            for (int bx = eg; bx < NBOX; bx += 2) {
+            for (int bx = eg; bx < NBOX; bx += EPI_GROUPS) {
                 const int col0 = nt * BN + bx * 64;
+                if (issuer) {
+                    tma_store_wait_read();                               // the previous box of this group has left smem
+                    if (has_residual) {                                  // residual box lands in the staging buffer (TMA, swizzled)
+                        mbar_expect_tx(&res_full[eg], BOX_BYTES);
+                        tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, mt * BM);
+                    }
+                }
                 uint32_t r0[32], r1[32];
                 tmem_ld32(tm + lane_addr + a * BN + bx * 64, r0);
                 tmem_ld32(tm + lane_addr + a * BN + bx * 64 + 32, r1);
                 tmem_wait_ld();
-                if (issuer) tma_store_wait_read();                       // the previous box of this group has left smem
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-                const bool rok = row < M;
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");      // staging box reusable for everyone
+                if (has_residual) { mbar_wait(&res_full[eg], res_phase); res_phase ^= 1; }
 #pragma unroll
                 for (int j = 0; j < 64; j += 8) {
                     float v[8];
@@ -162,13 +173,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
                     }
-                    if (residual != nullptr && rok) {
-                        const uint4 rr = *reinterpret_cast<const uint4*>(residual + (long long)row * N + col0 + j);
-                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { v[2 * e] += __low2float(h[e]); v[2 * e + 1] += __high2float(h[e]); }
-                    }
                     const uint32_t dst = my_row + (((j >> 3) ^ sw) << 4);
+                    if (has_residual) {
+                        uint32_t q0, q1, q2, q3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q0), "=r"(q1), "=r"(q2), "=r"(q3) : "r"(dst) : "memory");
+                        const uint32_t qq[4] = {q0, q1, q2, q3};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&qq[e]);
+                            v[2 * e] += __low2float(h); v[2 * e + 1] += __high2float(h);
+                        }
+                    }
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
                                  "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
                 }
@@ -183,7 +198,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_slot, 512);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_slot, 512);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -223,18 +238,18 @@ bool make_out_map(CUtensorMap* m, void* base, int M, int N) {
 template <int BN, int STAGES>
 int launch(const void* x, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K, int act,
            int num_sms, cudaStream_t stream) {
-    CUtensorMap mx, mw, mo;
+    CUtensorMap mx, mw, mo, mr;
     if (!make_map(&mx, x, M, K, BM) || !make_map(&mw, w, N, K, BN) || !make_out_map(&mo, out, M, N)) return SODT_ERR_CUDA;
+    if (!make_out_map(&mr, const_cast<void*>(residual ? residual : out), M, N)) return SODT_ERR_CUDA;
     const int num_n_tiles = N / BN, num_m_tiles = (M + BM - 1) / BM;
     const long long tiles = (long long)num_n_tiles * num_m_tiles;
     if (tiles > 2147483647LL) return SODT_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)STAGES * (A_BYTES + BN * BK * 2) + 2 * BOX_BYTES + 1024;
+    const size_t smem = (size_t)STAGES * (A_BYTES + BN * BK * 2) + EPI_GROUPS * BOX_BYTES + 1024;
     auto kern = linear_tc_kernel<BN, STAGES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mw, mo, bias, static_cast<const __nv_bfloat16*>(residual), M, N, K, act, num_n_tiles,
-                                           (int)tiles);
+    kern<<<grid, NTHREADS, smem, stream>>>(mx, mw, mo, mr, bias, residual != nullptr ? 1 : 0, M, N, K, act, num_n_tiles, (int)tiles);
     return check_launch();
 }
 

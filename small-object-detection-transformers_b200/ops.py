@@ -224,7 +224,7 @@ def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=No
 
 
 # ----------------------------------------------------------------------- Linear with fused epilogue
-USE_TC_LINEAR = False   # bf16 Linear layers on the tcgen05 kernel (False: cuBLAS + separate elementwise passes)
+USE_TC_LINEAR = True    # bf16 Linear layers on the tcgen05 kernel (False: cuBLAS + separate elementwise passes)
 
 
 def linear(x, weight, bias=None, act=None, residual=None):
