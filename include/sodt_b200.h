@@ -114,6 +114,18 @@ int sodt_cattn_block_fwd(const void* r, const void* g, const void* b, const void
                          float eps, float mask_value, int dtype, void* stream);
 
 /*
+ * Fused front end: the four single-channel 4x4 / stride-4 patch embeddings (R with padding `pad_r` = 1, the others 0:
+ * backbone_vit.py:69-98,751) + the window-1 cross-channel block (backbone_vit.py:469-561) + the concatenation (:210).
+ *   x        [B, 4, H, W] through element strides (sb, sc, sy, sx); channels R, G, B, IR
+ *   conv_w   [4, E, 16] fp32 (the four Conv2d(1, E, 4, 4) weights), conv_b [4, E], ln_w / ln_b [4, E]
+ *   out      [B, H/4, W/4, 4*E]
+ * Supported: E == 48, and H, W such that the padded R stream has the same output size as the others (H, W % 4 == 0).
+ */
+int sodt_frontend_fwd(const void* x, long long sb, long long sc, long long sy, long long sx,
+                      const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b, void* out,
+                      int B, int H, int W, int E, int pad_r, float eps, int dtype, void* stream);
+
+/*
  * YOLOv5 Detect decode for one level.  Replaces model.py:55-64 (view/permute/contiguous,
  * sigmoid, grid + anchor decode, view) for the output of the level's 1x1 conv (model.py:53).
  *

@@ -195,6 +195,24 @@ def cattn_block(r, g, b, ir, ln_w, ln_b, heads, ws=1, shift=0, eps=1e-5, mask_va
     return out
 
 
+# ------------------------------------------------------------------------------------- front end
+def frontend(x, conv_w, conv_b, ln_w, ln_b, pad_r=1, eps=1e-5):
+    """x [B,4,H,W] -> [B,H/4,W/4,4E]: four channel embeddings + window-1 cross-channel block.  conv_w [4,E,16],
+    conv_b / ln_w / ln_b [4,E] (fp32).  See sodt_frontend_fwd."""
+    _require_cuda(x, conv_w, conv_b, ln_w, ln_b)
+    if x.dim() != 4 or x.shape[1] != 4 or x.dtype not in _DT:
+        raise ValueError("x must be [B, 4, H, W] in fp32 / bf16")
+    B, _, H, W = x.shape
+    E = conv_w.shape[1]
+    out = torch.empty((B, (H - 4) // 4 + 1, (W - 4) // 4 + 1, 4 * E), dtype=x.dtype, device=x.device)
+    sb, sc, sy, sx = x.stride()
+    with torch.cuda.device(x.device), _Timed(f"frontend[B={B},H={H},W={W}]"):
+        st = _capi.lib().sodt_frontend_fwd(x.data_ptr(), sb, sc, sy, sx, conv_w.data_ptr(), conv_b.data_ptr(), ln_w.data_ptr(),
+                                           ln_b.data_ptr(), out.data_ptr(), B, H, W, E, pad_r, float(eps), _DT[x.dtype], _stream())
+    _capi.check(st, "sodt_frontend_fwd")
+    return out
+
+
 # --------------------------------------------------------------------------------- Detect decode
 def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=None, row_offset=0):
     """raw [B, na*no, ny, nx] (any strides) -> (z [B, na*ny*nx, no] fp32, x_perm [B,na,ny,nx,no] or None)."""

@@ -262,6 +262,29 @@ def test_fused_model_matches_unfused():
     assert rel_err(p1, p0) < 1e-5
 
 
+# ------------------------------------------------------------------------------------- front end
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("pad_r", [1, 0])
+def test_frontend_vs_oracle(pad_r, dtype):
+    """Fused channel embeddings + cross-channel block against conv2d + the cross-channel oracle."""
+    B, H, W, E = 2, 64, 48, 48
+    x = fx.det_input("fe:x", (B, 4, H, W), kind="uniform").to("cuda", dtype)
+    cw = 0.3 * fx.det_input("fe:cw", (4, E, 16))
+    cb = 0.1 * fx.det_input("fe:cb", (4, E))
+    lw = 1.0 + 0.1 * fx.det_input("fe:lw", (4, E))
+    lb = 0.1 * fx.det_input("fe:lb", (4, E))
+    out = ops().frontend(x, cw.cuda(), cb.cuda(), lw.cuda(), lb.cuda(), pad_r=pad_r)
+    xc = x.double().cpu()
+    streams = []
+    for s in range(4):
+        pad = pad_r if s == 0 else 0
+        e = torch.nn.functional.conv2d(xc[:, s:s + 1], cw[s].double().reshape(E, 1, 4, 4), cb[s].double(), 4, pad)
+        streams.append(e.permute(0, 2, 3, 1))
+    ref = torch.cat(A.cattention_block(streams, list(lw), list(lb), 12, ws=1), -1)
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < (1e-5 if dtype == torch.float32 else 1e-2)
+
+
 # ---------------------------------------------------------------------------------------- Detect
 @pytest.mark.parametrize("memory_format", ["nchw", "channels_last"])
 def test_detect_module_vs_reference_golden(golden, memory_format):
