@@ -164,16 +164,41 @@ int sodt_nms(const float* pred, const int* classes, int n_classes, float* out, i
              int max_det, int max_nms, float max_wh, void* stream);
 
 /*
- * bf16 Linear with fused epilogue on tcgen05 tensor cores (TMA-fed, TMEM accumulators):
- *   out[M, N] = act(x[M, K] . w[N, K]^T + bias[N]) (+ residual[M, N]),  act: 0 identity, 1 exact GELU.
- * Replaces nn.Linear + the separate GELU pass of Mlp (backbone_vit.py:885-890) and nn.Linear + the separate residual add
- * of SwinTransformerBlock (backbone_vit.py:968,990,1125,1128).  x, w, residual, out bf16 row-major, bias fp32 or NULL.
- * Supported: SODT_BF16, K % 64 == 0, N % 192 == 0 or N % 256 == 0 (sodt_linear_supported); others -> SODT_ERR_UNSUPPORTED
- * (the host wrapper then uses cuBLAS).
+ * bf16 GEMM-shaped layers with fused epilogue on tcgen05 tensor cores (TMA-fed, TMEM accumulators):
+ *   out[M, N] = act(A[M, K] . w[N, K]^T + bias[N]) (+ residual[M, N]),  act: 0 identity, 1 GELU, 2 SiLU.
+ * w bf16 [N, K] row-major, bias fp32 [N] or NULL, out / residual bf16.  GELU is x Phi(x) with Phi evaluated through one
+ * MUFU.TANH on a fitted odd polynomial (|error| < 0.5 |x| 2^-11 against the erf form: below a quarter bf16 ulp), SiLU is
+ * 0.5 x (1 + tanh(x/2)).  All: SODT_BF16 only, K % 64 == 0, N % 64 == 0; others -> SODT_ERR_UNSUPPORTED (the host wrapper
+ * then uses the cuBLAS / cuDNN library path).
+ *
+ * sodt_linear_fwd            A = x[M, K] contiguous.  Replaces nn.Linear + the separate GELU pass of Mlp
+ *                            (backbone_vit.py:885-890) and nn.Linear + the separate residual add of SwinTransformerBlock
+ *                            (backbone_vit.py:968,990,1125,1128).
+ * sodt_linear_strided_fwd    the same with row strides (elements, multiples of 8) for x, residual and out, so operands /
+ *                            results can be column slices of wider tensors (the head's C3 writes both branches into one
+ *                            buffer instead of torch.cat, common.py:114-126); if x2 != NULL, columns [0, k_split) of A come
+ *                            from x and [k_split, K) from x2 (neck over concat(block5, block6), backbone_vit.py:239,262).
+ * sodt_conv2d_nhwc_fwd       stride-1 kh x kw convolution as a tap GEMM on an NHWC tensor: A[(b,y,x), (ky,kx,c)] =
+ *                            in[b, y+ky-pad_t, x+kx-pad_l, c] addressed by a rank-4 TMA map, zero padding from the TMA
+ *                            out-of-bounds fill; w = conv weight permuted to [Cout, kh, kw, Cin].  Replaces F.pad + Conv2d +
+ *                            GELU of the conv-MLP (backbone_vit.py:896-902) and Conv2d + BatchNorm (folded) + SiLU of the
+ *                            head (common.py:38-52).  Needs W % 128 == 0, or 128 % W == 0 and H % (128 / W) == 0.
+ * sodt_patch_merge_linear_fwd  PatchMerging's 2x2 gather + Linear(4C -> N) (backbone_vit.py:840-853): A[(b,i,j), (dx,dy,c)] =
+ *                            x[b, 2i+dy, 2j+dx, c] addressed by a rank-5 TMA map; x bf16 [B, H, W, C] contiguous.
  */
 int sodt_linear_supported(int M, int N, int K, int dtype);
 int sodt_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* out,
                     int M, int N, int K, int act, int dtype, void* stream);
+int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, int ldx2, int k_split, const void* w,
+                            const float* bias, const void* residual, int ldr, void* out, int ldo,
+                            int M, int N, int K, int act, int dtype, void* stream);
+int sodt_conv2d_nhwc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw, int dtype);
+int sodt_conv2d_nhwc_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo,
+                         int B, int H, int W, int Cin, int Cout, int kh, int kw, int pad_t, int pad_l,
+                         int act, int dtype, void* stream);
+int sodt_patch_merge_linear_supported(int B, int H, int W, int C, int N, int dtype);
+int sodt_patch_merge_linear_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
+                                int C, int N, int dtype, void* stream);
 
 /*
  * Fused bias + activation (+ crop) on channels-last activations: out[b,y,x,c] = act(in[b, y+off_y, x+off_x, c] + bias[c]),

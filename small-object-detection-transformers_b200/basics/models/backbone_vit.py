@@ -112,10 +112,10 @@ class PatchMerging(nn.Module):
         B, L, C = x.shape
         if L != H * W or H % 2 or W % 2:
             raise ValueError(f"PatchMerging: bad token grid {H}x{W} for {L} tokens")
-        g = x.view(B, H // 2, 2, W // 2, 2, C)
-        # channel order of the reference concat: (dy,dx) = (0,0), (1,0), (0,1), (1,1)
-        g = g.permute(0, 1, 3, 4, 2, 5).reshape(B, (H // 2) * (W // 2), 4 * C)
-        return ops.add_layernorm(self.reduction(g), None, self.norm.weight, self.norm.bias, self.norm.eps)[0]
+        # gather in the channel order of the reference concat, (dy,dx) = (0,0), (1,0), (0,1), (1,1), + Linear(4C -> 2C):
+        # the gather is the TMA addressing of the GEMM's A operand, the concatenated tensor is never written
+        y = ops.patch_merge_linear(x.view(B, H, W, C), self.reduction.weight, self.reduction.bias)
+        return ops.add_layernorm(y, None, self.norm.weight, self.norm.bias, self.norm.eps)[0]
 
 
 class Mlp(nn.Module):
@@ -148,8 +148,13 @@ class Mlp(nn.Module):
             return self.act(self.fc1(x))
         B, L, C = x.shape
         h = ops.linear(x, self.fc1.weight, self.fc1.bias) if x.is_cuda else self.fc1(x)
-        h = h.view(B, H, W, C).permute(0, 3, 1, 2)             # NCHW view of channels-last memory
+        h4 = h.view(B, H, W, C)
         conv = self.conv1
+        if exact_gelu and conv.kernel_size == (2, 2) and ops.conv2d_nhwc_supported(h4, C, 2, 2):
+            # zero-pad right / below + valid 2x2 conv + bias + GELU as one tap GEMM: the four taps are TMA boxes of the
+            # fc1 output shifted by (ky, kx); rows / columns past the image come from the TMA out-of-bounds fill
+            return ops.conv2d_nhwc(h4, ops.conv_weight_taps(conv.weight), conv.bias, (2, 2), (0, 0), "gelu").view(B, L, C)
+        h = h4.permute(0, 3, 1, 2)                             # NCHW view of channels-last memory
         if isinstance(self.act, nn.GELU) and self.act.approximate == "none" and C % 8 == 0:
             # pad(0,1,0,1) + valid 2x2 conv == rows/cols 1.. of the same conv with symmetric padding 1; the crop, the
             # conv bias and the GELU run in one sm_100a pass instead of a pad copy, a bias-add pass and a GELU pass
@@ -375,9 +380,14 @@ class ImageEncoderViT(nn.Module):
         self.neck1 = nn.Conv2d(384, 256, kernel_size=1, bias=False)
 
     @staticmethod
-    def _neck(conv, tokens):
+    def _neck(conv, tokens, tokens2=None):
         w = conv.weight
-        return F.linear(tokens, w.reshape(w.shape[0], w.shape[1])).permute(0, 3, 1, 2)
+        w = w.reshape(w.shape[0], w.shape[1])
+        if tokens.is_cuda:
+            return ops.linear(tokens, w, None, x2=tokens2).permute(0, 3, 1, 2)
+        if tokens2 is not None:
+            tokens = torch.cat((tokens, tokens2), dim=-1)
+        return F.linear(tokens, w).permute(0, 3, 1, 2)
 
     @staticmethod
     def _run_stage(blocks, x, hw):
@@ -427,7 +437,6 @@ class ImageEncoderViT(nn.Module):
             x = blk(x, (h, w))
             if n in (4, 5):
                 kept.append(x.view(B, h, w, C))
-        y0 = torch.cat(kept, dim=-1)
         x = self.pmerging1(x, (h, w))
         h2, w2 = h // 2, w // 2
         x = self._run_stage(self.stage2, x, (h2, w2))
@@ -440,4 +449,5 @@ class ImageEncoderViT(nn.Module):
                              "inputs must be multiples of 512 px (or exactly 16*window)")
         x = self._run_stage(self.stage3, x, (h3, w3))
         y2 = x.view(B, h3, w3, -1)
-        return [self._neck(self.neck1, y0), self._neck(self.neck2, y1), self._neck(self.neck3, y2)]
+        # neck1 reads concat(block 5, block 6) of stage 1: two A operands of one GEMM instead of a concatenated copy
+        return [self._neck(self.neck1, kept[0], kept[1]), self._neck(self.neck2, y1), self._neck(self.neck3, y2)]

@@ -30,14 +30,28 @@ class Conv(nn.Module):
     def forward(self, x):
         return self.act(self.bn(self.conv(x)))
 
-    def fuseforward(self, x):
+    def fuseforward(self, x, out=None):
+        """BatchNorm already folded into the conv (Model.fuse).  ``out``: optional [B,H,W,c2] channel-slice view that
+        receives the result (C3 writes its two branches into one buffer instead of concatenating them)."""
         conv = self.conv
         if (x.is_cuda and isinstance(self.act, nn.SiLU) and conv.bias is not None and conv.out_channels % 8 == 0
                 and x.dtype in (torch.float32, torch.bfloat16)):
             from ... import ops
+            kh, kw = conv.kernel_size
+            xh = x.permute(0, 2, 3, 1)                            # [B,H,W,C] view of channels-last memory
+            if (conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1 and conv.padding == (kh // 2, kw // 2)
+                    and kh % 2 == 1 and kw % 2 == 1 and ops.conv2d_nhwc_supported(xh, conv.out_channels, kh, kw)):
+                # conv + folded BN + SiLU as one tap GEMM on the tcgen05 kernel (1x1: a plain GEMM)
+                y = ops.conv2d_nhwc(xh, ops.conv_weight_taps(conv.weight), conv.bias, (kh, kw), conv.padding, "silu", out=out)
+                return y.permute(0, 3, 1, 2)
             y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
-            return ops.bias_act_crop(y, conv.bias, "silu").permute(0, 3, 1, 2)   # bias + SiLU in one pass
-        return self.act(conv(x))
+            y = ops.bias_act_crop(y, conv.bias, "silu")           # bias + SiLU in one pass
+        else:
+            y = self.act(conv(x)).permute(0, 2, 3, 1)
+        if out is not None:
+            out.copy_(y)
+            y = out
+        return y.permute(0, 3, 1, 2)
 
 
 def DWConv(c1, c2, k=1, s=1, act=True):
@@ -54,9 +68,14 @@ class Bottleneck(nn.Module):
         self.cv2 = Conv(c_, c2, 3, 1, g=g)
         self.add = shortcut and c1 == c2
 
-    def forward(self, x):
-        y = self.cv2(self.cv1(x))
-        return x + y if self.add else y
+    def forward(self, x, out=None):
+        fused = out is not None and not hasattr(self.cv2, "bn") and not self.add
+        y = self.cv2.fuseforward(self.cv1(x), out=out) if fused else self.cv2(self.cv1(x))
+        y = x + y if self.add else y
+        if out is not None and not fused:
+            out.copy_(y.permute(0, 2, 3, 1))
+            y = out.permute(0, 3, 1, 2)
+        return y
 
 
 class C3(nn.Module):
@@ -70,7 +89,34 @@ class C3(nn.Module):
         self.cv3 = Conv(2 * c_, c2, 1)
         self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
 
+    def _branch_weights(self):
+        """cv1 and cv2 read the same input: one GEMM with the stacked [2c_, c1] weight (cached per parameter version)."""
+        from ... import ops
+        w1, w2, b1, b2 = self.cv1.conv.weight, self.cv2.conv.weight, self.cv1.conv.bias, self.cv2.conv.bias
+        key = tuple((id(t), t._version, t.data_ptr()) for t in (w1, w2, b1, b2))
+        if getattr(self, "_bw_key", None) != key:
+            self._bw = (torch.cat((ops.conv_weight_taps(w1), ops.conv_weight_taps(w2))).contiguous(),
+                        torch.cat((b1.detach().float(), b2.detach().float())).contiguous())
+            self._bw_key = key
+        return self._bw
+
     def forward(self, x):
+        convs = (self.cv1, self.cv2, self.cv3)
+        if (x.is_cuda and x.dtype == torch.bfloat16 and all(not hasattr(c, "bn") and isinstance(c.act, nn.SiLU)
+                                                            and c.conv.kernel_size == (1, 1) and c.conv.bias is not None for c in convs)):
+            from ... import ops
+            xh = x.permute(0, 2, 3, 1)
+            c_ = self.cv1.conv.out_channels
+            if ops.conv2d_nhwc_supported(xh, 2 * c_, 1, 1):
+                # both branches land in the halves of one [B,H,W,2c_] buffer: no torch.cat, the bottleneck chain's last
+                # conv writes over the cv1 half it no longer needs
+                w12, b12 = self._branch_weights()
+                buf = ops.conv2d_nhwc(xh, w12, b12, (1, 1), (0, 0), "silu")
+                half = buf[..., :c_]
+                t = half.permute(0, 3, 1, 2)
+                for i, m in enumerate(self.m):
+                    t = m(t, out=half) if i == len(self.m) - 1 else m(t)
+                return self.cv3(buf.permute(0, 3, 1, 2))
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
 

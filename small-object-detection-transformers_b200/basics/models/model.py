@@ -38,9 +38,27 @@ class Detect(nn.Module):
         self.register_buffer("anchor_grid", a.clone().view(self.nl, 1, -1, 1, 1, 2))
         self.m = nn.ModuleList(nn.Conv2d(c, self.no * self.na, 1) for c in ch)
 
+    def _level_conv(self, i, xi):
+        """The level's 1x1 conv (reference model.py:53).  Inference on bf16: the tcgen05 GEMM with the na*no = 39 output
+        channels zero-padded to 64 (the cuBLAS path falls back to a pre-tensor-core kernel for N = 39); the decode kernel
+        reads the first na*no channels through strides."""
+        conv = self.m[i]
+        ch = self.no * self.na
+        if not self.training and xi.is_cuda and xi.dtype == torch.bfloat16 and conv.kernel_size == (1, 1):
+            npad = (ch + 63) // 64 * 64
+            xh = xi.permute(0, 2, 3, 1)
+            if ops.conv2d_nhwc_supported(xh, npad, 1, 1):
+                w = ops.cached_derived(conv.weight, "pad64", lambda t: torch.cat(
+                    (t.detach().reshape(ch, -1), t.new_zeros(npad - ch, t.shape[1]))).contiguous())
+                b = ops.cached_derived(conv.bias, "pad64", lambda t: torch.cat(
+                    (t.detach().float(), torch.zeros(npad - ch, dtype=torch.float32, device=t.device))).contiguous())
+                y = ops.conv2d_nhwc(xh, w, b, (1, 1), (0, 0), None)
+                return y[..., :ch].permute(0, 3, 1, 2)
+        return conv(xi)
+
     def forward(self, x):
         self.training |= self.export
-        raws = [self.m[i](x[i]) for i in range(self.nl)]
+        raws = [self._level_conv(i, x[i]) for i in range(self.nl)]
         if self.training:
             for i, r in enumerate(raws):
                 bs, _, ny, nx = r.shape

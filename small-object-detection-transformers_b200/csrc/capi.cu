@@ -1,5 +1,6 @@
 // C-ABI entry points that only validate and dispatch (see include/sodt_b200.h), plus library bookkeeping.
 #include "common.cuh"
+#include "linear_tc.h"
 
 namespace sodt {
 
@@ -19,10 +20,6 @@ size_t window_attn_win8_workspace(int heads);
 bool window_attn_win8_supported(int H, int W, int C, int heads, int ws, int shift, int dtype);
 int window_attn_win8(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
                      int heads, int shift, float scale, float mask_value, int num_sms, cudaStream_t stream);
-
-int linear_tc(const void* x, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K, int act,
-              int num_sms, cudaStream_t stream);
-bool linear_tc_supported(int M, int N, int K);
 
 static int sm_count() {
     int dev = 0, n = 0;
@@ -45,12 +42,47 @@ extern "C" int sodt_linear_supported(int M, int N, int K, int dtype) {
 
 extern "C" int sodt_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* out,
                                int M, int N, int K, int act, int dtype, void* stream) {
+    return sodt_linear_strided_fwd(x, K, nullptr, 0, 0, w, bias, residual, N, out, N, M, N, K, act, dtype, stream);
+}
+
+extern "C" int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, int ldx2, int k_split, const void* w,
+                                       const float* bias, const void* residual, int ldr, void* out, int ldo,
+                                       int M, int N, int K, int act, int dtype, void* stream) {
     using namespace sodt;
-    if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0 || act < 0 || act > 1) return SODT_ERR_INVALID_ARG;
+    if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0 || act < 0 || act > 2) return SODT_ERR_INVALID_ARG;
     if (dtype != SODT_BF16 || !linear_tc_supported(M, N, K)) return SODT_ERR_UNSUPPORTED;
-    if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)))
+    if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)) ||
+        (x2 && !aligned16(x2)))
         return SODT_ERR_ALIGNMENT;
-    return linear_tc(x, w, bias, residual, out, M, N, K, act, sm_count(), static_cast<cudaStream_t>(stream));
+    LinearTcArgs g{x, ldx, w, bias, residual, ldr, out, ldo, M, N, K, act};
+    return linear_tc(g, x2, ldx2, k_split, sm_count(), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sodt_conv2d_nhwc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw, int dtype) {
+    return dtype == SODT_BF16 && sodt::conv_tc_supported(B, H, W, Cin, Cout, kh, kw) ? 1 : 0;
+}
+
+extern "C" int sodt_conv2d_nhwc_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo,
+                                    int B, int H, int W, int Cin, int Cout, int kh, int kw, int pad_t, int pad_l,
+                                    int act, int dtype, void* stream) {
+    using namespace sodt;
+    if (!x || !w || !out || B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || act < 0 || act > 2) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_BF16 || !conv_tc_supported(B, H, W, Cin, Cout, kh, kw)) return SODT_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias))) return SODT_ERR_ALIGNMENT;
+    return conv_tc(x, ldx, w, bias, out, ldo, B, H, W, Cin, Cout, kh, kw, pad_t, pad_l, act, sm_count(), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sodt_patch_merge_linear_supported(int B, int H, int W, int C, int N, int dtype) {
+    return dtype == SODT_BF16 && sodt::merge_tc_supported(B, H, W, C, N) ? 1 : 0;
+}
+
+extern "C" int sodt_patch_merge_linear_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
+                                           int C, int N, int dtype, void* stream) {
+    using namespace sodt;
+    if (!x || !w || !out || B <= 0 || H <= 0 || W <= 0 || C <= 0 || N <= 0) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_BF16 || !merge_tc_supported(B, H, W, C, N)) return SODT_ERR_UNSUPPORTED;
+    if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias))) return SODT_ERR_ALIGNMENT;
+    return merge_tc(x, w, bias, out, B, H, W, C, N, sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sodt_version(void) { return 100; }

@@ -1,23 +1,33 @@
-// bf16 Linear layers of the Swin blocks on tcgen05 tensor cores with fused epilogues:
+// bf16 GEMM-shaped layers of the detector on tcgen05 tensor cores with TMA-addressed operands and fused epilogues
+// (SURVEY.md section 8f, rank 1-2):
 //
-//   out[M, N] = act(x[M, K] . W[N, K]^T + bias[N]) (+ residual[M, N])          act = identity | exact GELU
+//   out[M, N] = act(A[M, K] . W[N, K]^T + bias[N]) (+ residual[M, N])          act = identity | GELU | SiLU
 //
-// replaces nn.Linear + the separate GELU pass of Mlp (reference basics/models/backbone_vit.py:885-890,968,990) and the
-// separate residual add of SwinTransformerBlock (:1125,:1128).  These GEMMs are HBM-bound (K = 192..768 on millions of
-// token rows), so removing the extra elementwise passes over the 4C-wide hidden tensor is worth more than MMA efficiency.
+// The A operand is never materialised when it is only a re-indexing of an activation tensor; the TMA producer addresses
+//   plain   A = x[M, K] (row stride ldx), optionally continued by a second tensor x2 for columns >= k_split
+//           (neck over the concatenation of two stage outputs, reference backbone_vit.py:239-262, without the concat)
+//   conv    A[(b,y,x), (ky,kx,c)] = in[b, y+ky-pad_t, x+kx-pad_l, c]  -- stride-1 kh x kw convolution on an NHWC tensor as
+//           a "tap GEMM"; zero padding comes from the TMA out-of-bounds fill (conv-MLP 2x2 conv, reference
+//           backbone_vit.py:881-899; the head's 1x1 / 3x3 Conv blocks, common.py:38-52)
+//   merge   A[(b,i,j), (dx,dy,c)] = in[b, 2i+dy, 2j+dx, c]  -- the 2x2 neighbourhood gather of PatchMerging
+//           (reference backbone_vit.py:840-851) as a rank-5 tensor map
+// and replaces nn.Linear + the separate GELU pass of Mlp (backbone_vit.py:885-890,968,990), the separate residual add of
+// SwinTransformerBlock (:1125,:1128), F.pad + Conv2d + GELU of the conv-MLP, and conv + BatchNorm(folded) + SiLU of the head.
+// These GEMMs are HBM-bound (K = 64..3072 on millions of rows), so removing the extra passes is worth more than MMA efficiency.
 //
-// Persistent CTAs (one per SM), tile 128 x BN (BN = 256 or 192), k-block 64:
-//   warp 16     TMA producer: cp.async.bulk.tensor 2-D boxes of x and W, SWIZZLE_128B, 4-stage mbarrier ring
+// Persistent CTAs (one per SM), tile 128 x BN (BN = 256 / 192 / 128 / 64), k-block 64:
+//   warp 16     TMA producer: cp.async.bulk.tensor boxes of A and W, SWIZZLE_128B, mbarrier ring of STAGES stages
 //   warp 17     MMA issuer:   tcgen05.mma kind::f16, M=128, N=BN, K-major SWIZZLE_128B operands, fp32 accumulators in TMEM,
-//                             two accumulator buffers (2 x BN columns) so the epilogue of tile t overlaps the MMAs of t+1
-//   warps 0-15  epilogue:     four groups of 4 warps take the tile's 64-column boxes (residual box TMA-loaded into the group's
-//                             staging buffer first): tcgen05.ld (warp w: TMEM lanes
-//                             32*(w%4)..), bias, GELU (erf by A&S 7.1.26, |error| < 2e-7, far below bf16), residual, bf16
-//                             pack into a SWIZZLE_128B staging box in shared memory, one TMA store per box (full 128-byte
-//                             lines; per-thread 16-byte row stores capped the kernel at ~1.9 TB/s)
+//                             NACC accumulator buffers so the epilogue of tile t overlaps the MMAs of the next tiles
+//   warps 0-15  epilogue:     four groups of 4 warps take the 64-column boxes of the tiles round-robin (residual box
+//                             TMA-loaded into the group's staging buffer first): tcgen05.ld (warp w: TMEM lanes
+//                             32*(w%4)..), bias, activation, residual, bf16 pack into a SWIZZLE_128B staging box in shared
+//                             memory, one TMA store per box (full 128-byte lines; per-thread 16-byte row stores capped
+//                             the kernel at ~1.9 TB/s)
 #include <cuda.h>
 
 #include "common.cuh"
+#include "linear_tc.h"
 #include "tc05.cuh"
 
 namespace sodt {
@@ -33,9 +43,27 @@ constexpr int EPI_WARPS = EPI_GROUPS * 4;
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 
+enum { MODE_PLAIN = 0, MODE_CONV = 1, MODE_MERGE = 2 };
+
+struct Addressing {
+    int mode;
+    int k_split;     // plain: k-blocks read from x before switching to x2 (== K/64 when there is no x2)
+    int cpb;         // conv / merge: 64-channel blocks per tap / per 2x2 position
+    int kw, pad_t, pad_l;
+    int HW, W;       // conv: pixels per image and row width;  merge: W = output row width
+};
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -51,28 +79,23 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
 }
-// exact-GELU with erf from Abramowitz & Stegun 7.1.26 (max abs error 1.5e-7): one MUFU.RCP, one MUFU.EX2, ~10 FMA
-__device__ __forceinline__ float gelu_erf(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float e = p * t * fast_exp2(-z * z * 1.4426950408889634f);   // 1 - erf(z)
-    const float phi = x >= 0.f ? 1.f - 0.5f * e : 0.5f * e;            // Phi(x)
-    return x * phi;
-}
 
-template <int BN, int STAGES>
+template <int BN> struct Cfg {
+    static constexpr int NACC = BN <= 128 ? 4 : 2;                                    // TMEM accumulator buffers (NACC * BN <= 512)
+    static constexpr int STAGES = BN == 256 ? 3 : BN == 192 ? 4 : BN == 128 ? 5 : 6;
+};
+
+template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                 const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r,
-                 const float* __restrict__ bias, int has_residual, int M, int N, int K, int act, int num_n_tiles, int num_tiles) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
+                 const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
+                 const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ bias, int has_residual,
+                 const Addressing ad, int K, int act, int num_n_tiles, int num_tiles) {
+    constexpr int STAGES = Cfg<BN>::STAGES, NACC = Cfg<BN>::NACC;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], res_full[EPI_GROUPS];
+    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[NACC], acc_empty[NACC], res_full[EPI_GROUPS];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -80,7 +103,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32); }
         for (int g = 0; g < EPI_GROUPS; ++g) mbar_init(&res_full[g], 1);
         fence_barrier_init();
     }
@@ -95,11 +118,32 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             int stage = 0, round = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+                const int row0 = mt * BM;
+                int p0 = 0, p1 = 0, p2 = 0;                      // conv: x0, y0, b;  merge: j0, bi0
+                if (ad.mode == MODE_CONV) {
+                    p2 = row0 / ad.HW;
+                    const int rem = row0 - p2 * ad.HW;
+                    p1 = rem / ad.W;
+                    p0 = rem - p1 * ad.W;
+                } else if (ad.mode == MODE_MERGE) {
+                    p1 = row0 / ad.W;
+                    p0 = row0 - p1 * ad.W;
+                }
+                int tap = 0, cc = 0;                             // running (tap, channel block) of the k loop
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (round > 0) mbar_wait(&empty[stage], (uint32_t)((round - 1) & 1));
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     const uint32_t sa = sbase + stage * STAGE_BYTES;
-                    tma_load_2d(sa, &tmap_x, &full[stage], kb * BK, mt * BM);
+                    if (ad.mode == MODE_PLAIN) {
+                        if (kb < ad.k_split) tma_load_2d(sa, &tmap_x, &full[stage], kb * BK, row0);
+                        else tma_load_2d(sa, &tmap_x2, &full[stage], (kb - ad.k_split) * BK, row0);
+                    } else if (ad.mode == MODE_CONV) {
+                        const int ky = tap / ad.kw, kx = tap - ky * ad.kw;
+                        tma_load_4d(sa, &tmap_x, &full[stage], cc * BK, p0 + kx - ad.pad_l, p1 + ky - ad.pad_t, p2);
+                    } else {                                     // K order of the reference concat: (dy,dx) = (0,0),(1,0),(0,1),(1,1)
+                        tma_load_5d(sa, &tmap_x, &full[stage], cc * BK, tap >> 1, p0, tap & 1, p1);
+                    }
+                    if (++cc == ad.cpb) { cc = 0; ++tap; }
                     tma_load_2d(sa + A_BYTES, &tmap_w, &full[stage], kb * BK, nt * BN);
                     if (++stage == STAGES) { stage = 0; ++round; }
                 }
@@ -110,8 +154,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             constexpr uint32_t idesc = idesc_bf16(BM, BN, false, false);
             int stage = 0, round = 0, it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                const int a = it & 1;
-                if (it >= 2) mbar_wait(&acc_empty[a], (uint32_t)(((it >> 1) - 1) & 1));
+                const int a = it % NACC;
+                if (it >= NACC) mbar_wait(&acc_empty[a], (uint32_t)(((it / NACC) - 1) & 1));
                 fence_after_sync();
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[stage], (uint32_t)(round & 1));
@@ -126,7 +170,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         }
     } else {
-        // epilogue group eg = warp/4 takes the tile's 64-column boxes eg, eg + EPI_GROUPS, ...; thread = one row of the box
+        // the 64-column boxes of successive tiles go round-robin to the epilogue groups; thread = one row of the box
         const int quarter = warp & 3, eg = warp >> 2;
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -138,12 +182,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         int it = 0;
         uint32_t res_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int a = it & 1;
+            const int a = it % NACC;
             const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
-            mbar_wait(&acc_full[a], (uint32_t)((it >> 1) & 1));
+            mbar_wait(&acc_full[a], (uint32_t)((it / NACC) & 1));
             fence_after_sync();
 #pragma unroll 1
-            for (int bx = eg; bx < NBOX; bx += EPI_GROUPS) {
+            for (int bx = 0; bx < NBOX; ++bx) {
+                if (((it * NBOX + bx) & (EPI_GROUPS - 1)) != eg) continue;
                 const int col0 = nt * BN + bx * 64;
                 if (issuer) {
                     tma_store_wait_read();                               // the previous box of this group has left smem
@@ -171,7 +216,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                     if (act == 1) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                        for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
+                    } else if (act == 2) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);
                     }
                     const uint32_t dst = my_row + (((j >> 3) ^ sw) << 4);
                     if (has_residual) {
@@ -215,52 +263,125 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-bool make_map(CUtensorMap* m, const void* base, int rows, int K, int box_rows) {
+// bf16 tensor map of rank `rank`; dims / box innermost first, strides in ELEMENTS for dims 1..rank-1
+bool make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const long long* strides, const int* box,
+              CUtensorMapL2promotion promo) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows}, es[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    cuuint64_t d[5], s[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = (cuuint64_t)dims[i]; b[i] = (cuuint32_t)box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) s[i] = (cuuint64_t)strides[i] * 2;
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool make_out_map(CUtensorMap* m, void* base, int M, int N) {
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
-    cuuint64_t strides[1] = {(cuuint64_t)N * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)BM}, es[2] = {1, 1};
-    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+bool make_map_2d(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_rows, bool is_output) {
+    const long long dims[2] = {cols, rows}, strides[1] = {ld};
+    const int box[2] = {64, box_rows};
+    return make_map(m, base, 2, dims, strides, box, is_output ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-template <int BN, int STAGES>
-int launch(const void* x, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K, int act,
-           int num_sms, cudaStream_t stream) {
-    CUtensorMap mx, mw, mo, mr;
-    if (!make_map(&mx, x, M, K, BM) || !make_map(&mw, w, N, K, BN) || !make_out_map(&mo, out, M, N)) return SODT_ERR_CUDA;
-    if (!make_out_map(&mr, const_cast<void*>(residual ? residual : out), M, N)) return SODT_ERR_CUDA;
-    const int num_n_tiles = N / BN, num_m_tiles = (M + BM - 1) / BM;
+template <int BN>
+int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
+    CUtensorMap mw, mo, mr;
+    if (!make_map_2d(&mw, g.w, g.N, g.K, g.K, BN, false) || !make_map_2d(&mo, g.out, g.M, g.N, g.ldo, BM, true)) return SODT_ERR_CUDA;
+    if (!make_map_2d(&mr, g.residual ? g.residual : g.out, g.M, g.N, g.residual ? g.ldr : g.ldo, BM, true)) return SODT_ERR_CUDA;
+    const int num_n_tiles = g.N / BN, num_m_tiles = (g.M + BM - 1) / BM;
     const long long tiles = (long long)num_n_tiles * num_m_tiles;
     if (tiles > 2147483647LL) return SODT_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)STAGES * (A_BYTES + BN * BK * 2) + EPI_GROUPS * BOX_BYTES + 1024;
-    auto kern = linear_tc_kernel<BN, STAGES>;
+    const size_t smem = (size_t)Cfg<BN>::STAGES * (A_BYTES + BN * BK * 2) + EPI_GROUPS * BOX_BYTES + 1024;
+    auto kern = linear_tc_kernel<BN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mw, mo, mr, bias, residual != nullptr ? 1 : 0, M, N, K, act, num_n_tiles, (int)tiles);
+    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, g.bias, g.residual != nullptr ? 1 : 0, ad, g.K, g.act, num_n_tiles, (int)tiles);
     return check_launch();
+}
+
+int dispatch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
+    if (g.N % 256 == 0) return launch<256>(mx, mx2, ad, g, num_sms, stream);
+    if (g.N % 192 == 0) return launch<192>(mx, mx2, ad, g, num_sms, stream);
+    if (g.N % 128 == 0) return launch<128>(mx, mx2, ad, g, num_sms, stream);
+    return launch<64>(mx, mx2, ad, g, num_sms, stream);
 }
 
 }  // namespace
 
-int linear_tc(const void* x, const void* w, const float* bias, const void* residual, void* out, int M, int N, int K, int act,
-              int num_sms, cudaStream_t stream) {
-    if (N % 256 == 0) return launch<256, 3>(x, w, bias, residual, out, M, N, K, act, num_sms, stream);
-    return launch<192, 4>(x, w, bias, residual, out, M, N, K, act, num_sms, stream);
+bool linear_tc_supported(int M, int N, int K) { return M > 0 && K % BK == 0 && K >= BK && N % 64 == 0 && N >= 64; }
+
+int linear_tc(const LinearTcArgs& g, const void* x2, int ldx2, int k_split, int num_sms, cudaStream_t stream) {
+    if (!linear_tc_supported(g.M, g.N, g.K)) return SODT_ERR_UNSUPPORTED;
+    if (g.ldx % 8 || g.ldo % 8 || (g.residual && g.ldr % 8) || g.ldx < (x2 ? k_split : g.K) || g.ldo < g.N) return SODT_ERR_INVALID_ARG;
+    Addressing ad{};
+    ad.mode = MODE_PLAIN;
+    ad.k_split = g.K / BK;
+    ad.cpb = 1 << 30;
+    CUtensorMap mx, mx2;
+    if (x2 != nullptr) {
+        if (k_split <= 0 || k_split >= g.K || k_split % BK || ldx2 % 8 || ldx2 < g.K - k_split) return SODT_ERR_INVALID_ARG;
+        ad.k_split = k_split / BK;
+        if (!make_map_2d(&mx, g.x, g.M, k_split, g.ldx, BM, false) || !make_map_2d(&mx2, x2, g.M, g.K - k_split, ldx2, BM, false))
+            return SODT_ERR_CUDA;
+    } else {
+        if (!make_map_2d(&mx, g.x, g.M, g.K, g.ldx, BM, false)) return SODT_ERR_CUDA;
+        mx2 = mx;
+    }
+    return dispatch(mx, mx2, ad, g, num_sms, stream);
 }
 
-bool linear_tc_supported(int M, int N, int K) { return M > 0 && K % BK == 0 && K >= BK && (N % 256 == 0 || N % 192 == 0); }
+// one 128-row tile = 128 consecutive pixels of an image row (W % 128 == 0) or 128 / W whole rows (128 % W == 0)
+static bool tile_geometry(int H, int W, int* bw, int* bh) {
+    if (W % BM == 0) { *bw = BM; *bh = 1; return true; }
+    if (W > 0 && BM % W == 0 && H % (BM / W) == 0) { *bw = W; *bh = BM / W; return true; }
+    return false;
+}
+
+bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw) {
+    int bw, bh;
+    return B > 0 && Cin % BK == 0 && Cin >= BK && Cout % 64 == 0 && Cout >= 64 && kh >= 1 && kw >= 1 && kh <= 7 && kw <= 7 &&
+           tile_geometry(H, W, &bw, &bh) && (long long)B * H * W < 2147483647LL;
+}
+
+int conv_tc(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int H, int W, int Cin, int Cout,
+            int kh, int kw, int pad_t, int pad_l, int act, int num_sms, cudaStream_t stream) {
+    int bw, bh;
+    if (!conv_tc_supported(B, H, W, Cin, Cout, kh, kw) || !tile_geometry(H, W, &bw, &bh)) return SODT_ERR_UNSUPPORTED;
+    if (ldx % 8 || ldx < Cin || ldo % 8 || ldo < Cout || pad_t < 0 || pad_l < 0 || pad_t >= kh + H || pad_l >= kw + W) return SODT_ERR_INVALID_ARG;
+    LinearTcArgs g{};
+    g.x = x; g.ldx = ldx; g.w = w; g.bias = bias; g.residual = nullptr; g.ldr = 0; g.out = out; g.ldo = ldo;
+    g.M = B * H * W; g.N = Cout; g.K = kh * kw * Cin; g.act = act;
+    Addressing ad{};
+    ad.mode = MODE_CONV; ad.k_split = 0; ad.cpb = Cin / BK; ad.kw = kw; ad.pad_t = pad_t; ad.pad_l = pad_l; ad.HW = H * W; ad.W = W;
+    const long long dims[4] = {Cin, W, H, B}, strides[3] = {ldx, (long long)W * ldx, (long long)H * W * ldx};
+    const int box[4] = {64, bw, bh, 1};
+    CUtensorMap mx;
+    if (!make_map(&mx, x, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return SODT_ERR_CUDA;
+    return dispatch(mx, mx, ad, g, num_sms, stream);
+}
+
+bool merge_tc_supported(int B, int H, int W, int C, int N) {
+    int bw, bh;
+    return B > 0 && H % 2 == 0 && W % 2 == 0 && C % BK == 0 && C >= BK && N % 64 == 0 && N >= 64 &&
+           tile_geometry(B * (H / 2), W / 2, &bw, &bh) && (long long)B * H * W < 2147483647LL;
+}
+
+int merge_tc(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int C, int N, int num_sms,
+             cudaStream_t stream) {
+    int bw, bh;
+    if (!merge_tc_supported(B, H, W, C, N) || !tile_geometry(B * (H / 2), W / 2, &bw, &bh)) return SODT_ERR_UNSUPPORTED;
+    LinearTcArgs g{};
+    g.x = x; g.ldx = C; g.w = w; g.bias = bias; g.residual = nullptr; g.ldr = 0; g.out = out; g.ldo = N;
+    g.M = B * (H / 2) * (W / 2); g.N = N; g.K = 4 * C; g.act = 0;
+    Addressing ad{};
+    ad.mode = MODE_MERGE; ad.k_split = 0; ad.cpb = C / BK; ad.W = W / 2;
+    // in[b, 2i+dy, 2j+dx, c] as (c, dx, j, dy, b*H/2+i)
+    const long long dims[5] = {C, 2, W / 2, 2, (long long)B * (H / 2)};
+    const long long strides[4] = {C, 2LL * C, (long long)W * C, 2LL * W * C};
+    const int box[5] = {64, 1, bw, 1, bh};
+    CUtensorMap mx;
+    if (!make_map(&mx, x, 5, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return SODT_ERR_CUDA;
+    return dispatch(mx, mx, ad, g, num_sms, stream);
+}
 
 }  // namespace sodt

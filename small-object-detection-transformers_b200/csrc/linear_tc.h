@@ -1,0 +1,31 @@
+// Host-side interface of linear_tc.cu (tcgen05 GEMM with TMA-addressed A operand), used by capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sodt {
+
+struct LinearTcArgs {
+    const void* x;          // bf16 A operand (meaning depends on the entry point)
+    int ldx;                // row stride of x in elements
+    const void* w;          // bf16 [N, K] row-major
+    const float* bias;      // fp32 [N] or null
+    const void* residual;   // bf16 [M, N] (row stride ldr) or null
+    int ldr;
+    void* out;              // bf16 [M, N] (row stride ldo)
+    int ldo;
+    int M, N, K;
+    int act;                // 0 identity, 1 GELU, 2 SiLU
+};
+
+bool linear_tc_supported(int M, int N, int K);
+int linear_tc(const LinearTcArgs& g, const void* x2, int ldx2, int k_split, int num_sms, cudaStream_t stream);
+
+bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw);
+int conv_tc(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int H, int W, int Cin, int Cout,
+            int kh, int kw, int pad_t, int pad_l, int act, int num_sms, cudaStream_t stream);
+
+bool merge_tc_supported(int B, int H, int W, int C, int N);
+int merge_tc(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int C, int N, int num_sms,
+             cudaStream_t stream);
+
+}  // namespace sodt

@@ -144,6 +144,24 @@ def _as_f32(t):
     return val
 
 
+_derived_cache = {}
+
+
+def cached_derived(t, tag, fn):
+    """fn(t) cached per tensor object / version / storage address (weights re-laid-out once per load, e.g. conv taps)."""
+    key = (id(t), tag)
+    hit = _derived_cache.get(key)
+    if hit is not None:
+        ref, version, ptr, val = hit
+        if ref() is t and version == t._version and ptr == t.data_ptr():
+            return val
+    if len(_derived_cache) > 4096:
+        _derived_cache.clear()
+    val = fn(t)
+    _derived_cache[key] = (weakref.ref(t), t._version, t.data_ptr(), val)
+    return val
+
+
 def add_layernorm(a, r, weight, bias, eps=1e-5, extra_bias=None, want_sum=False):
     """y = LayerNorm(a (+ r)) over the last dim; optionally also returns a (+ r) (+ extra_bias).
     See sodt_add_layernorm_fwd.  Returns (y, sum_or_None)."""
@@ -245,37 +263,140 @@ def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=No
 USE_TC_LINEAR = True    # bf16 Linear layers on the tcgen05 kernel (False: cuBLAS + separate elementwise passes)
 
 
-def linear(x, weight, bias=None, act=None, residual=None):
-    """act(x @ weight.T + bias) (+ residual) over the last dim of x.  bf16 shapes the tcgen05 kernel supports run there
-    with the activation / residual fused into the epilogue; fp32 and other shapes use cuBLAS (torch) plus elementwise ops."""
-    _require_cuda(x, weight, bias, residual)
-    K = x.shape[-1]
+_LIN_ACT = {None: 0, "none": 0, "gelu": 1, "silu": 2}
+
+
+def _rows(t):
+    """(t2, ld): ``t`` seen as rows of its last dim with one uniform row stride ``ld`` (elements); copies only if the
+    strides do not collapse (column slices of contiguous tensors collapse)."""
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    ld = t.stride(-2) if t.dim() > 1 else t.shape[-1]
+    ok = ld % 8 == 0 and ld >= t.shape[-1] and t.data_ptr() % 16 == 0
+    for d in range(t.dim() - 2):
+        if t.shape[d] != 1 and t.stride(d) != t.stride(d + 1) * t.shape[d + 1]:
+            ok = False
+    if not ok:
+        t = t.contiguous()
+        ld = t.shape[-1]
+    return t, ld
+
+
+def _torch_act(y, act):
+    if act == "gelu":
+        return torch.nn.functional.gelu(y)
+    if act == "silu":
+        return torch.nn.functional.silu(y)
+    if act not in (None, "none"):
+        raise ValueError(f"unsupported activation {act!r}")
+    return y
+
+
+def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None):
+    """act(cat(x, x2) @ weight.T + bias) (+ residual) over the last dim.  bf16 shapes the tcgen05 kernel supports run there
+    with the activation / residual fused into the epilogue; ``x``, ``x2``, ``residual`` and ``out`` may be column slices of
+    wider tensors (row-strided).  fp32 and other shapes use cuBLAS (torch) plus elementwise ops."""
+    _require_cuda(x, weight, bias, residual, x2, out)
+    if act not in _LIN_ACT:
+        raise ValueError(f"unsupported activation {act!r}")
+    K1 = x.shape[-1]
+    K = K1 + (x2.shape[-1] if x2 is not None else 0)
     N = weight.shape[0]
-    M = x.numel() // K
-    if (USE_TC_LINEAR and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and act in (None, "gelu")
+    M = x.numel() // K1
+    if weight.shape[1] != K:
+        raise ValueError("weight must be [N, K]")
+    if (USE_TC_LINEAR and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and (x2 is None or K1 % 64 == 0)
             and _capi.lib().sodt_linear_supported(M, N, K, 1)):
-        x2 = x.contiguous()
+        xa, ldx = _rows(x)
+        xb, ldx2 = _rows(x2) if x2 is not None else (None, 0)
         w = weight.detach().contiguous()
-        res = None
+        res, ldr = None, 0
         if residual is not None:
-            res = residual.contiguous()
-            if res.numel() != M * N or res.dtype != torch.bfloat16:
+            if residual.numel() != M * N or residual.dtype != torch.bfloat16:
                 raise ValueError("residual must be bf16 with the shape of the output")
-        out = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)
+            res, ldr = _rows(residual.reshape(x.shape[:-1] + (N,)) if residual.dim() != x.dim() else residual)
+        if out is None:
+            out = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)
+            ldo = N
+        else:
+            o2, ldo = _rows(out)
+            if o2 is not out or out.dtype != torch.bfloat16 or out.numel() != M * N:
+                raise ValueError("out must be a bf16 row-strided view with M*N elements")
         b32 = _as_f32(bias)
         with torch.cuda.device(x.device), _Timed(f"linear[M={M},N={N},K={K},act={act},res={residual is not None}]"):
-            st = _capi.lib().sodt_linear_fwd(x2.data_ptr(), w.data_ptr(), _ptr(b32), _ptr(res), out.data_ptr(), M, N, K,
-                                             1 if act == "gelu" else 0, 1, _stream())
-        _capi.check(st, "sodt_linear_fwd")
+            st = _capi.lib().sodt_linear_strided_fwd(xa.data_ptr(), ldx, _ptr(xb), ldx2, K1 if x2 is not None else 0, w.data_ptr(),
+                                                     _ptr(b32), _ptr(res), ldr, out.data_ptr(), ldo, M, N, K,
+                                                     _LIN_ACT[act], 1, _stream())
+        _capi.check(st, "sodt_linear_strided_fwd")
         return out
-    y = torch.nn.functional.linear(x, weight, bias)
-    if act == "gelu":
-        y = torch.nn.functional.gelu(y)
-    elif act is not None:
-        raise ValueError(f"unsupported activation {act!r}")
+    xin = torch.cat((x, x2), dim=-1) if x2 is not None else x
+    y = _torch_act(torch.nn.functional.linear(xin, weight, bias), act)
     if residual is not None:
         y = y + residual.view_as(y)
+    if out is not None:
+        out.copy_(y)
+        return out
     return y
+
+
+def conv2d_nhwc_supported(x, cout, kh, kw):
+    """True if ops.conv2d_nhwc runs ``x`` [B,H,W,Cin] on the tcgen05 tap-GEMM kernel."""
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and USE_TC_LINEAR):
+        return False
+    B, H, W, Cin = x.shape
+    return bool(_capi.lib().sodt_conv2d_nhwc_supported(B, H, W, Cin, cout, kh, kw, 1))
+
+
+def conv_weight_taps(weight):
+    """Conv2d weight [Cout, Cin, kh, kw] -> the [Cout, kh*kw*Cin] tap-major matrix sodt_conv2d_nhwc_fwd reads (cached)."""
+    return cached_derived(weight, "taps", lambda w: w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
+
+
+def conv2d_nhwc(x, w_taps, bias, kernel, pad=(0, 0), act=None, out=None):
+    """Stride-1 convolution of a channels-last tensor as a tap GEMM: x [B,H,W,Cin] bf16 (may be a channel slice of a wider
+    tensor), w_taps = conv_weight_taps(weight), ``pad`` = zero rows above / columns left (rows below / right of the image
+    read as zero as far as the kernel reaches).  Returns act(conv + bias) as [B,H,W,Cout]; ``out`` may be a channel slice."""
+    _require_cuda(x, w_taps, bias, out)
+    B, H, W, Cin = x.shape
+    kh, kw = kernel
+    Cout = w_taps.shape[0]
+    if w_taps.shape[1] != kh * kw * Cin or w_taps.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        raise ValueError("w_taps must be bf16 [Cout, kh*kw*Cin]")
+    xa, ldx = _rows(x)
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+        ldo = Cout
+    else:
+        o2, ldo = _rows(out)
+        if o2 is not out or out.dtype != torch.bfloat16 or tuple(out.shape) != (B, H, W, Cout):
+            raise ValueError("out must be a bf16 [B,H,W,Cout] channel-slice view")
+    b32 = _as_f32(bias)
+    with torch.cuda.device(x.device), _Timed(f"conv2d_nhwc[B={B},H={H},W={W},Cin={Cin},Cout={Cout},k={kh}x{kw},act={act}]"):
+        st = _capi.lib().sodt_conv2d_nhwc_fwd(xa.data_ptr(), ldx, w_taps.data_ptr(), _ptr(b32), out.data_ptr(), ldo, B, H, W, Cin, Cout,
+                                              kh, kw, pad[0], pad[1], _LIN_ACT[act], 1, _stream())
+    _capi.check(st, "sodt_conv2d_nhwc_fwd")
+    return out
+
+
+def patch_merge_linear(x, weight, bias=None):
+    """PatchMerging's gather + reduction: x [B,H,W,C] -> [B, H/2 * W/2, N] with the 2x2 neighbourhood concatenated in the
+    reference's channel order (dy,dx) = (0,0),(1,0),(0,1),(1,1) and multiplied by weight [N, 4C]."""
+    _require_cuda(x, weight, bias)
+    B, H, W, C = x.shape
+    N = weight.shape[0]
+    if (USE_TC_LINEAR and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+            and _capi.lib().sodt_patch_merge_linear_supported(B, H, W, C, N, 1)):
+        xa = x.contiguous()
+        w = weight.detach().contiguous()
+        out = torch.empty((B, (H // 2) * (W // 2), N), dtype=torch.bfloat16, device=x.device)
+        b32 = _as_f32(bias)
+        with torch.cuda.device(x.device), _Timed(f"patch_merge_linear[B={B},H={H},W={W},C={C},N={N}]"):
+            st = _capi.lib().sodt_patch_merge_linear_fwd(xa.data_ptr(), w.data_ptr(), _ptr(b32), out.data_ptr(), B, H, W, C, N, 1,
+                                                         _stream())
+        _capi.check(st, "sodt_patch_merge_linear_fwd")
+        return out
+    g = x.view(B, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 4, 2, 5).reshape(B, (H // 2) * (W // 2), 4 * C)
+    return torch.nn.functional.linear(g, weight, bias)
 
 
 # ------------------------------------------------------------------- fused bias + activation (+ crop)

@@ -151,6 +151,82 @@ def test_linear_tc_vs_torch(M, N, K, act, res):
     assert (out.double().cpu() - ref).abs().max() < 0.06 * max(1.0, ref.abs().max().item() / 8)
 
 
+@pytest.mark.parametrize("M,N,K,act", [(1000, 64, 64, "silu"), (777, 128, 384, "silu"), (4096, 128, 512, None), (130, 64, 128, "gelu"),
+                                       (3000, 320, 64, "silu")])
+def test_linear_tc_small_n_and_silu(M, N, K, act):
+    x = fx.det_input(f"lin2_x:{M}:{K}", (M, K)).to("cuda", torch.bfloat16)
+    w = (fx.det_input(f"lin2_w:{N}:{K}", (N, K)) / K ** 0.5).to("cuda", torch.bfloat16)
+    b = 0.2 * fx.det_input(f"lin2_b:{N}", (N,))
+    out = ops().linear(x, w, b.cuda(), act=act)
+    ref = x.double().cpu() @ w.double().cpu().t() + b.double()
+    ref = torch.nn.functional.silu(ref) if act == "silu" else torch.nn.functional.gelu(ref) if act == "gelu" else ref
+    assert out.shape == (M, N) and rel_err(out, ref) < 4e-3
+
+
+def test_linear_tc_strided_operands_and_split_k_sources():
+    """Column slices as x / residual / out (row strides) and an A operand continued by a second tensor (x2)."""
+    M, K1, K2, N = 1500, 192, 192, 256
+    wide = fx.det_input("lin3_wide", (M, 512)).to("cuda", torch.bfloat16)
+    x1, x2 = wide[:, 64:64 + K1], fx.det_input("lin3_x2", (M, K2)).to("cuda", torch.bfloat16)
+    w = (fx.det_input("lin3_w", (N, K1 + K2)) / 20).to("cuda", torch.bfloat16)
+    rwide = fx.det_input("lin3_r", (M, 2 * N)).to("cuda", torch.bfloat16)
+    obuf = torch.full((M, 3 * N), 7.0, dtype=torch.bfloat16, device="cuda")
+    out = ops().linear(x1, w, None, residual=rwide[:, N:], x2=x2, out=obuf[:, N:2 * N])
+    assert out.data_ptr() == obuf[:, N:2 * N].data_ptr()
+    ref = torch.cat((x1, x2), 1).double().cpu() @ w.double().cpu().t() + rwide[:, N:].double().cpu()
+    assert rel_err(obuf[:, N:2 * N], ref) < 4e-3
+    assert (obuf[:, :N] == 7).all() and (obuf[:, 2 * N:] == 7).all()      # neighbours of the slice untouched
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,pad,act", [
+    (2, 16, 256, 192, 192, (2, 2), (0, 0), "gelu"),      # conv-MLP geometry, stage 1 row width
+    (3, 8, 128, 384, 384, (2, 2), (0, 0), "gelu"),       # stage 2 row width
+    (2, 64, 64, 128, 128, (3, 3), (1, 1), "silu"),       # head 3x3, two image rows per tile
+    (1, 128, 128, 64, 64, (3, 3), (1, 1), "silu"),
+    (2, 32, 32, 64, 128, (1, 1), (0, 0), "silu"),        # four rows per tile
+    (2, 4, 256, 128, 64, (1, 1), (0, 0), None),
+    (1, 16, 16, 64, 64, (3, 3), (1, 1), None),           # eight rows per tile
+])
+def test_conv2d_nhwc_tap_gemm_vs_torch(B, H, W, Cin, Cout, k, pad, act):
+    x = fx.det_input(f"cv_x:{B}:{H}:{W}:{Cin}", (B, H, W, Cin)).to("cuda", torch.bfloat16)
+    w = (fx.det_input(f"cv_w:{Cout}:{Cin}:{k}", (Cout, Cin, *k)) / (Cin * k[0] * k[1]) ** 0.5).to("cuda", torch.bfloat16)
+    b = 0.2 * fx.det_input(f"cv_b:{Cout}", (Cout,))
+    assert ops().conv2d_nhwc_supported(x, Cout, *k)
+    out = ops().conv2d_nhwc(x, ops().conv_weight_taps(w), b.cuda(), k, pad, act)
+    xin = x.double().cpu().permute(0, 3, 1, 2)
+    # zero rows / columns: pad[0] above, pad[1] left, and as many below / right as the kernel needs for a same-size output
+    xin = torch.nn.functional.pad(xin, (pad[1], k[1] - 1 - pad[1], pad[0], k[0] - 1 - pad[0]))
+    ref = torch.nn.functional.conv2d(xin, w.double().cpu(), b.double())
+    ref = torch.nn.functional.silu(ref) if act == "silu" else torch.nn.functional.gelu(ref) if act == "gelu" else ref
+    assert out.shape == (B, H, W, Cout)
+    assert rel_err(out, ref.permute(0, 2, 3, 1)) < 4e-3
+
+
+def test_conv2d_nhwc_channel_slices():
+    """Input and output as channel slices of wider NHWC buffers (the head's C3 without torch.cat)."""
+    B, H, W, C = 2, 32, 128, 64
+    wide = fx.det_input("cvs_x", (B, H, W, 2 * C)).to("cuda", torch.bfloat16)
+    w = (fx.det_input("cvs_w", (C, C, 3, 3)) / 24).to("cuda", torch.bfloat16)
+    b = 0.1 * fx.det_input("cvs_b", (C,))
+    obuf = torch.zeros((B, H, W, 2 * C), dtype=torch.bfloat16, device="cuda")
+    ops().conv2d_nhwc(wide[..., C:], ops().conv_weight_taps(w), b.cuda(), (3, 3), (1, 1), "silu", out=obuf[..., :C])
+    ref = torch.nn.functional.silu(torch.nn.functional.conv2d(wide[..., C:].double().cpu().permute(0, 3, 1, 2), w.double().cpu(),
+                                                              b.double(), padding=1)).permute(0, 2, 3, 1)
+    assert rel_err(obuf[..., :C], ref) < 4e-3 and (obuf[..., C:] == 0).all()
+
+
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 16, 256, 192, 384), (2, 32, 128, 384, 768), (3, 8, 64, 64, 128), (1, 64, 16, 128, 64)])
+def test_patch_merge_linear_vs_torch(B, H, W, C, N):
+    x = fx.det_input(f"pm_x:{B}:{H}:{W}:{C}", (B, H, W, C)).to("cuda", torch.bfloat16)
+    w = (fx.det_input(f"pm_w:{N}:{C}", (N, 4 * C)) / (4 * C) ** 0.5).to("cuda", torch.bfloat16)
+    assert ops()._capi.lib().sodt_patch_merge_linear_supported(B, H, W, C, N, 1) == 1
+    out = ops().patch_merge_linear(x, w)
+    xd = x.double().cpu()
+    g = torch.cat([xd[:, 0::2, 0::2], xd[:, 1::2, 0::2], xd[:, 0::2, 1::2], xd[:, 1::2, 1::2]], -1)   # reference order
+    ref = g.reshape(B, -1, 4 * C) @ w.double().cpu().t()
+    assert out.shape == (B, (H // 2) * (W // 2), N) and rel_err(out, ref) < 4e-3
+
+
 # ------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,C,with_r,with_e", [(1000, 192, False, True), (257, 384, True, True), (64, 768, True, False),
