@@ -39,6 +39,10 @@ def enable_kernel_timing(on=True):
     _timing = {} if on else None
 
 
+def kernel_timing_enabled():
+    return _timing is not None
+
+
 def kernel_timings():
     """{label: [ms, ...]} of everything recorded since enable_kernel_timing(); synchronises."""
     if _timing is None:

@@ -63,7 +63,7 @@ class Detector:
     backbone and head (bf16 by default); softmax, LayerNorm statistics, Detect decode and NMS are fp32."""
 
     def __init__(self, cfg=DEFAULT_CFG, state_dict=None, device="cuda", dtype=torch.bfloat16, conf_thres=0.25,
-                 iou_thres=0.45, multi_label=False, agnostic=False, classes=None, nc=8, seed=0):
+                 iou_thres=0.45, multi_label=False, agnostic=False, classes=None, nc=8, seed=0, cuda_graph=True):
         self.device = torch.device(device)
         self.dtype = dtype
         self.nms_args = dict(conf_thres=conf_thres, iou_thres=iou_thres, multi_label=multi_label, agnostic=agnostic,
@@ -76,6 +76,9 @@ class Detector:
         self.model = model.eval().fuse().to(self.device, dtype)
         self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._bufs = {}
+        # one CUDA graph per input shape: the ~1400 launches of a step are replayed with one driver call
+        self.cuda_graph = bool(cuda_graph) and self.device.type == "cuda"
+        self._graphs = {}
 
     def buffer(self, batch):
         if batch not in self._bufs:
@@ -91,12 +94,52 @@ class Detector:
         return pred
 
     @torch.no_grad()
-    def detect_device(self, rgb_u8, ir_u8, buf=None):
-        """Device uint8 inputs -> DetectionBuffer (device resident, no host sync)."""
-        buf = buf or self.buffer(rgb_u8.shape[0])
+    def _detect_eager(self, rgb_u8, ir_u8, buf):
         pred = self.predict(rgb_u8, ir_u8)
         ops.nms(pred, out=buf.det, counts=buf.counts, **self.nms_args)
         return buf
+
+    def _graph_for(self, rgb_u8, ir_u8):
+        """Captures (once per input shape) the whole step on static input / output buffers."""
+        key = (tuple(rgb_u8.shape), tuple(ir_u8.shape))
+        entry = self._graphs.get(key)
+        if entry is None:
+            srgb, sir = rgb_u8.clone(), ir_u8.clone()
+            buf = DetectionBuffer(rgb_u8.shape[0], self.device)
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):          # lazy initialisation (allocator, weight caches, function attributes)
+                for _ in range(2):
+                    self._detect_eager(srgb, sir, buf)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                self._detect_eager(srgb, sir, buf)
+            entry = (graph, srgb, sir, buf, ops.launch_count() - n0)
+            self._graphs[key] = entry
+        return entry
+
+    def launches_per_step(self, rgb_u8, ir_u8):
+        """sodt kernels one step launches (counted while the step's CUDA graph was captured)."""
+        return self._graph_for(rgb_u8, ir_u8)[4]
+
+    @torch.no_grad()
+    def detect_device(self, rgb_u8, ir_u8, buf=None):
+        """Device uint8 inputs -> DetectionBuffer (device resident, no host sync).  Without ``buf`` the returned buffer
+        is reused by the next call with the same batch size."""
+        if (self.cuda_graph and rgb_u8.dtype == torch.uint8 and ir_u8.dtype == torch.uint8 and not ops.kernel_timing_enabled()
+                and not torch.cuda.is_current_stream_capturing()):
+            graph, srgb, sir, gbuf, _ = self._graph_for(rgb_u8, ir_u8)
+            srgb.copy_(rgb_u8)
+            sir.copy_(ir_u8)
+            graph.replay()
+            if buf is None:
+                return gbuf
+            buf.flat.copy_(gbuf.flat)
+            return buf
+        return self._detect_eager(rgb_u8, ir_u8, buf or self.buffer(rgb_u8.shape[0]))
 
     def detect(self, rgb_u8_host, ir_u8_host):
         """Host uint8 images (pinned for async copies) -> (det [B,300,6], counts [B]) on the host."""

@@ -143,6 +143,28 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* Q, const __nv_
             for (int i = 0; i < REP; ++i) mma_ts(tm + 128, tm + 256, bv64, ido64, i > 0);
             mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
             printf("TS M128 N64  K16        : %6.1f cycles per MMA\n", (double)(t1 - t0) / REP);
+            // independent accumulators, round-robin: is ~64 cycles a dependent-chain latency or the throughput floor?
+            for (int nacc = 2; nacc <= 8; nacc *= 2) {
+                t0 = clock64();
+                for (int i = 0; i < REP; ++i) mma_ts(tm + 128 + (i % nacc) * 16, tm + 256, bv, ido16, i >= nacc);
+                mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+                printf("TS M128 N16  K16, %d independent accumulators : %6.1f cycles per MMA\n", nacc, (double)(t1 - t0) / REP);
+            }
+            for (int nacc = 2; nacc <= 4; nacc *= 2) {
+                t0 = clock64();
+                for (int i = 0; i < REP; ++i) mma_ss(tm + (i % nacc) * 64, a, b, ids, i >= nacc);
+                mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+                printf("SS M128 N64  K16, %d independent accumulators : %6.1f cycles per MMA\n", nacc, (double)(t1 - t0) / REP);
+            }
+            for (int nacc = 2; nacc <= 4; nacc *= 2) {   // masked halves: same columns, disjoint lanes
+                t0 = clock64();
+                for (int i = 0; i < REP; ++i) {
+                    const uint32_t A = 0xFFFFFFFFu; const bool up = i & 1;
+                    mma_ts_masked(tm + 128 + ((i >> 1) % nacc) * 16, tm + 256, bv, ido16, i >= 2 * nacc, up ? A : 0u, up ? A : 0u, up ? 0u : A, up ? 0u : A);
+                }
+                mma_commit(&bar); mbar_wait(&bar, phase); phase ^= 1; t1 = clock64();
+                printf("TS M128 N16 masked halves, %d accumulators x 2 lane halves : %6.1f cycles per MMA\n", nacc, (double)(t1 - t0) / REP);
+            }
             {   // the window kernel's per-head issue stream: 2 masked SS (N=64) + commit, 8 masked TS (N=16) + 2 commits
                 const uint32_t A = 0xFFFFFFFFu;
                 t0 = clock64();

@@ -550,3 +550,23 @@ def test_model_1024_runs_and_matches_oracle_adapter():
     assert rel_err(raw[0], raw_ref[0]) < 1e-4
     got, ref = pred.double().cpu(), pred_ref.double()
     assert ((got[..., :4] - ref[..., :4]).abs() / ref[..., :4].abs().clamp_min(1.0)).max() < 1e-3
+
+
+def test_model_detector_graph_replay_matches_eager_and_stream():
+    """runtime.Detector: the CUDA-graph replay of a step, the eager step and the pipelined host API give the same detections."""
+    from sodt_b200.runtime import Detector
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randint(0, 256, (2, 3, 512, 512), dtype=torch.uint8, generator=g).pin_memory(),
+                torch.randint(0, 256, (2, 3, 512, 512), dtype=torch.uint8, generator=g).pin_memory()) for _ in range(3)]
+    eager = Detector(device="cuda", dtype=torch.bfloat16, seed=3, conf_thres=1e-6, cuda_graph=False)
+    graph = Detector(device="cuda", dtype=torch.bfloat16, seed=3, conf_thres=1e-6, cuda_graph=True)
+    want = [tuple(t.clone() for t in eager.detect(*b)) for b in batches]
+    assert sum(int(c.sum()) for _, c in want) > 0
+    for b, (d, c) in zip(batches, want):                      # replayed graph (second and third call reuse the capture)
+        d2, c2 = graph.detect(*b)
+        assert torch.equal(c2, c) and torch.equal(d2, d)
+    assert graph.launches_per_step(batches[0][0].cuda(), batches[0][1].cuda()) > 100
+    got = [(d.clone(), c.clone()) for d, c in graph.detect_stream(iter(batches))]
+    assert len(got) == len(want)
+    for (d2, c2), (d, c) in zip(got, want):
+        assert torch.equal(c2, c) and torch.equal(d2, d)
