@@ -1,24 +1,26 @@
 // 8x8-window attention (N = 64 tokens, head_dim 16 or 32) on tcgen05 tensor cores: the kernel of the
 // backbone's stage 1 and stage 2 (basics/models/backbone_vit.py:114-145; shift 0 or any 0 < shift < 8).
 //
-// A tile is a PAIR of windows (128 query rows = 128 TMEM lanes).  Per head
-//   S[128x64]                      rows 0-63 = Q_w0 K_w0^T, rows 64-127 = Q_w1 K_w1^T: two tcgen05.mma (M=128, N=64) whose
-//                                  "disable output lane" masks let each write only its window's 64 lanes, so the score
-//                                  buffer holds no wasted off-diagonal block (64 TMEM columns per head in flight)
-//   softmax                        one thread per query row: tcgen05.ld of its 64 scores, relative position bias
+// The 128 TMEM lanes of an MMA hold TWO HEADS of one window: lane = 64 * (head parity) + query token.  Per head pair
+//   S[128x64]                      lanes 0-63 = Q_h0 K_h0^T, lanes 64-127 = Q_h1 K_h1^T: two tcgen05.mma (M=128, N=64) whose
+//                                  "disable output lane" masks let each write only its head's 64 lanes (64 TMEM columns)
+//   softmax                        one thread per (head, query row): tcgen05.ld of its 64 scores, relative position bias
 //                                  (closed-form index, bank-conflict-free padded table in shared memory), shifted-window
 //                                  mask from two 64-bit region masks (border windows only), exp2, row sum; P written
 //                                  back to TMEM as packed bf16 (32 columns)
-//   O[128xhd]                      = P V, again two lane-masked MMAs (TS: A = P from TMEM, B = V MN-major), K = 64 keys
-//   epilogue                       O / rowsum -> bf16 -> straight to the un-rolled, un-partitioned output image
+//   O[128 x 2hd]                   = P [V_h0 | V_h1]: ONE unmasked MMA chain (TS: A = P from TMEM, B = the two heads'
+//                                  adjacent V channels, MN-major, N = 2 hd); lane half x reads its head's hd columns.
+//                                  (Pairing two WINDOWS per MMA instead needed two lane-masked chains per head: a masked
+//                                  MMA of these shapes holds the tensor pipe ~100 cycles whatever N is, measured.)
+//   epilogue                       O / rowsum -> bf16 -> staging tile -> full 128-byte lines of the un-rolled output image
 // Roll, partition, reverse partition and reverse roll are address arithmetic in the producer / epilogue.
 //
-// Persistent CTAs (one per SM), 12 warps: NG = 2 softmax groups of 4 warps take head PAIRS round-robin, each with its
-// own S / P / O columns in TMEM (2 x (64 + 32 + 32) columns per group), so one group's TMEM / shared-memory / MUFU
-// latencies are covered by the other.  Hand-offs between the MMA thread and a group happen once per two heads: the
-// mbarrier round trips (not the math) bound the per-head version of this kernel (measured: more groups did not help); three producer warps (q, k, v) stream 64 channels
-// (4 or 2 heads) per stage through a 4-stage cp.async ring; one warp issues the MMAs (a tcgen05.mma of these shapes
-// occupies the tensor pipe ~64 cycles whatever N is: ten MMAs per head make the issue stream a first-order cost).
+// Persistent CTAs (one per SM) walk PAIRS of windows (128 token rows per shared-memory stage), 12 warps: softmax group g
+// (4 warps) owns window g of every pair and takes its head pairs in order, with its own S / P / O columns in TMEM, so
+// one group's TMEM / shared-memory / MUFU latencies are covered by the other.  Hand-offs between the MMA thread and a
+// group happen once per unit (head_dim 16: two head pairs = the 64 channels of a stage; head_dim 32: one pair): the
+// mbarrier round trips, not the math, bound a per-head hand-off.  Three producer warps (q, k, v) stream 64 channels per
+// stage with coalesced 128-byte-per-token loads; one warp issues the MMAs.
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -39,16 +41,19 @@ constexpr int STAGES = 3;
 // rows.  Planes are padded by 16 B so that the 8 chunks of one token row fall into 8 different bank groups when a
 // producer warp writes a whole 128-byte row segment (conflict-free), which lets the producers use fully coalesced
 // 128-byte-per-token global loads (cp.async fetched a 32-byte sector per 16-byte request: 2.5x L2 read traffic).
-constexpr int PLANE = ROWS * 16 + 16;
-constexpr int STAGE_BYTES = 3 * 8 * PLANE;    // q,k,v x 8 planes (= G heads x hd/8 chunks = 64 channels)
-constexpr int CHUNK_STRIDE = PLANE;           // bytes between 8-element chunks of a canonical tile
+constexpr int PLANE = ROWS * 16 + 16;         // V: plane c = channels 8c..8c+7 of the stage, rows = (window, token)
+// Q and K: plane (head pair p, chunk pc) holds chunk pc of BOTH heads of the pair, rows ordered (window, head parity, token),
+// so the 128 rows of one window's head pair are contiguous: the K-major A / B operand of that pair's score MMAs.
+constexpr int PLANE2 = 2 * ROWS * 16 + 32;
+constexpr int OPERAND_BYTES = 8 * PLANE;      // q, k or v part of a stage (8 planes x 128 rows = 4 planes2 x 256 rows)
+constexpr int STAGE_BYTES = 3 * OPERAND_BYTES;
 constexpr int OT_LD = 128 + 16;               // row pitch of the output staging tile (64 channels + pad)
 constexpr int OT_BYTES = ROWS * OT_LD;
 constexpr int TAB_LD = 40;                    // padded row stride of the bias table (bank-conflict free)
 constexpr int TAB_ENTRIES = (2 * WS - 1) * TAB_LD;   // 600 floats per head
 constexpr float LOG2E = 1.4426950408889634f;
-// HPB = heads per barrier hand-off (a "unit"); 2 for head_dim 16 (4 heads per stage), 1 for head_dim 32 (2 per stage)
-// TMEM column bases: S[g][hh] = g*128 + hh*64, P[g][hh] = 256 + g*64 + hh*32, O[g][hh] = 384 + g*64 + hh*32
+// HPB = head pairs per barrier hand-off (a "unit" = one window x the stage's 64 channels): 2 for head_dim 16, 1 for 32
+// TMEM column bases: S[g][hh] = g*HPB*64 + hh*64, P[g][hh] = 256 + g*HPB*32 + hh*32, O[g][hh] = 384 + g*64 + hh*2*hd
 constexpr uint32_t TM_S = 0, TM_P = 256, TM_O = 384;
 
 // [heads][15][40] bias table, scaled by log2(e):  tab[h][(dy+7)*40 + (dx+7)]
@@ -80,9 +85,9 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                         __nv_bfloat16* __restrict__ out, Geo geo, int C, int heads, float scale, float mask_value,
                         long long ntiles) {
     constexpr int G = 64 / HD;                // heads per stage
-    constexpr int HPB = HD == 16 ? 2 : 1;     // heads per hand-off
+    constexpr int HPB = G / 2;                // head pairs per stage = per hand-off
     constexpr int CPH = HD / 8;               // 16-byte chunks per head row
-    constexpr int TILE_BYTES = CPH * PLANE;   // one (q|k|v, head) tile
+    constexpr int PAIR_BYTES = CPH * PLANE2;  // q or k of one head pair, both windows
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t stage_full[STAGES], stage_empty[STAGES], s_full[NG], s_free[NG], p_full[NG], pv_done[NG];
     __shared__ uint32_t tmem_slot;
@@ -97,7 +102,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
     const int groups = heads / G;
     long long my_tiles = 0;
     if ((long long)blockIdx.x < ntiles) my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const long long n_total = my_tiles * (heads / HPB);   // units (head pairs) this CTA processes: u = tile_iter*(heads/2) + h/2
+    const long long n_total = my_tiles * groups * 2;      // units this CTA processes: u = (tile_iter*groups + stage)*2 + window
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&stage_full[s], 32 * NPROD); mbar_init(&stage_empty[s], 1); }
@@ -130,15 +135,17 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
             __syncwarp();
             for (int gi = 0; gi < groups; ++gi) {
                 if (round > 0) mbar_wait(&stage_empty[stage], (uint32_t)((round - 1) & 1));
-                unsigned char* dst = smem + stage * STAGE_BYTES + (which * G + pg) * TILE_BYTES + pc * PLANE + r4 * 16;
+                unsigned char* dst = smem + stage * STAGE_BYTES + which * OPERAND_BYTES + r4 * 16 +
+                                     (which < 2 ? (pg >> 1) * PAIR_BYTES + pc * PLANE2 + (pg & 1) * (NTOK * 16) : (pg * CPH + pc) * PLANE);
+                const int wskip = which < 2 ? NTOK * 16 : 0;        // q, k: window 1 rows start after both heads of window 0
                 const __nv_bfloat16* src = qkv + gi * 64 + j * 8;
 #pragma unroll 1
-                for (int b0 = 0; b0 < ROWS / 4; b0 += 16) {       // 16 x 512 B in flight per warp
+                for (int b0 = 0; b0 < ROWS / 4; b0 += 16) {       // 16 x 512 B in flight per warp; b0 = 16 * window
                     uint4 v[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const uint4*>(src + my_off[(b0 + i) * 4 + r4]));
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) *reinterpret_cast<uint4*>(dst + (b0 + i) * 64) = v[i];
+                    for (int i = 0; i < 16; ++i) *reinterpret_cast<uint4*>(dst + (b0 + i) * 64 + (b0 >> 4) * wskip) = v[i];
                 }
                 fence_proxy_async();
                 mbar_arrive(&stage_full[stage]);
@@ -151,11 +158,11 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         // descriptors are a per-tile base plus compile-time constants.  Work is issued per unit = HPB consecutive heads.
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc_bf16(ROWS, NTOK, false, false);
-            constexpr uint32_t idesc_o = idesc_bf16(ROWS, HD, false, true);
+            constexpr uint32_t idesc_o = idesc_bf16(ROWS, 2 * HD, false, true);
             constexpr uint32_t ALL = 0xFFFFFFFFu;
-            constexpr int UPS = G / HPB;                                       // units per stage
-            const uint64_t kdesc0 = smem_desc(sbase, CHUNK_STRIDE, 128);      // K-major tiles (Q, K)
-            const uint64_t vdesc0 = smem_desc(sbase, 128, CHUNK_STRIDE);      // MN-major tile (V)
+            constexpr int UPS = 2;                                             // units per stage = windows of the pair
+            const uint64_t kdesc0 = smem_desc(sbase, PLANE2, 128);            // K-major tiles (Q, K)
+            const uint64_t vdesc0 = smem_desc(sbase, 128, PLANE);             // MN-major tile (V)
             const int nt = (int)n_total;
             // ---- cursor of the next unit whose scores are to be issued
             int qn = 0, q_us = 0, q_stage = 0, q_stage_par = 0, q_g = 0, q_k = 0;
@@ -165,15 +172,15 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                 fence_after_sync();
 #pragma unroll
                 for (int hh = 0; hh < HPB; ++hh) {
-                    const uint32_t toff = (uint32_t)(q_stage * STAGE_BYTES + (q_us * HPB + hh) * TILE_BYTES) >> 4;
-                    const uint64_t qd = kdesc0 + toff, kd = kdesc0 + toff + ((G * TILE_BYTES) >> 4);
+                    const uint32_t toff = (uint32_t)(q_stage * STAGE_BYTES + hh * PAIR_BYTES + q_us * (2 * NTOK * 16)) >> 4;
+                    const uint64_t qd = kdesc0 + toff, kd = kdesc0 + toff + (OPERAND_BYTES >> 4);
                     const uint32_t d = tm + TM_S + q_g * (HPB * 64) + hh * 64;
 #pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks)
-                        mma_ss_masked(d, qd + ((ks * 2 * CHUNK_STRIDE) >> 4), kd + ((ks * 2 * CHUNK_STRIDE) >> 4), idesc_s, ks > 0, 0u, 0u, ALL, ALL);
+                    for (int ks = 0; ks < HD / 16; ++ks)       // lanes 0-63: even head of the pair
+                        mma_ss_masked(d, qd + ((ks * 2 * PLANE2) >> 4), kd + ((ks * 2 * PLANE2) >> 4), idesc_s, ks > 0, 0u, 0u, ALL, ALL);
 #pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks)
-                        mma_ss_masked(d, qd + ((ks * 2 * CHUNK_STRIDE) >> 4), kd + ((NTOK * 16 + ks * 2 * CHUNK_STRIDE) >> 4), idesc_s, ks > 0,
+                    for (int ks = 0; ks < HD / 16; ++ks)       // lanes 64-127: odd head (its K rows follow the even head's)
+                        mma_ss_masked(d, qd + ((ks * 2 * PLANE2) >> 4), kd + ((NTOK * 16 + ks * 2 * PLANE2) >> 4), idesc_s, ks > 0,
                                       ALL, ALL, 0u, 0u);
                 }
                 mma_commit(&s_full[q_g]);
@@ -189,16 +196,15 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                 if (qn < nt) issue_qk();
                 mbar_wait(&p_full[g], (uint32_t)(k & 1));
                 fence_after_sync();
+                // O[128 x 2hd] = P [V_even | V_odd] per head pair; the pairs' chains are interleaved (independent accumulators)
 #pragma unroll
-                for (int hh = 0; hh < HPB; ++hh) {
-                    const uint64_t vd = vdesc0 + ((uint32_t)(stage * STAGE_BYTES + (2 * G + us * HPB + hh) * TILE_BYTES) >> 4);
-                    const uint32_t d = tm + TM_O + g * (HPB * 32) + hh * 32, a = tm + TM_P + g * (HPB * 32) + hh * 32;
+                for (int ks = 0; ks < NTOK / 16; ++ks) {
 #pragma unroll
-                    for (int ks = 0; ks < NTOK / 16; ++ks)
-                        mma_ts_masked(d, a + ks * 8, vd + ((ks * 256) >> 4), idesc_o, ks > 0, 0u, 0u, ALL, ALL);
-#pragma unroll
-                    for (int ks = 0; ks < NTOK / 16; ++ks)
-                        mma_ts_masked(d, a + ks * 8, vd + ((NTOK * 16 + ks * 256) >> 4), idesc_o, ks > 0, ALL, ALL, 0u, 0u);
+                    for (int hh = 0; hh < HPB; ++hh) {
+                        const uint64_t vd = vdesc0 + ((uint32_t)(stage * STAGE_BYTES + 2 * OPERAND_BYTES + hh * 2 * CPH * PLANE + us * (NTOK * 16)) >> 4);
+                        const uint32_t d = tm + TM_O + g * 64 + hh * (2 * HD), a = tm + TM_P + g * (HPB * 32) + hh * 32;
+                        mma_ts(d, a + ks * 8, vd + ((ks * 256) >> 4), idesc_o, ks > 0);
+                    }
                 }
                 mma_commit(&pv_done[g]);
                 if (++us == UPS) { us = 0; mma_commit(&stage_empty[stage]); if (++stage == STAGES) stage = 0; }
@@ -207,20 +213,20 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         }
     } else {
         // ====================================================== softmax + epilogue groups
-        const int g = warp >> 2;                       // group g takes units n = g, g + NG, ...
-        const int row = tid & 127;                     // TMEM lane == query row of the pair
-        const int wh = row >> 6, ti = row & 63, ty = ti >> 3, tx = ti & 7;
+        const int g = warp >> 2;                       // group g takes units n = g, g + NG, ... = window g of every pair
+        const int row = tid & 127;                     // TMEM lane = 64 * (head parity) + query token
+        const int hp = row >> 6, ti = row & 63, ty = ti >> 3, tx = ti & 7;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tS = tm + TM_S + g * (HPB * 64) + lane_addr;
         const uint32_t tP = tm + TM_P + g * (HPB * 32) + lane_addr;
-        const uint32_t tO = tm + TM_O + g * (HPB * 32) + lane_addr;
+        const uint32_t tO = tm + TM_O + g * 64 + hp * HD + lane_addr;
         const float c = scale * LOG2E, mv2 = mask_value * LOG2E;
         const float* tab_row = tab + (ty + WS - 1) * TAB_LD + (tx + WS - 1);
         const int s_ = geo.shift;
         const uint64_t yhi = s_ > 0 ? (~0ull << (8 * (WS - s_))) : 0ull;                       // keys with ty >= ws - shift
         const uint64_t xhi = s_ > 0 ? 0x0101010101010101ull * (uint64_t)((0xFFu << (WS - s_)) & 0xFFu) : 0ull;  // tx >= ws - shift
         const int nwh = geo.nW / geo.nww;
-        const int units_per_tile = heads / HPB;
+        const int units_per_tile = groups * 2;
         long long k = 0, cur_iter = -1;
         __nv_bfloat16* out_tok = nullptr;
         uint64_t mbits = 0;
@@ -228,7 +234,6 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         // Epilogue: O / rowsum of the previous unit goes to the stage's staging tile; when both groups have delivered
         // their unit of that stage, all 256 softmax threads write the 128 rows x 128 B of the tile with full-line stores.
         bool have_prev = false;
-        int prev_hcol = 0;                              // byte column of the previous unit's first head inside the tile
         long long prev_stage = 0;                       // global stage index of the previous unit (tile_iter*groups + gi)
         float prev_inv[HPB] = {};
         const int st_tid = tid;                         // 0..255 among the softmax threads
@@ -237,7 +242,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
 #pragma unroll
             for (int hh = 0; hh < HPB; ++hh) {
                 uint32_t o[HD];
-                if constexpr (HD == 16) tmem_ld16(tO + hh * 32, o); else tmem_ld32(tO + hh * 32, o);
+                if constexpr (HD == 16) tmem_ld16(tO + hh * (2 * HD), o); else tmem_ld32(tO + hh * (2 * HD), o);
                 tmem_wait_ld();
                 const float inv = prev_inv[hh];
 #pragma unroll
@@ -247,7 +252,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                     v.y = pack_bf16(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
                     v.z = pack_bf16(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
                     v.w = pack_bf16(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
-                    *reinterpret_cast<uint4*>(tile + row * OT_LD + prev_hcol + hh * HD * 2 + j * 2) = v;
+                    *reinterpret_cast<uint4*>(tile + (g * NTOK + ti) * OT_LD + (2 * hh + hp) * HD * 2 + j * 2) = v;
                 }
             }
             asm volatile("bar.sync 2, 256;" ::: "memory");           // both groups' halves of the stage tile are in smem
@@ -268,10 +273,13 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         for (long long n = g; n < n_total; n += NG, ++k) {
             if (it != cur_iter) {                      // new window pair: output row pointer and shifted-window mask bits
                 cur_iter = it;
-                const long long wdx = 2 * ((long long)blockIdx.x + it * gridDim.x) + wh;
+                const long long wdx = 2 * ((long long)blockIdx.x + it * gridDim.x) + g;
                 out_tok = nullptr;
                 mbits = 0;
-                if (g == 0) out_off[(it & 1) * ROWS + row] = wdx < geo.total_windows ? geo.token(wdx, ty, tx) * (long long)C : -1;
+                if (g == 0) {                          // output offsets of the pair's 128 token rows (row = 64 * window + token)
+                    const long long wr = wdx + hp;
+                    out_off[(it & 1) * ROWS + row] = wr < geo.total_windows ? geo.token(wr, ty, tx) * (long long)C : -1;
+                }
                 if (wdx < geo.total_windows) {
                     out_tok = out;
                     if (s_ > 0) {
@@ -288,7 +296,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
             float inv_cur[HPB];
 #pragma unroll
             for (int hh = 0; hh < HPB; ++hh) {
-                const int h = ut * HPB + hh;
+                const int h = (ut >> 1) * G + 2 * hh + hp;
                 float s2[NTOK];
                 {
                     uint32_t r0[32], r1[32];
@@ -330,8 +338,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
             fence_before_sync();
             mbar_arrive(&p_full[g]);
             have_prev = true;
-            prev_stage = it * groups + (ut * HPB) / G;
-            prev_hcol = ((ut * HPB) % G) * HD * 2;
+            prev_stage = it * groups + (ut >> 1);
 #pragma unroll
             for (int hh = 0; hh < HPB; ++hh) prev_inv[hh] = inv_cur[hh];
             ut += NG;
