@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-baseline-images", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
     return ap.parse_args()
 
 
@@ -174,7 +175,7 @@ def run_sodt(args):
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
     B, S, steps, warmup = args.batch, args.img, max(1, args.steps), max(3, args.warmup)
-    det = Detector(device=dev, dtype=dtype, seed=0)
+    det = Detector(device=dev, dtype=dtype, seed=0, cuda_graph=not args.no_graph)
     sharded = ShardedDetector(det) if world > 1 else None
 
     g = torch.Generator().manual_seed(1234 + rank)

@@ -178,6 +178,8 @@ int sodt_nms(const float* pred, const int* classes, int n_classes, float* out, i
  *                            results can be column slices of wider tensors (the head's C3 writes both branches into one
  *                            buffer instead of torch.cat, common.py:114-126); if x2 != NULL, columns [0, k_split) of A come
  *                            from x and [k_split, K) from x2 (neck over concat(block5, block6), backbone_vit.py:239,262).
+ *                            res_rows > 0: the residual has res_rows rows (multiple of 128 dividing M) and repeats, i.e. it is
+ *                            broadcast over the batch (pos_embed added by the 1x1 patch embedding's GEMM, backbone_vit.py:212-214).
  * sodt_conv2d_nhwc_fwd       stride-1 kh x kw convolution as a tap GEMM on an NHWC tensor: A[(b,y,x), (ky,kx,c)] =
  *                            in[b, y+ky-pad_t, x+kx-pad_l, c] addressed by a rank-4 TMA map, zero padding from the TMA
  *                            out-of-bounds fill; w = conv weight permuted to [Cout, kh, kw, Cin].  Replaces F.pad + Conv2d +
@@ -190,7 +192,7 @@ int sodt_linear_supported(int M, int N, int K, int dtype);
 int sodt_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* out,
                     int M, int N, int K, int act, int dtype, void* stream);
 int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, int ldx2, int k_split, const void* w,
-                            const float* bias, const void* residual, int ldr, void* out, int ldo,
+                            const float* bias, const void* residual, int ldr, int res_rows, void* out, int ldo,
                             int M, int N, int K, int act, int dtype, void* stream);
 int sodt_conv2d_nhwc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw, int dtype);
 int sodt_conv2d_nhwc_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo,

@@ -33,7 +33,7 @@ SIGNATURES = {
     "sodt_nms": (_i, [_p, _p, _i, _p, _p, _p, _p, _sz, _i, _i, _i, _f, _d, _i, _i, _i, _i, _i, _i, _f, _p]),
     "sodt_linear_supported": (_i, [_i, _i, _i, _i]),
     "sodt_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
-    "sodt_linear_strided_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "sodt_linear_strided_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_conv2d_nhwc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "sodt_conv2d_nhwc_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_patch_merge_linear_supported": (_i, [_i, _i, _i, _i, _i, _i]),

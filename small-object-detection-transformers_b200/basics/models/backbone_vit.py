@@ -91,10 +91,16 @@ class PatchEmbed(nn.Module):
     def forward(self, x):
         return self.proj(x).permute(0, 2, 3, 1)
 
-    def forward_tokens(self, x):
-        """1x1 / stride-1 projection applied directly on [B,H,W,Cin] tokens as a GEMM."""
+    def forward_tokens(self, x, pos=None):
+        """1x1 / stride-1 projection applied directly on [B,H,W,Cin] tokens as a GEMM; ``pos`` [1,H,W,C] (the absolute
+        position embedding, reference backbone_vit.py:212-214) is added in the GEMM epilogue, broadcast over the batch."""
         w = self.proj.weight
-        return F.linear(x, w.reshape(w.shape[0], w.shape[1]), self.proj.bias)
+        w = w.reshape(w.shape[0], w.shape[1])
+        if x.is_cuda and x.dtype == torch.bfloat16 and (pos is None or (tuple(pos.shape[1:]) == tuple(x.shape[1:3]) + (w.shape[0],)
+                                                                        and (pos.shape[1] * pos.shape[2]) % 128 == 0)):
+            return ops.linear(x, w, self.proj.bias, residual=pos)
+        y = F.linear(x, w, self.proj.bias)
+        return y if pos is None else y + pos
 
 
 class PatchMerging(nn.Module):
@@ -427,9 +433,10 @@ class ImageEncoderViT(nn.Module):
 
     def forward(self, x: torch.Tensor):
         x = self._front_end(x)                                   # [B,h,w,192], the reference's concat
-        x = self.patch_embed.forward_tokens(x)
-        if self.pos_embed is not None and x.shape[1] == self.pos_embed.shape[1]:
-            x = x + self.pos_embed                               # silently skipped on a size mismatch, like the reference
+        pos = self.pos_embed                                     # silently skipped on a size mismatch, like the reference
+        if pos is not None and x.shape[1] != pos.shape[1]:
+            pos = None
+        x = self.patch_embed.forward_tokens(x, pos)
         B, h, w, C = x.shape
         x = x.reshape(B, h * w, C)
         kept = []

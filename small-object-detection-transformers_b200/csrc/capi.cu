@@ -42,11 +42,11 @@ extern "C" int sodt_linear_supported(int M, int N, int K, int dtype) {
 
 extern "C" int sodt_linear_fwd(const void* x, const void* w, const float* bias, const void* residual, void* out,
                                int M, int N, int K, int act, int dtype, void* stream) {
-    return sodt_linear_strided_fwd(x, K, nullptr, 0, 0, w, bias, residual, N, out, N, M, N, K, act, dtype, stream);
+    return sodt_linear_strided_fwd(x, K, nullptr, 0, 0, w, bias, residual, N, 0, out, N, M, N, K, act, dtype, stream);
 }
 
 extern "C" int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, int ldx2, int k_split, const void* w,
-                                       const float* bias, const void* residual, int ldr, void* out, int ldo,
+                                       const float* bias, const void* residual, int ldr, int res_rows, void* out, int ldo,
                                        int M, int N, int K, int act, int dtype, void* stream) {
     using namespace sodt;
     if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0 || act < 0 || act > 2) return SODT_ERR_INVALID_ARG;
@@ -54,7 +54,8 @@ extern "C" int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, i
     if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)) ||
         (x2 && !aligned16(x2)))
         return SODT_ERR_ALIGNMENT;
-    LinearTcArgs g{x, ldx, w, bias, residual, ldr, out, ldo, M, N, K, act};
+    if (res_rows < 0) return SODT_ERR_INVALID_ARG;
+    LinearTcArgs g{x, ldx, w, bias, residual, ldr, res_rows, out, ldo, M, N, K, act};
     return linear_tc(g, x2, ldx2, k_split, sm_count(), static_cast<cudaStream_t>(stream));
 }
 

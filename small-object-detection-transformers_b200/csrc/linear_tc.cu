@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                  const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
                  const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ bias, int has_residual,
-                 const Addressing ad, int K, int act, int num_n_tiles, int num_tiles) {
+                 const Addressing ad, int K, int act, int num_n_tiles, int num_tiles, int res_tiles) {
     constexpr int STAGES = Cfg<BN>::STAGES, NACC = Cfg<BN>::NACC;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -194,7 +194,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tma_store_wait_read();                               // the previous box of this group has left smem
                     if (has_residual) {                                  // residual box lands in the staging buffer (TMA, swizzled)
                         mbar_expect_tx(&res_full[eg], BOX_BYTES);
-                        tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, mt * BM);
+                        tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, (mt % res_tiles) * BM);
                     }
                 }
                 uint32_t r0[32], r1[32];
@@ -286,7 +286,8 @@ template <int BN>
 int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
     CUtensorMap mw, mo, mr;
     if (!make_map_2d(&mw, g.w, g.N, g.K, g.K, BN, false) || !make_map_2d(&mo, g.out, g.M, g.N, g.ldo, BM, true)) return SODT_ERR_CUDA;
-    if (!make_map_2d(&mr, g.residual ? g.residual : g.out, g.M, g.N, g.residual ? g.ldr : g.ldo, BM, true)) return SODT_ERR_CUDA;
+    const int res_rows = g.residual && g.res_rows > 0 ? g.res_rows : g.M;
+    if (!make_map_2d(&mr, g.residual ? g.residual : g.out, res_rows, g.N, g.residual ? g.ldr : g.ldo, BM, true)) return SODT_ERR_CUDA;
     const int num_n_tiles = g.N / BN, num_m_tiles = (g.M + BM - 1) / BM;
     const long long tiles = (long long)num_n_tiles * num_m_tiles;
     if (tiles > 2147483647LL) return SODT_ERR_UNSUPPORTED;
@@ -295,7 +296,8 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, g.bias, g.residual != nullptr ? 1 : 0, ad, g.K, g.act, num_n_tiles, (int)tiles);
+    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, g.bias, g.residual != nullptr ? 1 : 0, ad, g.K, g.act, num_n_tiles, (int)tiles,
+                                          (res_rows + BM - 1) / BM);
     return check_launch();
 }
 
@@ -312,6 +314,7 @@ bool linear_tc_supported(int M, int N, int K) { return M > 0 && K % BK == 0 && K
 
 int linear_tc(const LinearTcArgs& g, const void* x2, int ldx2, int k_split, int num_sms, cudaStream_t stream) {
     if (!linear_tc_supported(g.M, g.N, g.K)) return SODT_ERR_UNSUPPORTED;
+    if (g.residual && g.res_rows > 0 && g.res_rows != g.M && (g.res_rows % BM || g.M % g.res_rows)) return SODT_ERR_INVALID_ARG;
     if (g.ldx % 8 || g.ldo % 8 || (g.residual && g.ldr % 8) || g.ldx < (x2 ? k_split : g.K) || g.ldo < g.N) return SODT_ERR_INVALID_ARG;
     Addressing ad{};
     ad.mode = MODE_PLAIN;
@@ -349,7 +352,7 @@ int conv_tc(const void* x, int ldx, const void* w, const float* bias, void* out,
     if (!conv_tc_supported(B, H, W, Cin, Cout, kh, kw) || !tile_geometry(H, W, &bw, &bh)) return SODT_ERR_UNSUPPORTED;
     if (ldx % 8 || ldx < Cin || ldo % 8 || ldo < Cout || pad_t < 0 || pad_l < 0 || pad_t >= kh + H || pad_l >= kw + W) return SODT_ERR_INVALID_ARG;
     LinearTcArgs g{};
-    g.x = x; g.ldx = ldx; g.w = w; g.bias = bias; g.residual = nullptr; g.ldr = 0; g.out = out; g.ldo = ldo;
+    g.x = x; g.ldx = ldx; g.w = w; g.bias = bias; g.residual = nullptr; g.ldr = 0; g.res_rows = 0; g.out = out; g.ldo = ldo;
     g.M = B * H * W; g.N = Cout; g.K = kh * kw * Cin; g.act = act;
     Addressing ad{};
     ad.mode = MODE_CONV; ad.k_split = 0; ad.cpb = Cin / BK; ad.kw = kw; ad.pad_t = pad_t; ad.pad_l = pad_l; ad.HW = H * W; ad.W = W;
@@ -371,7 +374,7 @@ int merge_tc(const void* x, const void* w, const float* bias, void* out, int B, 
     int bw, bh;
     if (!merge_tc_supported(B, H, W, C, N) || !tile_geometry(B * (H / 2), W / 2, &bw, &bh)) return SODT_ERR_UNSUPPORTED;
     LinearTcArgs g{};
-    g.x = x; g.ldx = C; g.w = w; g.bias = bias; g.residual = nullptr; g.ldr = 0; g.out = out; g.ldo = N;
+    g.x = x; g.ldx = C; g.w = w; g.bias = bias; g.residual = nullptr; g.ldr = 0; g.res_rows = 0; g.out = out; g.ldo = N;
     g.M = B * (H / 2) * (W / 2); g.N = N; g.K = 4 * C; g.act = 0;
     Addressing ad{};
     ad.mode = MODE_MERGE; ad.k_split = 0; ad.cpb = C / BK; ad.W = W / 2;

@@ -11,6 +11,7 @@ struct LinearTcArgs {
     const float* bias;      // fp32 [N] or null
     const void* residual;   // bf16 [M, N] (row stride ldr) or null
     int ldr;
+    int res_rows;           // the residual has res_rows rows and repeats every res_rows rows of out (0: M rows)
     void* out;              // bf16 [M, N] (row stride ldo)
     int ldo;
     int M, N, K;

@@ -314,11 +314,17 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None):
         xa, ldx = _rows(x)
         xb, ldx2 = _rows(x2) if x2 is not None else (None, 0)
         w = weight.detach().contiguous()
-        res, ldr = None, 0
+        res, ldr, res_rows = None, 0, 0
         if residual is not None:
-            if residual.numel() != M * N or residual.dtype != torch.bfloat16:
-                raise ValueError("residual must be bf16 with the shape of the output")
-            res, ldr = _rows(residual.reshape(x.shape[:-1] + (N,)) if residual.dim() != x.dim() else residual)
+            if residual.dtype != torch.bfloat16 or residual.shape[-1] != N:
+                raise ValueError("residual must be bf16 with N columns")
+            if residual.numel() == M * N:
+                res, ldr = _rows(residual.reshape(x.shape[:-1] + (N,)) if residual.dim() != x.dim() else residual)
+            else:       # broadcast over the leading (batch) dims: the residual repeats every res_rows rows
+                res_rows = residual.numel() // N
+                if res_rows % 128 or M % res_rows:
+                    raise ValueError("a broadcast residual must have a multiple of 128 rows that divides M")
+                res, ldr = residual.reshape(res_rows, N).contiguous(), N
         if out is None:
             out = torch.empty(x.shape[:-1] + (N,), dtype=torch.bfloat16, device=x.device)
             ldo = N
@@ -329,14 +335,14 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None):
         b32 = _as_f32(bias)
         with torch.cuda.device(x.device), _Timed(f"linear[M={M},N={N},K={K},act={act},res={residual is not None}]"):
             st = _capi.lib().sodt_linear_strided_fwd(xa.data_ptr(), ldx, _ptr(xb), ldx2, K1 if x2 is not None else 0, w.data_ptr(),
-                                                     _ptr(b32), _ptr(res), ldr, out.data_ptr(), ldo, M, N, K,
+                                                     _ptr(b32), _ptr(res), ldr, res_rows, out.data_ptr(), ldo, M, N, K,
                                                      _LIN_ACT[act], 1, _stream())
         _capi.check(st, "sodt_linear_strided_fwd")
         return out
     xin = torch.cat((x, x2), dim=-1) if x2 is not None else x
     y = _torch_act(torch.nn.functional.linear(xin, weight, bias), act)
     if residual is not None:
-        y = y + residual.view_as(y)
+        y = y + (residual.view_as(y) if residual.numel() == y.numel() else residual)
     if out is not None:
         out.copy_(y)
         return out

@@ -178,6 +178,18 @@ def test_linear_tc_strided_operands_and_split_k_sources():
     assert (obuf[:, :N] == 7).all() and (obuf[:, 2 * N:] == 7).all()      # neighbours of the slice untouched
 
 
+def test_linear_tc_batch_broadcast_residual():
+    """A residual with fewer rows than the output repeats over the batch (pos_embed in the patch-embedding GEMM)."""
+    B, L, K, N = 3, 256, 192, 192
+    x = fx.det_input("lin4_x", (B, L, K)).to("cuda", torch.bfloat16)
+    w = (fx.det_input("lin4_w", (N, K)) / 14).to("cuda", torch.bfloat16)
+    b = 0.2 * fx.det_input("lin4_b", (N,))
+    pos = fx.det_input("lin4_pos", (1, L, N)).to("cuda", torch.bfloat16)
+    out = ops().linear(x, w, b.cuda(), residual=pos)
+    ref = x.double().cpu() @ w.double().cpu().t() + b.double() + pos.double().cpu()
+    assert out.shape == (B, L, N) and rel_err(out, ref) < 4e-3
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,pad,act", [
     (2, 16, 256, 192, 192, (2, 2), (0, 0), "gelu"),      # conv-MLP geometry, stage 1 row width
     (3, 8, 128, 384, 384, (2, 2), (0, 0), "gelu"),       # stage 2 row width

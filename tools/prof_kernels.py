@@ -29,6 +29,27 @@ for name, t, heads, ws in cases:
             ops.window_attention(t, table, heads, ws, shift)
     torch.cuda.synchronize()
     del t
+# GEMM-shaped layers (stage-1 geometry): qkv, proj + residual, fc1 + GELU, fc2 + residual, conv-MLP taps, PatchMerging
+M = B * 256 * 256
+xt = torch.randn(M, 192, device=dev, generator=g).to(torch.bfloat16)
+w = lambda n, k: (torch.randn(n, k, device=dev, generator=g) / k ** 0.5).to(torch.bfloat16)
+bias = lambda n: 0.1 * torch.randn(n, device=dev, generator=g)
+for _ in range(reps):
+    ops.linear(xt, w(576, 192), bias(576))
+    ops.linear(xt, w(192, 192), bias(192), residual=xt)
+    hid = ops.linear(xt, w(768, 192), bias(768), act="gelu")
+    ops.linear(hid, w(192, 768), bias(192), residual=xt)
+    ops.conv2d_nhwc(xt.view(B, 256, 256, 192), w(192, 4 * 192), bias(192), (2, 2), (0, 0), "gelu")
+    ops.patch_merge_linear(xt.view(B, 256, 256, 192), w(384, 768))
+    ops.add_layernorm(xt, None, torch.ones(192, device=dev), torch.zeros(192, device=dev), 1e-5)
+    del hid
+del xt
+img = torch.rand(B, 4, 1024, 1024, device=dev, generator=g).to(torch.bfloat16)
+cw, cb = 0.3 * torch.randn(4, 48, 16, device=dev, generator=g), 0.1 * torch.randn(4, 48, device=dev, generator=g)
+for _ in range(reps):
+    ops.frontend(img, cw, cb, torch.ones(4, 48, device=dev), torch.zeros(4, 48, device=dev), pad_r=1, eps=1e-5)
+del img
+torch.cuda.synchronize()
 streams = [torch.randn(B, 48, 256, 256, device=dev, generator=g).to(torch.bfloat16).permute(0, 2, 3, 1) for _ in range(4)]
 ln_w, ln_b = torch.ones(4, 48, device=dev), torch.zeros(4, 48, device=dev)
 for _ in range(reps):
