@@ -194,6 +194,22 @@ int sodt_linear_fwd(const void* x, const void* w, const float* bias, const void*
 int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, int ldx2, int k_split, const void* w,
                             const float* bias, const void* residual, int ldr, int res_rows, void* out, int ldo,
                             int M, int N, int K, int act, int dtype, void* stream);
+/*
+ * LayerNorm folded into the following Linear (norm1 -> attn.qkv, norm2 -> mlp.fc1: backbone_vit.py:1089-1093,1128):
+ *   out = act(LayerNorm(x) . W^T + b) (+ residual)  computed as  rstd_row * (x . W'^T) - mean_row * rstd_row * colsum + b'
+ * with W' = W * diag(ln_weight) (bf16), colsum[n] = sum_k W'[n,k] (fp32, of the bf16 values), b' = b + W . ln_bias, all
+ * prepared by the caller once per weight load.  ln_mean_rstd [M][2] fp32 holds (mean, rstd) of every row of x, from
+ *   sodt_row_stats       one read pass over x, or
+ *   sodt_stats_finalize  from the partial (sum, sum of squares) pairs, one per 64-column box, [N/64][M][2], that the GEMM
+ *                        which WROTE x emitted through `stats_out` of this function (from its fp32 values before the bf16
+ *                        rounding) - then no pass over the token tensor is left for the LayerNorm at all.
+ * ln_mean_rstd == NULL: a plain Linear that only emits stats_out.
+ */
+int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, const float* ln_colsum,
+                       const void* w, const float* bias, const void* residual, int ldr, void* out, int ldo,
+                       float* stats_out, int M, int N, int K, int act, int dtype, void* stream);
+int sodt_row_stats(const void* x, long long ld, float* mean_rstd, long long rows, int C, float eps, int dtype, void* stream);
+int sodt_stats_finalize(const float* partials, int boxes, float* mean_rstd, long long rows, int C, float eps, void* stream);
 int sodt_conv2d_nhwc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw, int dtype);
 int sodt_conv2d_nhwc_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo,
                          int B, int H, int W, int Cin, int Cout, int kh, int kw, int pad_t, int pad_l,

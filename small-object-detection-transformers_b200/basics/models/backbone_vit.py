@@ -91,16 +91,18 @@ class PatchEmbed(nn.Module):
     def forward(self, x):
         return self.proj(x).permute(0, 2, 3, 1)
 
-    def forward_tokens(self, x, pos=None):
+    def forward_tokens(self, x, pos=None, want_stats=False):
         """1x1 / stride-1 projection applied directly on [B,H,W,Cin] tokens as a GEMM; ``pos`` [1,H,W,C] (the absolute
         position embedding, reference backbone_vit.py:212-214) is added in the GEMM epilogue, broadcast over the batch."""
         w = self.proj.weight
         w = w.reshape(w.shape[0], w.shape[1])
         if x.is_cuda and x.dtype == torch.bfloat16 and (pos is None or (tuple(pos.shape[1:]) == tuple(x.shape[1:3]) + (w.shape[0],)
                                                                         and (pos.shape[1] * pos.shape[2]) % 128 == 0)):
-            return ops.linear(x, w, self.proj.bias, residual=pos)
+            y = ops.linear(x, w, self.proj.bias, residual=pos)
+            return (y, None) if want_stats else y
         y = F.linear(x, w, self.proj.bias)
-        return y if pos is None else y + pos
+        y = y if pos is None else y + pos
+        return (y, None) if want_stats else y
 
 
 class PatchMerging(nn.Module):
@@ -145,15 +147,21 @@ class Mlp(nn.Module):
             self.fc2 = nn.Linear(in_features, out_features)
         self.drop = nn.Dropout(drop)
 
-    def hidden(self, x, H, W):
-        """Everything before fc2: fc1 -> GELU, or fc1 -> zero-pad -> 2x2 conv -> GELU.  [B, L, hidden]."""
+    def hidden(self, x, H, W, ln=None):
+        """Everything before fc2: fc1 -> GELU, or fc1 -> zero-pad -> 2x2 conv -> GELU.  [B, L, hidden].
+        ``ln=(norm, mean_rstd)``: ``x`` is the un-normalised residual stream and ``norm`` (the block's norm2) is folded into fc1."""
         exact_gelu = isinstance(self.act, nn.GELU) and self.act.approximate == "none"
+        w1, b1, fold = self.fc1.weight, self.fc1.bias, None
+        if ln is not None:
+            norm, stats = ln
+            w1, colsum, b1 = ops.fold_layernorm(self.fc1.weight, self.fc1.bias, norm.weight, norm.bias)
+            fold = (stats, colsum)
         if self.linear:
             if exact_gelu and x.is_cuda:
-                return ops.linear(x, self.fc1.weight, self.fc1.bias, act="gelu")    # GELU fused into the GEMM epilogue (bf16)
+                return ops.linear(x, w1, b1, act="gelu", ln=fold)    # GELU fused into the GEMM epilogue (bf16)
             return self.act(self.fc1(x))
         B, L, C = x.shape
-        h = ops.linear(x, self.fc1.weight, self.fc1.bias) if x.is_cuda else self.fc1(x)
+        h = ops.linear(x, w1, b1, ln=fold) if x.is_cuda else self.fc1(x)
         h4 = h.view(B, H, W, C)
         conv = self.conv1
         if exact_gelu and conv.kernel_size == (2, 2) and ops.conv2d_nhwc_supported(h4, C, 2, 2):
@@ -255,8 +263,10 @@ class SwinTransformerBlock(nn.Module):
         self.register_buffer("attn_mask", mask)
         self.fused_window_process = fused_window_process   # subsumed: windows are never materialised
 
-    def forward(self, x, hw: Optional[Tuple[int, int]] = None):
-        """x [B, H*W, C].  ``hw`` overrides the construction-time token grid (extension)."""
+    def forward(self, x, hw: Optional[Tuple[int, int]] = None, stats=None, want_stats=False):
+        """x [B, H*W, C].  ``hw`` overrides the construction-time token grid (extension).
+        ``stats`` / ``want_stats`` (extension, bf16): row statistics of ``x`` from the kernel that produced it, and whether to
+        return those of the result -> (x, stats); they let norm1 / norm2 run inside the qkv / fc1 GEMMs."""
         H, W = hw if hw is not None else self.input_resolution
         B, L, C = x.shape
         if L != H * W:
@@ -264,6 +274,20 @@ class SwinTransformerBlock(nn.Module):
         if min(H, W) <= self.window_size and (H != W or H != self.window_size):
             raise ValueError(f"token grid {H}x{W} is smaller than the window {self.window_size}")
         attn, mlp = self.attn, self.mlp
+        if x.dtype == torch.bfloat16 and ops.USE_TC_LINEAR and ops.linear_ln_supported(x, C):
+            # bf16, LayerNorms folded: qkv and fc1 read the raw residual stream and normalise in their epilogues from the row
+            # statistics that the proj / fc2 GEMM (or the producer of x) emitted with its result
+            mr = ops.finalize_stats(stats, C, self.norm1.eps) if stats is not None else ops.row_stats(x, self.norm1.eps)
+            wq, csq, bq = ops.fold_layernorm(attn.qkv.weight, attn.qkv.bias, self.norm1.weight, self.norm1.bias)
+            qkv = ops.linear(x, wq, bq, ln=(mr, csq))
+            o = ops.window_attention(qkv.view(B, H, W, 3 * C), attn.relative_position_bias_table, attn.num_heads,
+                                     self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
+                                     mask_value=MASK_VALUE)
+            x, st = ops.linear(o.view(B, L, C), attn.proj.weight, attn.proj.bias, residual=x, want_stats=True)
+            h = mlp.hidden(x, H, W, ln=(self.norm2, ops.finalize_stats(st, C, self.norm2.eps)))
+            if want_stats:
+                return ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x, want_stats=True)
+            return ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x)
         if x.dtype == torch.bfloat16 and ops.USE_TC_LINEAR:
             # bf16: every Linear runs on the tcgen05 GEMM with its bias / GELU / residual fused into the epilogue
             y, _ = ops.add_layernorm(x, None, self.norm1.weight, self.norm1.bias, self.norm1.eps)
@@ -274,7 +298,8 @@ class SwinTransformerBlock(nn.Module):
             x = ops.linear(o.view(B, L, C), attn.proj.weight, attn.proj.bias, residual=x)
             z, _ = ops.add_layernorm(x, None, self.norm2.weight, self.norm2.bias, self.norm2.eps)
             h = mlp.hidden(z, H, W)
-            return ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x)
+            x = ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x)
+            return (x, None) if want_stats else x
         # fp32 (exact) mode: cuBLAS GEMMs; LN1's second output is the residual stream with proj.bias pre-added, so that the
         # proj GEMM adds the residual in its epilogue (addmm) and no elementwise add pass is left.
         y, xb = ops.add_layernorm(x, None, self.norm1.weight, self.norm1.bias, self.norm1.eps,
@@ -286,7 +311,8 @@ class SwinTransformerBlock(nn.Module):
         z, xb = ops.add_layernorm(x, None, self.norm2.weight, self.norm2.bias, self.norm2.eps,
                                   extra_bias=mlp.fc2.bias, want_sum=True)
         h = mlp.hidden(z, H, W)
-        return torch.addmm(xb.view(B * L, C), h.view(B * L, h.shape[-1]), mlp.fc2.weight.t()).view(B, L, C)
+        x = torch.addmm(xb.view(B * L, C), h.view(B * L, h.shape[-1]), mlp.fc2.weight.t()).view(B, L, C)
+        return (x, None) if want_stats else x
 
     def extra_repr(self):
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
@@ -397,8 +423,9 @@ class ImageEncoderViT(nn.Module):
 
     @staticmethod
     def _run_stage(blocks, x, hw):
+        st = None                                  # row statistics travel with x from GEMM epilogue to GEMM epilogue
         for blk in blocks:
-            x = blk(x, hw)
+            x, st = blk(x, hw, stats=st, want_stats=True)
         return x
 
     def _front_end_params(self):
@@ -439,9 +466,9 @@ class ImageEncoderViT(nn.Module):
         x = self.patch_embed.forward_tokens(x, pos)
         B, h, w, C = x.shape
         x = x.reshape(B, h * w, C)
-        kept = []
+        kept, st = [], None
         for n, blk in enumerate(self.stage1):
-            x = blk(x, (h, w))
+            x, st = blk(x, (h, w), stats=st, want_stats=True)
             if n in (4, 5):
                 kept.append(x.view(B, h, w, C))
         x = self.pmerging1(x, (h, w))

@@ -218,8 +218,78 @@ int dispatch(const void* a, const void* r, const float* w, const float* b, const
     return launch<T, 16>(a, r, w, b, extra_bias, sum_out, y, rows, C, eps, stream);
 }
 
+// (mean, rstd) of every bf16 row: the statistics a LayerNorm folded into the next GEMM needs (linear_tc.cu).
+// 8 lanes per row, 16-byte loads; one read pass, 8 bytes written per row.
+__global__ void __launch_bounds__(256)
+row_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ stats, long long rows, int C, long long ld, float eps) {
+    const int sub = threadIdx.x & 7;
+    const int chunks = C >> 3;
+    const float inv = 1.f / (float)C;
+    for (long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); row < rows; row += (long long)gridDim.x * 32) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + row * ld);
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = sub; c < chunks; c += 8) {
+            const uint4 q = __ldg(src + c);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xFFFF0000u);
+                s1 += lo + hi;
+                s2 = fmaf(lo, lo, fmaf(hi, hi, s2));
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        const float mean = s1 * inv;
+        if (sub == 0) stats[row] = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, s2 * inv), 0.f) + eps));
+    }
+}
+
+// Partial (sum, sum of squares) per 64-column box, [boxes][rows][2] as emitted by the GEMM epilogue, -> (mean, rstd) per row.
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ stats, long long rows, int boxes, float inv, float eps) {
+    for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < rows; row += (long long)gridDim.x * 256) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int b = 0; b < boxes; b += 4) {
+            float2 p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[i] = b + i < boxes ? __ldg(part + (size_t)(b + i) * rows + row) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { s1 += p[i].x; s2 += p[i].y; }
+        }
+        const float mean = s1 * inv;
+        stats[row] = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, s2 * inv), 0.f) + eps));
+    }
+}
+
 }  // namespace
 }  // namespace sodt
+
+extern "C" int sodt_row_stats(const void* x, long long ld, float* mean_rstd, long long rows, int C, float eps, int dtype, void* stream) {
+    using namespace sodt;
+    if (!x || !mean_rstd || rows <= 0 || C <= 0 || ld < C || eps < 0.f) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_BF16 || C % 8 || ld % 8) return SODT_ERR_UNSUPPORTED;
+    if (!aligned16(x) || (reinterpret_cast<uintptr_t>(mean_rstd) & 7)) return SODT_ERR_ALIGNMENT;
+    long long blocks = (rows + 31) / 32;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    row_stats_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), reinterpret_cast<float2*>(mean_rstd), rows, C, ld, eps);
+    return check_launch();
+}
+
+extern "C" int sodt_stats_finalize(const float* partials, int boxes, float* mean_rstd, long long rows, int C, float eps, void* stream) {
+    using namespace sodt;
+    if (!partials || !mean_rstd || rows <= 0 || boxes <= 0 || C <= 0 || eps < 0.f) return SODT_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(partials) & 7) || (reinterpret_cast<uintptr_t>(mean_rstd) & 7)) return SODT_ERR_ALIGNMENT;
+    long long blocks = (rows + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    stats_finalize_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(partials), reinterpret_cast<float2*>(mean_rstd), rows, boxes, 1.f / (float)C, eps);
+    return check_launch();
+}
 
 extern "C" int sodt_add_layernorm_fwd(const void* a, const void* r, const float* w, const float* b, const float* extra_bias,
                                       void* sum_out, void* y, long long rows, int C, float eps, int dtype, void* stream) {

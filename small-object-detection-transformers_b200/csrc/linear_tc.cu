@@ -45,6 +45,14 @@ constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 
 enum { MODE_PLAIN = 0, MODE_CONV = 1, MODE_MERGE = 2 };
 
+struct Epilogue {
+    const float* bias;
+    const float* ln_stats;      // [M][2] (mean, rstd) of the A rows or null
+    const float* ln_colsum;
+    float* stats_out;
+    int M, has_residual, act, res_tiles;
+};
+
 struct Addressing {
     int mode;
     int k_split;     // plain: k-blocks read from x before switching to x2 (== K/64 when there is no x2)
@@ -89,8 +97,8 @@ template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                  const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
-                 const __grid_constant__ CUtensorMap tmap_r, const float* __restrict__ bias, int has_residual,
-                 const Addressing ad, int K, int act, int num_n_tiles, int num_tiles, int res_tiles) {
+                 const __grid_constant__ CUtensorMap tmap_r, const Epilogue ep,
+                 const Addressing ad, int K, int num_n_tiles, int num_tiles) {
     constexpr int STAGES = Cfg<BN>::STAGES, NACC = Cfg<BN>::NACC;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -181,9 +189,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         constexpr int NBOX = BN / 64;
         int it = 0;
         uint32_t res_phase = 0;
+        const float* __restrict__ bias = ep.bias;
+        const int has_residual = ep.has_residual, act = ep.act;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int a = it % NACC;
             const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+            const int grow = mt * BM + row_in_tile;                      // global output row of this thread
             mbar_wait(&acc_full[a], (uint32_t)((it / NACC) & 1));
             fence_after_sync();
 #pragma unroll 1
@@ -194,25 +205,45 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tma_store_wait_read();                               // the previous box of this group has left smem
                     if (has_residual) {                                  // residual box lands in the staging buffer (TMA, swizzled)
                         mbar_expect_tx(&res_full[eg], BOX_BYTES);
-                        tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, (mt % res_tiles) * BM);
+                        tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, (mt % ep.res_tiles) * BM);
                     }
                 }
-                uint32_t r0[32], r1[32];
-                tmem_ld32(tm + lane_addr + a * BN + bx * 64, r0);
-                tmem_ld32(tm + lane_addr + a * BN + bx * 64 + 32, r1);
+                // (mean, rstd) of this thread's A row for a folded LayerNorm; the load is issued ahead of the TMEM load
+                float2 mr = make_float2(0.f, 1.f);
+                if (ep.ln_stats != nullptr && grow < ep.M) mr = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + grow);
+                // accumulator columns in chunks of 16, the next chunk in flight while this one is processed (the kernel
+                // runs at the register cap of 576 threads: two 32-column loads spilled once the LayerNorm terms were added)
+                uint32_t ra[16], rb[16];
+                const uint32_t tsrc = tm + lane_addr + a * BN + bx * 64;
+                tmem_ld16(tsrc, ra);
                 tmem_wait_ld();
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");      // staging box reusable for everyone
                 if (has_residual) { mbar_wait(&res_full[eg], res_phase); res_phase ^= 1; }
+                const float rstd = mr.y, nmr = -mr.x * mr.y;                      // rstd and -mean * rstd of the A row
+                float so = 0.f, sso = 0.f;                                        // statistics of the output row
 #pragma unroll
                 for (int j = 0; j < 64; j += 8) {
+                    if ((j & 15) == 0 && j + 16 < 64) {                           // prefetch the next 16 columns
+                        if (j & 16) tmem_ld16(tsrc + j + 16, ra); else tmem_ld16(tsrc + j + 16, rb);
+                    }
                     float v[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(j < 32 ? r0[j + e] : r1[j - 32 + e]);
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float((j & 16) ? rb[(j & 8) + e] : ra[(j & 8) + e]);
+                    float bb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     if (bias != nullptr) {
                         const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
                         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                        bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+                    }
+                    if (ep.ln_stats != nullptr) {                                 // rstd acc + (bias - mean rstd colsum[n]): two FMAs
+                        const float4 c0 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0 + j));
+                        const float4 c1 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0 + j + 4));
+                        const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = fmaf(rstd, v[e], fmaf(nmr, cs[e], bb[e]));
+                    } else if (bias != nullptr) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] += bb[e];
                     }
                     if (act == 1) {
 #pragma unroll
@@ -232,9 +263,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             v[2 * e] += __low2float(h); v[2 * e + 1] += __high2float(h);
                         }
                     }
+                    if (ep.stats_out != nullptr) {        // of the fp32 values: differs from the stored bf16 row by < 2^-9 / sqrt(N) rms
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { so += v[e]; sso = fmaf(v[e], v[e], sso); }
+                    }
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
                                  "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
+                    if ((j & 15) == 8 && j + 8 < 64) tmem_wait_ld();              // the prefetched chunk has landed
                 }
+                if (ep.stats_out != nullptr && grow < ep.M)
+                    reinterpret_cast<float2*>(ep.stats_out)[(size_t)(col0 >> 6) * ep.M + grow] = make_float2(so, sso);
                 fence_proxy_async();
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
                 if (issuer) { tma_store_2d(&tmap_o, stage_box, col0, mt * BM); tma_store_commit(); }
@@ -296,8 +334,11 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, g.bias, g.residual != nullptr ? 1 : 0, ad, g.K, g.act, num_n_tiles, (int)tiles,
-                                          (res_rows + BM - 1) / BM);
+    Epilogue ep{};
+    ep.bias = g.bias; ep.ln_stats = g.ln_stats; ep.ln_colsum = g.ln_colsum; ep.stats_out = g.stats_out;
+    ep.M = g.M; ep.has_residual = g.residual != nullptr ? 1 : 0; ep.act = g.act;
+    ep.res_tiles = (res_rows + BM - 1) / BM;
+    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, ep, ad, g.K, num_n_tiles, (int)tiles);
     return check_launch();
 }
 
@@ -314,6 +355,7 @@ bool linear_tc_supported(int M, int N, int K) { return M > 0 && K % BK == 0 && K
 
 int linear_tc(const LinearTcArgs& g, const void* x2, int ldx2, int k_split, int num_sms, cudaStream_t stream) {
     if (!linear_tc_supported(g.M, g.N, g.K)) return SODT_ERR_UNSUPPORTED;
+    if (g.ln_stats && (!g.ln_colsum || x2 != nullptr)) return SODT_ERR_INVALID_ARG;
     if (g.residual && g.res_rows > 0 && g.res_rows != g.M && (g.res_rows % BM || g.M % g.res_rows)) return SODT_ERR_INVALID_ARG;
     if (g.ldx % 8 || g.ldo % 8 || (g.residual && g.ldr % 8) || g.ldx < (x2 ? k_split : g.K) || g.ldo < g.N) return SODT_ERR_INVALID_ARG;
     Addressing ad{};

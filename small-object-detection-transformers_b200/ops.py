@@ -296,8 +296,74 @@ def _torch_act(y, act):
     return y
 
 
-def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None):
-    """act(cat(x, x2) @ weight.T + bias) (+ residual) over the last dim.  bf16 shapes the tcgen05 kernel supports run there
+USE_LN_FOLD = True      # LayerNorm -> Linear pairs of the Swin blocks as one GEMM (statistics from the producing GEMM's epilogue)
+
+_fold_cache = {}
+
+
+def fold_layernorm(weight, bias, ln_weight, ln_bias):
+    """(W', colsum, b') for ``Linear(LayerNorm(x))`` as a GEMM on the raw rows (see sodt_linear_ln_fwd):
+    W' = W diag(ln_weight) in bf16, colsum = row sums of the bf16 W' in fp32, b' = bias + W ln_bias in fp32.
+    Cached per parameter objects / versions / storage."""
+    srcs = (weight, bias, ln_weight, ln_bias)
+    key = tuple((id(t), t._version, t.data_ptr()) if t is not None else None for t in srcs)
+    hit = _fold_cache.get(id(weight))
+    if hit is not None and hit[0] == key and all(r() is t for r, t in zip(hit[1], srcs) if t is not None):
+        return hit[2]
+    with torch.no_grad():
+        w32 = weight.detach().float()
+        wf = (w32 * ln_weight.detach().float()[None, :]).to(torch.bfloat16).contiguous()
+        colsum = wf.float().sum(dim=1).contiguous()
+        b2 = w32 @ ln_bias.detach().float()
+        if bias is not None:
+            b2 = b2 + bias.detach().float()
+        val = (wf, colsum, b2.contiguous())
+    if len(_fold_cache) > 1024:
+        _fold_cache.clear()
+    _fold_cache[id(weight)] = (key, tuple(weakref.ref(t) if t is not None else None for t in srcs), val)
+    return val
+
+
+def row_stats(x, eps=1e-5):
+    """[M, 2] fp32 (mean, rstd) of every row of bf16 ``x`` [..., C] (input of a LayerNorm folded into a GEMM)."""
+    _require_cuda(x)
+    if x.dtype != torch.bfloat16:
+        raise TypeError("row_stats: bf16 only")
+    xa, ld = _rows(x)
+    C = x.shape[-1]
+    M = x.numel() // C
+    st = torch.empty((M, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device), _Timed(f"row_stats[rows={M},C={C}]"):
+        rc = _capi.lib().sodt_row_stats(xa.data_ptr(), ld, st.data_ptr(), M, C, float(eps), 1, _stream())
+    _capi.check(rc, "sodt_row_stats")
+    return st
+
+
+def finalize_stats(partials, C, eps=1e-5):
+    """[boxes, M, 2] partial (sum, sum of squares) from ``linear(..., want_stats=True)`` -> [M, 2] (mean, rstd)."""
+    _require_cuda(partials)
+    if partials.dtype != torch.float32 or partials.dim() != 3 or partials.shape[2] != 2 or not partials.is_contiguous():
+        raise ValueError("partials must be contiguous fp32 [boxes, M, 2]")
+    boxes, M, _ = partials.shape
+    st = torch.empty((M, 2), dtype=torch.float32, device=partials.device)
+    with torch.cuda.device(partials.device), _Timed(f"stats_finalize[rows={M},boxes={boxes}]"):
+        rc = _capi.lib().sodt_stats_finalize(partials.data_ptr(), boxes, st.data_ptr(), M, C, float(eps), _stream())
+    _capi.check(rc, "sodt_stats_finalize")
+    return st
+
+
+def linear_ln_supported(x, n_out):
+    """True if ``linear(x, ..., ln=...)`` / ``want_stats`` can run (bf16 CUDA rows the tcgen05 GEMM covers)."""
+    K = x.shape[-1]
+    return bool(USE_TC_LINEAR and USE_LN_FOLD and x.is_cuda and x.dtype == torch.bfloat16
+                and _capi.lib().sodt_linear_supported(x.numel() // K, n_out, K, 1))
+
+
+def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=None, want_stats=False):
+    """act(cat(x, x2) @ weight.T + bias) (+ residual) over the last dim.
+    ``ln=(mean_rstd, colsum)``: ``weight`` / ``bias`` come from fold_layernorm and the LayerNorm of ``x`` is applied in
+    the epilogue from the row statistics ``mean_rstd`` [M, 2] (row_stats / finalize_stats).  ``want_stats``: also return
+    the [N/64, M, 2] partial (sum, sum of squares) of the result rows -> (out, partials).  Both need a shape for which linear_ln_supported() holds.  bf16 shapes the tcgen05 kernel supports run there
     with the activation / residual fused into the epilogue; ``x``, ``x2``, ``residual`` and ``out`` may be column slices of
     wider tensors (row-strided).  fp32 and other shapes use cuBLAS (torch) plus elementwise ops."""
     _require_cuda(x, weight, bias, residual, x2, out)
@@ -333,12 +399,29 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None):
             if o2 is not out or out.dtype != torch.bfloat16 or out.numel() != M * N:
                 raise ValueError("out must be a bf16 row-strided view with M*N elements")
         b32 = _as_f32(bias)
+        if ln is not None or want_stats:
+            if x2 is not None or res_rows:
+                raise ValueError("ln / want_stats cannot be combined with x2 or a broadcast residual")
+            stats_in, colsum = ln if ln is not None else (None, None)
+            if stats_in is not None and (stats_in.dtype != torch.float32 or not stats_in.is_contiguous()
+                                         or tuple(stats_in.shape) != (M, 2)):
+                raise ValueError("ln mean_rstd must be contiguous fp32 [M, 2]")
+            stats_out = torch.empty((N // 64, M, 2), dtype=torch.float32, device=x.device) if want_stats else None
+            with torch.cuda.device(x.device), _Timed(f"linear[M={M},N={N},K={K},act={act},res={residual is not None},"
+                                                     f"ln={ln is not None},stats={want_stats}]"):
+                st = _capi.lib().sodt_linear_ln_fwd(xa.data_ptr(), ldx, _ptr(stats_in), _ptr(colsum), w.data_ptr(), _ptr(b32),
+                                                    _ptr(res), ldr, out.data_ptr(), ldo, _ptr(stats_out), M, N, K,
+                                                    _LIN_ACT[act], 1, _stream())
+            _capi.check(st, "sodt_linear_ln_fwd")
+            return (out, stats_out) if want_stats else out
         with torch.cuda.device(x.device), _Timed(f"linear[M={M},N={N},K={K},act={act},res={residual is not None}]"):
             st = _capi.lib().sodt_linear_strided_fwd(xa.data_ptr(), ldx, _ptr(xb), ldx2, K1 if x2 is not None else 0, w.data_ptr(),
                                                      _ptr(b32), _ptr(res), ldr, res_rows, out.data_ptr(), ldo, M, N, K,
                                                      _LIN_ACT[act], 1, _stream())
         _capi.check(st, "sodt_linear_strided_fwd")
         return out
+    if ln is not None or want_stats:
+        raise _capi.SodtError("linear(ln=..., want_stats=...) needs a shape covered by the tcgen05 GEMM (linear_ln_supported)")
     xin = torch.cat((x, x2), dim=-1) if x2 is not None else x
     y = _torch_act(torch.nn.functional.linear(xin, weight, bias), act)
     if residual is not None:

@@ -178,6 +178,36 @@ def test_linear_tc_strided_operands_and_split_k_sources():
     assert (obuf[:, :N] == 7).all() and (obuf[:, 2 * N:] == 7).all()      # neighbours of the slice untouched
 
 
+@pytest.mark.parametrize("M,K,N,act", [(1000, 192, 576, None), (515, 384, 1536, "gelu"), (300, 768, 768, None), (4096, 192, 192, None)])
+def test_linear_tc_layernorm_fold_vs_torch(M, K, N, act):
+    """LayerNorm folded into the GEMM: statistics from row_stats and from the producing GEMM's epilogue (want_stats)."""
+    o = ops()
+    # producer GEMM writes x (with a residual, like proj / fc2) and its row statistics
+    a = fx.det_input(f"lnf_a:{M}:{K}", (M, K)).to("cuda", torch.bfloat16)
+    wp = (fx.det_input(f"lnf_wp:{K}", (K, K)) / K ** 0.5).to("cuda", torch.bfloat16)
+    r = (3.0 * fx.det_input(f"lnf_r:{M}:{K}", (M, K)) + 1.5).to("cuda", torch.bfloat16)         # non-zero mean rows
+    x, st = o.linear(a, wp, None, residual=r, want_stats=True)
+    assert st.shape == (K // 64, M, 2)
+    xd = x.double().cpu()
+    # emitted from the fp32 values before the bf16 rounding of x
+    assert rel_err(st.sum(0)[:, 0], xd.sum(1)) < 2e-3 and rel_err(st.sum(0)[:, 1], (xd * xd).sum(1)) < 2e-3
+    mean, var = xd.mean(1), xd.var(1, unbiased=False)
+    mr0, mr1 = o.finalize_stats(st, K, 1e-5), o.row_stats(x, 1e-5)
+    assert rel_err(mr1[:, 0], mean) < 1e-5 and rel_err(mr1[:, 1], (var + 1e-5).rsqrt()) < 1e-4
+    assert rel_err(mr0[:, 0], mean) < 2e-3 and rel_err(mr0[:, 1], (var + 1e-5).rsqrt()) < 2e-3
+    # consumer: Linear(LayerNorm(x))
+    w = (fx.det_input(f"lnf_w:{N}:{K}", (N, K)) / K ** 0.5).to("cuda", torch.bfloat16)
+    b = (0.2 * fx.det_input(f"lnf_b:{N}", (N,))).to("cuda", torch.bfloat16)
+    g = (1.0 + 0.2 * fx.det_input(f"lnf_g:{K}", (K,))).to("cuda", torch.bfloat16)
+    be = (0.1 * fx.det_input(f"lnf_be:{K}", (K,))).to("cuda", torch.bfloat16)
+    wf, colsum, bf = o.fold_layernorm(w, b, g, be)
+    ref = torch.nn.functional.layer_norm(xd, (K,), g.double().cpu(), be.double().cpu(), 1e-5) @ w.double().cpu().t() + b.double().cpu()
+    ref = torch.nn.functional.gelu(ref) if act == "gelu" else ref
+    for mr in (mr0, mr1):
+        out = o.linear(x, wf, bf, act=act, ln=(mr, colsum))
+        assert out.shape == (M, N) and rel_err(out, ref) < 6e-3
+
+
 def test_linear_tc_batch_broadcast_residual():
     """A residual with fewer rows than the output repeats over the batch (pos_embed in the patch-embedding GEMM)."""
     B, L, K, N = 3, 256, 192, 192
