@@ -124,6 +124,13 @@ int sodt_cattn_block_fwd(const void* r, const void* g, const void* b, const void
 int sodt_frontend_fwd(const void* x, long long sb, long long sc, long long sy, long long sx,
                       const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b, void* out,
                       int B, int H, int W, int E, int pad_r, float eps, int dtype, void* stream);
+/* The same from the uint8 images of the evaluation loop (basics/test.py:124-130: img / 255; model.py:192: IR channel 0):
+ * streams R, G, B = channels 0-2 of `rgb` (strides rb, rc, ry, rx), stream IR = the plane at `ir` (strides ib, iy, ix).
+ * Pixels are u8 * (1/255) rounded to `dtype` (the type of `out`), i.e. what the separate conversion passes produced. */
+int sodt_frontend_u8_fwd(const void* rgb, long long rb, long long rc, long long ry, long long rx,
+                         const void* ir, long long ib, long long iy, long long ix,
+                         const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b, void* out,
+                         int B, int H, int W, int E, int pad_r, float eps, int dtype, void* stream);
 
 /*
  * YOLOv5 Detect decode for one level.  Replaces model.py:55-64 (view/permute/contiguous,

@@ -442,9 +442,17 @@ class ImageEncoderViT(nn.Module):
             self._fe_key = key
         return self._fe_cache
 
-    def _front_end(self, x):
+    def _front_end(self, x, ir_u8=None):
         cb = self.chan_block
         e = self.channel_embed_r.proj
+        if ir_u8 is not None:
+            # uint8 images straight into the fused kernel (x = rgb uint8 [B,3,H,W]): no conversion / scaling / concat passes
+            if not (x.is_cuda and cb.window_size == 1 and e.out_channels == 48 and e.kernel_size == (4, 4) and e.stride == (4, 4)
+                    and self.channel_embed_g.proj.padding == (0, 0) and e.padding in ((1, 1), (0, 0))
+                    and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0):
+                raise ValueError("uint8 input needs the fused front end (CUDA, 4x4/4 channel embeddings, window-1 block)")
+            cw, cbias, lw, lb = self._front_end_params()
+            return ops.frontend_u8(x, ir_u8, cw, cbias, lw, lb, e.weight.dtype, pad_r=e.padding[0], eps=cb.norm1.eps)
         fused = (x.is_cuda and cb.window_size == 1 and e.out_channels == 48 and e.kernel_size == (4, 4) and e.stride == (4, 4)
                  and self.channel_embed_g.proj.padding == (0, 0) and e.padding in ((1, 1), (0, 0))
                  and x.shape[2] % 4 == 0 and x.shape[3] % 4 == 0)
@@ -458,8 +466,9 @@ class ImageEncoderViT(nn.Module):
         i = self.channel_embed_i(i)
         return self.chan_block.forward_fused(r, g, b, i)
 
-    def forward(self, x: torch.Tensor):
-        x = self._front_end(x)                                   # [B,h,w,192], the reference's concat
+    def forward(self, x: torch.Tensor, ir_u8: Optional[torch.Tensor] = None):
+        """x [B,4,H,W] in the model dtype, or (extension) x = uint8 RGB [B,3,H,W] with ``ir_u8`` uint8 [B,>=1,H,W]."""
+        x = self._front_end(x, ir_u8)                            # [B,h,w,192], the reference's concat
         pos = self.pos_embed                                     # silently skipped on a size mismatch, like the reference
         if pos is not None and x.shape[1] != pos.shape[1]:
             pos = None

@@ -220,14 +220,22 @@ class Model(nn.Module):
             raise NotImplementedError("test-time augmentation is out of scope")
         if ir is None:
             ir = x
-        head_out, feats = self.forward_once(self._stem(x, ir, input_mode), "yolo", profile)
+        if x.dtype == torch.uint8:
+            # extension: the evaluation loop's uint8 images (basics/test.py:124-130); /255 happens inside the front-end kernel
+            if input_mode != "RGB+IR" or ir.dtype != torch.uint8:
+                raise NotImplementedError("uint8 input is supported for input_mode='RGB+IR' with uint8 rgb and ir")
+            stem = (x, ir)
+        else:
+            stem = self._stem(x, ir, input_mode)
+        head_out, feats = self.forward_once(stem, "yolo", profile)
         self.training |= self.export
         if self.training:
             return head_out, feats
         return head_out[0], head_out[1], feats
 
     def forward_once(self, x, string="yolo", profile=False):
-        y = list(self.image_encoder(x))
+        y = list(self.image_encoder(x[0], ir_u8=x[1]) if isinstance(x, tuple) else self.image_encoder(x))
+        x = y[-1]
         mods = list(self.detect)
         i = 0
         while i < len(mods):

@@ -31,9 +31,18 @@ __device__ __forceinline__ void store6(T* dst, const float (&y)[CPL]) {
     }
 }
 
-template <typename T>
+// pixel -> fp32.  uint8 images are scaled like the reference's evaluation loop (img / 255, basics/test.py:124-130): the
+// product u * (1/255) is rounded to the activation type first, exactly what the separate conversion pass produced.
+template <typename T, typename TI> __device__ __forceinline__ float load_px(const TI* p) { return to_f32<TI>(*p); }
+template <> __device__ __forceinline__ float load_px<float, uint8_t>(const uint8_t* p) { return __fmul_rn((float)*p, 1.f / 255.f); }
+template <> __device__ __forceinline__ float load_px<__nv_bfloat16, uint8_t>(const uint8_t* p) {
+    return __bfloat162float(__float2bfloat16_rn(__fmul_rn((float)*p, 1.f / 255.f)));
+}
+
+template <typename T, typename TI>
 __global__ void __launch_bounds__(128)
-frontend_kernel(const T* __restrict__ x, long long sb, long long sc, long long sy, long long sx,
+frontend_kernel(const TI* __restrict__ x, long long sb, long long sc, long long sy, long long sx,
+                const TI* __restrict__ x_ir, long long ib, long long iy, long long ix,   // optional separate source of stream 3
                 const float* __restrict__ conv_w /*[4][E][16]*/, const float* __restrict__ conv_b /*[4][E]*/,
                 const float* __restrict__ ln_w /*[4][E]*/, const float* __restrict__ ln_b, T* __restrict__ out,
                 int H, int W, int h, int w, long long ntok, int pad0, float eps) {
@@ -67,14 +76,16 @@ frontend_kernel(const T* __restrict__ x, long long sb, long long sc, long long s
             const int ty = (int)(rest % h);
             const long long b = rest / h;
             const int off = s == 0 ? pad0 : 0;                        // only the R stream is padded
-            const T* img = x + b * sb + s * sc;
+            const bool sep = s == 3 && x_ir != nullptr;
+            const TI* img = sep ? x_ir + b * ib : x + b * sb + s * sc;
+            const long long psy = sep ? iy : sy, psx = sep ? ix : sx;
 #pragma unroll
             for (int ky = 0; ky < KS; ++ky) {
                 const int yy = ty * KS + ky - off;
 #pragma unroll
                 for (int kx = 0; kx < KS; ++kx) {
                     const int xx = tx * KS + kx - off;
-                    if (yy >= 0 && yy < H && xx >= 0 && xx < W) px[ky * KS + kx] = to_f32<T>(img[yy * sy + xx * sx]);
+                    if (yy >= 0 && yy < H && xx >= 0 && xx < W) px[ky * KS + kx] = load_px<T, TI>(img + yy * psy + xx * psx);
                 }
             }
         }
@@ -149,6 +160,25 @@ frontend_kernel(const T* __restrict__ x, long long sb, long long sc, long long s
 }  // namespace
 }  // namespace sodt
 
+namespace sodt {
+namespace {
+template <typename T, typename TI>
+int frontend_launch(const void* x, long long sb, long long sc, long long sy, long long sx, const void* x_ir, long long ib, long long iy,
+                    long long ix, const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b, void* out,
+                    int B, int H, int W, int pad_r, float eps, cudaStream_t s) {
+    // conv output size with padding p: floor((H + 2p - 4) / 4) + 1; the reference needs all four streams to agree
+    const int h = (H - 4) / 4 + 1, w = (W - 4) / 4 + 1;
+    if ((H + 2 * pad_r - 4) / 4 + 1 != h || (W + 2 * pad_r - 4) / 4 + 1 != w) return SODT_ERR_UNSUPPORTED;
+    const long long ntok = (long long)B * h * w;
+    long long blocks = (ntok + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
+    if (blocks > 148LL * 12) blocks = 148LL * 12;
+    frontend_kernel<T, TI><<<(unsigned)blocks, 128, 0, s>>>(static_cast<const TI*>(x), sb, sc, sy, sx, static_cast<const TI*>(x_ir), ib, iy, ix,
+                                                            conv_w, conv_b, ln_w, ln_b, static_cast<T*>(out), H, W, h, w, ntok, pad_r, eps);
+    return check_launch();
+}
+}  // namespace
+}  // namespace sodt
+
 extern "C" int sodt_frontend_fwd(const void* x, long long sb, long long sc, long long sy, long long sx,
                                  const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b, void* out,
                                  int B, int H, int W, int E, int pad_r, float eps, int dtype, void* stream) {
@@ -157,18 +187,23 @@ extern "C" int sodt_frontend_fwd(const void* x, long long sb, long long sc, long
     if (dtype != SODT_F32 && dtype != SODT_BF16) return SODT_ERR_INVALID_ARG;
     if (E != 48 || (pad_r != 0 && pad_r != 1)) return SODT_ERR_UNSUPPORTED;
     if (!aligned16(out)) return SODT_ERR_ALIGNMENT;
-    // conv output size with padding p: floor((H + 2p - 4) / 4) + 1; the reference needs all four streams to agree
-    const int h = (H - 4) / 4 + 1, w = (W - 4) / 4 + 1;
-    if ((H + 2 * pad_r - 4) / 4 + 1 != h || (W + 2 * pad_r - 4) / 4 + 1 != w) return SODT_ERR_UNSUPPORTED;
-    const long long ntok = (long long)B * h * w;
-    long long blocks = (ntok + TOK_PER_BLOCK - 1) / TOK_PER_BLOCK;
-    if (blocks > 148LL * 12) blocks = 148LL * 12;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == SODT_F32)
-        frontend_kernel<float><<<(unsigned)blocks, 128, 0, s>>>(static_cast<const float*>(x), sb, sc, sy, sx, conv_w, conv_b, ln_w, ln_b,
-                                                                      static_cast<float*>(out), H, W, h, w, ntok, pad_r, eps);
-    else
-        frontend_kernel<__nv_bfloat16><<<(unsigned)blocks, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(x), sb, sc, sy, sx, conv_w, conv_b,
-                                                                              ln_w, ln_b, static_cast<__nv_bfloat16*>(out), H, W, h, w, ntok, pad_r, eps);
-    return check_launch();
+        return frontend_launch<float, float>(x, sb, sc, sy, sx, nullptr, 0, 0, 0, conv_w, conv_b, ln_w, ln_b, out, B, H, W, pad_r, eps, s);
+    return frontend_launch<__nv_bfloat16, __nv_bfloat16>(x, sb, sc, sy, sx, nullptr, 0, 0, 0, conv_w, conv_b, ln_w, ln_b, out, B, H, W, pad_r, eps, s);
+}
+
+extern "C" int sodt_frontend_u8_fwd(const void* rgb, long long rb, long long rc, long long ry, long long rx,
+                                    const void* ir, long long ib, long long iy, long long ix,
+                                    const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b, void* out,
+                                    int B, int H, int W, int E, int pad_r, float eps, int dtype, void* stream) {
+    using namespace sodt;
+    if (!rgb || !ir || !conv_w || !conv_b || !ln_w || !ln_b || !out || B <= 0 || H < 4 || W < 4) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_F32 && dtype != SODT_BF16) return SODT_ERR_INVALID_ARG;
+    if (E != 48 || (pad_r != 0 && pad_r != 1)) return SODT_ERR_UNSUPPORTED;
+    if (!aligned16(out)) return SODT_ERR_ALIGNMENT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == SODT_F32)
+        return frontend_launch<float, uint8_t>(rgb, rb, rc, ry, rx, ir, ib, iy, ix, conv_w, conv_b, ln_w, ln_b, out, B, H, W, pad_r, eps, s);
+    return frontend_launch<__nv_bfloat16, uint8_t>(rgb, rb, rc, ry, rx, ir, ib, iy, ix, conv_w, conv_b, ln_w, ln_b, out, B, H, W, pad_r, eps, s);
 }

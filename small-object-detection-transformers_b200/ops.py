@@ -236,6 +236,27 @@ def frontend(x, conv_w, conv_b, ln_w, ln_b, pad_r=1, eps=1e-5):
 
 
 # --------------------------------------------------------------------------------- Detect decode
+def frontend_u8(rgb_u8, ir_u8, conv_w, conv_b, ln_w, ln_b, dtype, pad_r=1, eps=1e-5):
+    """frontend() straight from the uint8 images: rgb_u8 [B,3,H,W], ir_u8 [B,>=1,H,W] (channel 0 is read); pixels are scaled
+    by 1/255 and rounded to ``dtype`` inside the kernel.  See sodt_frontend_u8_fwd."""
+    _require_cuda(rgb_u8, ir_u8, conv_w, conv_b, ln_w, ln_b)
+    if rgb_u8.dtype != torch.uint8 or ir_u8.dtype != torch.uint8 or rgb_u8.dim() != 4 or rgb_u8.shape[1] != 3 or dtype not in _DT:
+        raise ValueError("rgb_u8 must be uint8 [B,3,H,W], ir_u8 uint8 [B,C,H,W]")
+    B, _, H, W = rgb_u8.shape
+    if ir_u8.shape[0] != B or tuple(ir_u8.shape[2:]) != (H, W):
+        raise ValueError("ir_u8 must match rgb_u8 in batch and image size")
+    E = conv_w.shape[1]
+    out = torch.empty((B, (H - 4) // 4 + 1, (W - 4) // 4 + 1, 4 * E), dtype=dtype, device=rgb_u8.device)
+    rb, rc, ry, rx = rgb_u8.stride()
+    ib, _, iy, ix = ir_u8.stride()
+    with torch.cuda.device(rgb_u8.device), _Timed(f"frontend_u8[B={B},H={H},W={W}]"):
+        st = _capi.lib().sodt_frontend_u8_fwd(rgb_u8.data_ptr(), rb, rc, ry, rx, ir_u8.data_ptr(), ib, iy, ix, conv_w.data_ptr(),
+                                              conv_b.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), out.data_ptr(), B, H, W, E,
+                                              pad_r, float(eps), _DT[dtype], _stream())
+    _capi.check(st, "sodt_frontend_u8_fwd")
+    return out
+
+
 def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=None, row_offset=0):
     """raw [B, na*no, ny, nx] (any strides) -> (z [B, na*ny*nx, no] fp32, x_perm [B,na,ny,nx,no] or None)."""
     _require_cuda(raw, anchors_px, z)

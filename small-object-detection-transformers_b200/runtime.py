@@ -88,6 +88,9 @@ class Detector:
     @torch.no_grad()
     def predict(self, rgb_u8, ir_u8):
         """Device uint8 [B,3,H,W] x2 -> decoded predictions [B, R, 5+nc] fp32 (the reference's ``out``)."""
+        if rgb_u8.dtype == torch.uint8 and ir_u8.dtype == torch.uint8:
+            pred, _, _ = self.model(rgb_u8, ir_u8, "RGB+IR")      # /255 and the IR channel-0 pick happen in the front-end kernel
+            return pred
         x = rgb_u8.to(self.dtype).div_(255.0)
         ir = ir_u8[:, 0:1].to(self.dtype).div_(255.0)     # the detector reads IR channel 0 only (model.py:192)
         pred, _, _ = self.model(x, ir, "RGB+IR")

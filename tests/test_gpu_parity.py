@@ -403,6 +403,23 @@ def test_frontend_vs_oracle(pad_r, dtype):
     assert rel_err(out, ref) < (1e-5 if dtype == torch.float32 else 1e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_frontend_u8_matches_converted_input(dtype):
+    """uint8 images straight into the front-end kernel == the separate /255 conversion + channel pick + concat."""
+    B, H, W, E = 2, 64, 96, 48
+    g = torch.Generator().manual_seed(11)
+    rgb = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).cuda()
+    ir = torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, generator=g).cuda()
+    cw = (0.3 * fx.det_input("fe8:cw", (4, E, 16))).cuda()
+    cb = (0.1 * fx.det_input("fe8:cb", (4, E))).cuda()
+    lw = (1.0 + 0.1 * fx.det_input("fe8:lw", (4, E))).cuda()
+    lb = (0.1 * fx.det_input("fe8:lb", (4, E))).cuda()
+    x = torch.cat((rgb.to(dtype).div_(255.0), ir[:, 0:1].to(dtype).div_(255.0)), 1)
+    want = ops().frontend(x, cw, cb, lw, lb, pad_r=1, eps=1e-5)
+    got = ops().frontend_u8(rgb, ir, cw, cb, lw, lb, dtype, pad_r=1, eps=1e-5)
+    assert got.dtype == dtype and torch.equal(got, want)
+
+
 # ---------------------------------------------------------------------------------------- Detect
 @pytest.mark.parametrize("memory_format", ["nchw", "channels_last"])
 def test_detect_module_vs_reference_golden(golden, memory_format):
