@@ -154,8 +154,7 @@ class Mlp(nn.Module):
         w1, b1, fold = self.fc1.weight, self.fc1.bias, None
         if ln is not None:
             norm, stats = ln
-            w1, colsum, b1 = ops.fold_layernorm(self.fc1.weight, self.fc1.bias, norm.weight, norm.bias)
-            fold = (stats, colsum)
+            fold = (stats, norm.weight, norm.bias)
         if self.linear:
             if exact_gelu and x.is_cuda:
                 return ops.linear(x, w1, b1, act="gelu", ln=fold)    # GELU fused into the GEMM epilogue (bf16)
@@ -278,8 +277,7 @@ class SwinTransformerBlock(nn.Module):
             # bf16, LayerNorms folded: qkv and fc1 read the raw residual stream and normalise in their epilogues from the row
             # statistics that the proj / fc2 GEMM (or the producer of x) emitted with its result
             mr = ops.finalize_stats(stats, C, self.norm1.eps) if stats is not None else ops.row_stats(x, self.norm1.eps)
-            wq, csq, bq = ops.fold_layernorm(attn.qkv.weight, attn.qkv.bias, self.norm1.weight, self.norm1.bias)
-            qkv = ops.linear(x, wq, bq, ln=(mr, csq))
+            qkv = ops.linear(x, attn.qkv.weight, attn.qkv.bias, ln=(mr, self.norm1.weight, self.norm1.bias))
             o = ops.window_attention(qkv.view(B, H, W, 3 * C), attn.relative_position_bias_table, attn.num_heads,
                                      self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
                                      mask_value=MASK_VALUE)

@@ -93,7 +93,16 @@ template <int BN> struct Cfg {
     static constexpr int STAGES = BN == 256 ? 3 : BN == 192 ? 4 : BN == 128 ? 5 : 6;
 };
 
-template <int BN>
+// Epilogue variants compiled as separate kernels: with every feature a run-time flag, the unrolled epilogue issued ~1500
+// instructions per 64-column box (predicated-off bias / LayerNorm / residual / statistics code still takes issue slots and
+// instruction-cache space; ncu: 57 % issue utilisation and 20 % instruction-fetch stalls on a bias-free GEMM).
+// bits: 1 bias, 2 LayerNorm fold, 4 residual, 8 row statistics out; act in bits 4-5; EPI_ANY keeps everything run-time.
+constexpr int EPI_BIAS = 1, EPI_LN = 2, EPI_RES = 4, EPI_STATS = 8, EPI_ACT_SHIFT = 4, EPI_ANY = 1 << 8;
+constexpr int epi_code(bool bias, bool ln, bool res, bool stats, int act) {
+    return (bias ? EPI_BIAS : 0) | (ln ? EPI_LN : 0) | (res ? EPI_RES : 0) | (stats ? EPI_STATS : 0) | (act << EPI_ACT_SHIFT);
+}
+
+template <int BN, int EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                  const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
@@ -189,8 +198,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         constexpr int NBOX = BN / 64;
         int it = 0;
         uint32_t res_phase = 0;
-        const float* __restrict__ bias = ep.bias;
-        const int has_residual = ep.has_residual, act = ep.act;
+        constexpr bool ANY = EPI == EPI_ANY;
+        const float* __restrict__ bias = (ANY || (EPI & EPI_BIAS)) ? ep.bias : nullptr;
+        const bool has_residual = ANY ? ep.has_residual != 0 : (EPI & EPI_RES) != 0;
+        const bool has_ln = ANY ? ep.ln_stats != nullptr : (EPI & EPI_LN) != 0;
+        const bool has_stats = ANY ? ep.stats_out != nullptr : (EPI & EPI_STATS) != 0;
+        const int act = ANY ? ep.act : (EPI >> EPI_ACT_SHIFT);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int a = it % NACC;
             const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
@@ -210,7 +223,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 // (mean, rstd) of this thread's A row for a folded LayerNorm; the load is issued ahead of the TMEM load
                 float2 mr = make_float2(0.f, 1.f);
-                if (ep.ln_stats != nullptr && grow < ep.M) mr = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + grow);
+                if (has_ln && grow < ep.M) mr = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + grow);
                 // accumulator columns in chunks of 16, the next chunk in flight while this one is processed (the kernel
                 // runs at the register cap of 576 threads: two 32-column loads spilled once the LayerNorm terms were added)
                 uint32_t ra[16], rb[16];
@@ -235,7 +248,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j + 4));
                         bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
                     }
-                    if (ep.ln_stats != nullptr) {                                 // rstd acc + (bias - mean rstd colsum[n]): two FMAs
+                    if (has_ln) {                                                 // rstd acc + (bias - mean rstd colsum[n]): two FMAs
                         const float4 c0 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0 + j));
                         const float4 c1 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0 + j + 4));
                         const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
@@ -263,7 +276,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                             v[2 * e] += __low2float(h); v[2 * e + 1] += __high2float(h);
                         }
                     }
-                    if (ep.stats_out != nullptr) {        // of the fp32 values: differs from the stored bf16 row by < 2^-9 / sqrt(N) rms
+                    if (has_stats) {                      // of the fp32 values: differs from the stored bf16 row by < 2^-9 / sqrt(N) rms
 #pragma unroll
                         for (int e = 0; e < 8; ++e) { so += v[e]; sso = fmaf(v[e], v[e], sso); }
                     }
@@ -271,7 +284,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                                  "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
                     if ((j & 15) == 8 && j + 8 < 64) tmem_wait_ld();              // the prefetched chunk has landed
                 }
-                if (ep.stats_out != nullptr && grow < ep.M)
+                if (has_stats && grow < ep.M)
                     reinterpret_cast<float2*>(ep.stats_out)[(size_t)(col0 >> 6) * ep.M + grow] = make_float2(so, sso);
                 fence_proxy_async();
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
@@ -320,7 +333,7 @@ bool make_map_2d(CUtensorMap* m, const void* base, long long rows, long long col
     return make_map(m, base, 2, dims, strides, box, is_output ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-template <int BN>
+template <int BN, int EPI>
 int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
     CUtensorMap mw, mo, mr;
     if (!make_map_2d(&mw, g.w, g.N, g.K, g.K, BN, false) || !make_map_2d(&mo, g.out, g.M, g.N, g.ldo, BM, true)) return SODT_ERR_CUDA;
@@ -330,7 +343,7 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     const long long tiles = (long long)num_n_tiles * num_m_tiles;
     if (tiles > 2147483647LL) return SODT_ERR_UNSUPPORTED;
     const size_t smem = (size_t)Cfg<BN>::STAGES * (A_BYTES + BN * BK * 2) + EPI_GROUPS * BOX_BYTES + 1024;
-    auto kern = linear_tc_kernel<BN>;
+    auto kern = linear_tc_kernel<BN, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = (int)(tiles < num_sms ? tiles : num_sms);
@@ -342,11 +355,31 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     return check_launch();
 }
 
+template <int EPI>
+int dispatch_bn(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
+    if (g.N % 256 == 0) return launch<256, EPI>(mx, mx2, ad, g, num_sms, stream);
+    if (g.N % 192 == 0) return launch<192, EPI>(mx, mx2, ad, g, num_sms, stream);
+    if (g.N % 128 == 0) return launch<128, EPI>(mx, mx2, ad, g, num_sms, stream);
+    return launch<64, EPI>(mx, mx2, ad, g, num_sms, stream);
+}
+
 int dispatch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
-    if (g.N % 256 == 0) return launch<256>(mx, mx2, ad, g, num_sms, stream);
-    if (g.N % 192 == 0) return launch<192>(mx, mx2, ad, g, num_sms, stream);
-    if (g.N % 128 == 0) return launch<128>(mx, mx2, ad, g, num_sms, stream);
-    return launch<64>(mx, mx2, ad, g, num_sms, stream);
+    // the epilogue variants the detector uses are specialised; any other combination runs the all-run-time kernel
+    const int code = epi_code(g.bias != nullptr, g.ln_stats != nullptr, g.residual != nullptr, g.stats_out != nullptr, g.act);
+    switch (code) {
+#define SODT_EPI_CASE(bias, ln, res, stats, act) \
+        case epi_code(bias, ln, res, stats, act): return dispatch_bn<epi_code(bias, ln, res, stats, act)>(mx, mx2, ad, g, num_sms, stream);
+        SODT_EPI_CASE(false, false, false, false, 0)     // necks, PatchMerging reduction
+        SODT_EPI_CASE(true, false, false, false, 0)      // Detect's 1x1 conv, unfolded qkv
+        SODT_EPI_CASE(true, true, false, false, 0)       // norm1 + qkv, norm2 + fc1 of the conv-MLP
+        SODT_EPI_CASE(true, true, false, false, 1)       // norm2 + fc1 + GELU
+        SODT_EPI_CASE(true, false, true, true, 0)        // proj / fc2 + residual, emitting row statistics
+        SODT_EPI_CASE(true, false, true, false, 0)       // proj / fc2 + residual; patch embedding + pos_embed
+        SODT_EPI_CASE(true, false, false, false, 1)      // conv-MLP taps + GELU, unfolded fc1
+        SODT_EPI_CASE(true, false, false, false, 2)      // head Conv: conv + folded BN + SiLU
+#undef SODT_EPI_CASE
+        default: return dispatch_bn<EPI_ANY>(mx, mx2, ad, g, num_sms, stream);
+    }
 }
 
 }  // namespace

@@ -382,11 +382,12 @@ def linear_ln_supported(x, n_out):
 
 def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=None, want_stats=False):
     """act(cat(x, x2) @ weight.T + bias) (+ residual) over the last dim.
-    ``ln=(mean_rstd, colsum)``: ``weight`` / ``bias`` come from fold_layernorm and the LayerNorm of ``x`` is applied in
-    the epilogue from the row statistics ``mean_rstd`` [M, 2] (row_stats / finalize_stats).  ``want_stats``: also return
-    the [N/64, M, 2] partial (sum, sum of squares) of the result rows -> (out, partials).  Both need a shape for which linear_ln_supported() holds.  bf16 shapes the tcgen05 kernel supports run there
-    with the activation / residual fused into the epilogue; ``x``, ``x2``, ``residual`` and ``out`` may be column slices of
-    wider tensors (row-strided).  fp32 and other shapes use cuBLAS (torch) plus elementwise ops."""
+    ``ln=(mean_rstd, ln_weight, ln_bias)``: computes ``Linear(LayerNorm(x))`` from the raw rows ``x`` and their statistics
+    ``mean_rstd`` [M, 2] (row_stats / finalize_stats); the LayerNorm is folded into the weights (cached) and the epilogue.
+    ``want_stats``: also return the [N/64, M, 2] partial (sum, sum of squares) of the result rows -> (out, partials).
+    Both need a shape for which linear_ln_supported() holds.  bf16 shapes the tcgen05 kernel supports run there with the
+    activation / residual fused into the epilogue; ``x``, ``x2``, ``residual`` and ``out`` may be column slices of wider
+    tensors (row-strided).  fp32 and other shapes use cuBLAS (torch) plus elementwise ops."""
     _require_cuda(x, weight, bias, residual, x2, out)
     if act not in _LIN_ACT:
         raise ValueError(f"unsupported activation {act!r}")
@@ -400,7 +401,6 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
             and _capi.lib().sodt_linear_supported(M, N, K, 1)):
         xa, ldx = _rows(x)
         xb, ldx2 = _rows(x2) if x2 is not None else (None, 0)
-        w = weight.detach().contiguous()
         res, ldr, res_rows = None, 0, 0
         if residual is not None:
             if residual.dtype != torch.bfloat16 or residual.shape[-1] != N:
@@ -419,28 +419,30 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
             o2, ldo = _rows(out)
             if o2 is not out or out.dtype != torch.bfloat16 or out.numel() != M * N:
                 raise ValueError("out must be a bf16 row-strided view with M*N elements")
-        b32 = _as_f32(bias)
+        if (ln is not None or want_stats) and (x2 is not None or res_rows):
+            raise ValueError("ln / want_stats cannot be combined with x2 or a broadcast residual")
+        mr, ln_w, ln_b = ln if ln is not None else (None, None, None)
+        if mr is not None and (mr.dtype != torch.float32 or not mr.is_contiguous() or tuple(mr.shape) != (M, 2)):
+            raise ValueError("ln mean_rstd must be contiguous fp32 [M, 2]")
+        stats_out = torch.empty((N // 64, M, 2), dtype=torch.float32, device=x.device) if want_stats else None
+        label = f"linear[M={M},N={N},K={K},act={act},res={residual is not None},ln={ln is not None},stats={want_stats}]"
         if ln is not None or want_stats:
-            if x2 is not None or res_rows:
-                raise ValueError("ln / want_stats cannot be combined with x2 or a broadcast residual")
-            stats_in, colsum = ln if ln is not None else (None, None)
-            if stats_in is not None and (stats_in.dtype != torch.float32 or not stats_in.is_contiguous()
-                                         or tuple(stats_in.shape) != (M, 2)):
-                raise ValueError("ln mean_rstd must be contiguous fp32 [M, 2]")
-            stats_out = torch.empty((N // 64, M, 2), dtype=torch.float32, device=x.device) if want_stats else None
-            with torch.cuda.device(x.device), _Timed(f"linear[M={M},N={N},K={K},act={act},res={residual is not None},"
-                                                     f"ln={ln is not None},stats={want_stats}]"):
-                st = _capi.lib().sodt_linear_ln_fwd(xa.data_ptr(), ldx, _ptr(stats_in), _ptr(colsum), w.data_ptr(), _ptr(b32),
+            w, colsum, b32 = (fold_layernorm(weight, bias, ln_w, ln_b) if ln is not None
+                              else (weight.detach().contiguous(), None, _as_f32(bias)))
+            with torch.cuda.device(x.device), _Timed(label):
+                st = _capi.lib().sodt_linear_ln_fwd(xa.data_ptr(), ldx, _ptr(mr), _ptr(colsum), w.data_ptr(), _ptr(b32),
                                                     _ptr(res), ldr, out.data_ptr(), ldo, _ptr(stats_out), M, N, K,
                                                     _LIN_ACT[act], 1, _stream())
             _capi.check(st, "sodt_linear_ln_fwd")
-            return (out, stats_out) if want_stats else out
-        with torch.cuda.device(x.device), _Timed(f"linear[M={M},N={N},K={K},act={act},res={residual is not None}]"):
-            st = _capi.lib().sodt_linear_strided_fwd(xa.data_ptr(), ldx, _ptr(xb), ldx2, K1 if x2 is not None else 0, w.data_ptr(),
-                                                     _ptr(b32), _ptr(res), ldr, res_rows, out.data_ptr(), ldo, M, N, K,
-                                                     _LIN_ACT[act], 1, _stream())
-        _capi.check(st, "sodt_linear_strided_fwd")
-        return out
+        else:
+            w = weight.detach().contiguous()
+            b32 = _as_f32(bias)
+            with torch.cuda.device(x.device), _Timed(label):
+                st = _capi.lib().sodt_linear_strided_fwd(xa.data_ptr(), ldx, _ptr(xb), ldx2, K1 if x2 is not None else 0, w.data_ptr(),
+                                                         _ptr(b32), _ptr(res), ldr, res_rows, out.data_ptr(), ldo, M, N, K,
+                                                         _LIN_ACT[act], 1, _stream())
+            _capi.check(st, "sodt_linear_strided_fwd")
+        return (out, stats_out) if want_stats else out
     if ln is not None or want_stats:
         raise _capi.SodtError("linear(ln=..., want_stats=...) needs a shape covered by the tcgen05 GEMM (linear_ln_supported)")
     xin = torch.cat((x, x2), dim=-1) if x2 is not None else x

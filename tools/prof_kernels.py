@@ -35,13 +35,12 @@ xt = torch.randn(M, 192, device=dev, generator=g).to(torch.bfloat16)
 w = lambda n, k: (torch.randn(n, k, device=dev, generator=g) / k ** 0.5).to(torch.bfloat16)
 bias = lambda n: 0.1 * torch.randn(n, device=dev, generator=g)
 gam, bet = 1.0 + 0.1 * torch.randn(192, device=dev, generator=g), 0.1 * torch.randn(192, device=dev, generator=g)
-wq, csq, bq = ops.fold_layernorm(w(576, 192), bias(576), gam, bet)
-w1, cs1, b1 = ops.fold_layernorm(w(768, 192), bias(768), gam, bet)
+wq, bq, w1, b1 = w(576, 192), bias(576), w(768, 192), bias(768)
 for _ in range(reps):
     x1, part = ops.linear(xt, w(192, 192), bias(192), residual=xt, want_stats=True)      # proj + residual, emits row statistics
     mr = ops.finalize_stats(part, 192, 1e-5)
-    ops.linear(x1, wq, bq, ln=(mr, csq))                                                 # norm1 + qkv
-    hid = ops.linear(x1, w1, b1, act="gelu", ln=(mr, cs1))                               # norm2 + fc1 + GELU
+    ops.linear(x1, wq, bq, ln=(mr, gam, bet))                                                 # norm1 + qkv
+    hid = ops.linear(x1, w1, b1, act="gelu", ln=(mr, gam, bet))                               # norm2 + fc1 + GELU
     ops.linear(hid, w(192, 768), bias(192), residual=xt, want_stats=True)                # fc2 + residual
     ops.conv2d_nhwc(xt.view(B, 256, 256, 192), w(192, 4 * 192), bias(192), (2, 2), (0, 0), "gelu")
     ops.patch_merge_linear(xt.view(B, 256, 256, 192), w(384, 768))
