@@ -90,7 +90,6 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 
 template <int BN> struct Cfg {
     static constexpr int NACC = BN <= 128 ? 4 : 2;                                    // TMEM accumulator buffers (NACC * BN <= 512)
-    static constexpr int STAGES = BN == 256 ? 3 : BN == 192 ? 4 : BN == 128 ? 5 : 6;
 };
 
 // Epilogue variants compiled as separate kernels: with every feature a run-time flag, the unrolled epilogue issued ~1500
@@ -102,26 +101,45 @@ constexpr int epi_code(bool bias, bool ln, bool res, bool stats, int act) {
     return (bias ? EPI_BIAS : 0) | (ln ? EPI_LN : 0) | (res ? EPI_RES : 0) | (stats ? EPI_STATS : 0) | (act << EPI_ACT_SHIFT);
 }
 
-template <int BN, int EPI>
+// WRES ("weights resident"): the CTA keeps ONE N-tile for its whole life, loads that tile's W once and streams only A.
+// Without it every 128-row tile re-fetches its W tile from L2 (72-96 KB for 48 KB of A at K = 192), and the wide GEMMs
+// (qkv, fc1) ran at the L2 -> SM rate (~9 TB/s measured), not at the HBM rate.
+constexpr int MAX_STAGES = 8;
+
+template <int BN, int EPI, bool WRES>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                  const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
                  const __grid_constant__ CUtensorMap tmap_r, const Epilogue ep,
-                 const Addressing ad, int K, int num_n_tiles, int num_tiles) {
-    constexpr int STAGES = Cfg<BN>::STAGES, NACC = Cfg<BN>::NACC;
+                 const Addressing ad, int K, int num_n_tiles, int num_m_tiles, int stages) {
+    constexpr int NACC = Cfg<BN>::NACC;
     constexpr int B_BYTES = BN * BK * 2;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[NACC], acc_empty[NACC], res_full[EPI_GROUPS];
+    __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_empty[NACC], res_full[EPI_GROUPS], w_full;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int nkb = K / BK;
+    // shared memory: [resident W: nkb k-blocks][ring of A (+ B) stages][4 staging boxes]
+    const uint32_t ring_base = sbase + (WRES ? nkb * B_BYTES : 0);
+    const uint32_t stage_bytes = A_BYTES + (WRES ? 0 : B_BYTES);
+    const uint32_t staging_base = ring_base + stages * stage_bytes;
+    // tile walk: WRES: N-tile nt0 is fixed, M-tiles mt0, mt0 + mstep, ...; otherwise tiles blockIdx.x, + gridDim.x, ... in (mt, nt) order
+    const int nt0 = WRES ? (int)blockIdx.x % num_n_tiles : 0;
+    const int mt0 = WRES ? (int)blockIdx.x / num_n_tiles : 0, mstep = WRES ? (int)gridDim.x / num_n_tiles : 1;
+    const int num_tiles = num_n_tiles * num_m_tiles;
+    const int n_iter = WRES ? (mt0 < num_m_tiles ? (num_m_tiles - mt0 + mstep - 1) / mstep : 0)
+                            : ((int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+    auto tile_at = [&](int i, int& mt, int& nt) {
+        if (WRES) { mt = mt0 + i * mstep; nt = nt0; }
+        else { const int tile = (int)blockIdx.x + i * (int)gridDim.x; mt = tile / num_n_tiles; nt = tile - mt * num_n_tiles; }
+    };
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32); }
         for (int g = 0; g < EPI_GROUPS; ++g) mbar_init(&res_full[g], 1);
+        mbar_init(&w_full, 1);
         fence_barrier_init();
     }
     if (warp == MMA_WARP) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
@@ -131,10 +149,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t tm = tmem_slot;
 
     if (warp == PRODUCER_WARP) {
-        if (lane == 0) {
+        if (lane == 0 && n_iter > 0) {
+            if (WRES) {                                          // this CTA's W tile, once
+                mbar_expect_tx(&w_full, nkb * B_BYTES);
+                for (int kb = 0; kb < nkb; ++kb) tma_load_2d(sbase + kb * B_BYTES, &tmap_w, &w_full, kb * BK, nt0 * BN);
+            }
             int stage = 0, round = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+            for (int it = 0; it < n_iter; ++it) {
+                int mt, nt;
+                tile_at(it, mt, nt);
                 const int row0 = mt * BM;
                 int p0 = 0, p1 = 0, p2 = 0;                      // conv: x0, y0, b;  merge: j0, bi0
                 if (ad.mode == MODE_CONV) {
@@ -149,8 +172,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 int tap = 0, cc = 0;                             // running (tap, channel block) of the k loop
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (round > 0) mbar_wait(&empty[stage], (uint32_t)((round - 1) & 1));
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    const uint32_t sa = sbase + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], stage_bytes);
+                    const uint32_t sa = ring_base + stage * stage_bytes;
                     if (ad.mode == MODE_PLAIN) {
                         if (kb < ad.k_split) tma_load_2d(sa, &tmap_x, &full[stage], kb * BK, row0);
                         else tma_load_2d(sa, &tmap_x2, &full[stage], (kb - ad.k_split) * BK, row0);
@@ -161,27 +184,29 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         tma_load_5d(sa, &tmap_x, &full[stage], cc * BK, tap >> 1, p0, tap & 1, p1);
                     }
                     if (++cc == ad.cpb) { cc = 0; ++tap; }
-                    tma_load_2d(sa + A_BYTES, &tmap_w, &full[stage], kb * BK, nt * BN);
-                    if (++stage == STAGES) { stage = 0; ++round; }
+                    if (!WRES) tma_load_2d(sa + A_BYTES, &tmap_w, &full[stage], kb * BK, nt * BN);
+                    if (++stage == stages) { stage = 0; ++round; }
                 }
             }
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
             constexpr uint32_t idesc = idesc_bf16(BM, BN, false, false);
-            int stage = 0, round = 0, it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            int stage = 0, round = 0;
+            if (WRES && n_iter > 0) { mbar_wait(&w_full, 0); fence_after_sync(); }
+            for (int it = 0; it < n_iter; ++it) {
                 const int a = it % NACC;
                 if (it >= NACC) mbar_wait(&acc_empty[a], (uint32_t)(((it / NACC) - 1) & 1));
                 fence_after_sync();
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&full[stage], (uint32_t)(round & 1));
                     fence_after_sync();
-                    const uint64_t da = desc_sw128(sbase + stage * STAGE_BYTES), db = desc_sw128(sbase + stage * STAGE_BYTES + A_BYTES);
+                    const uint32_t sa = ring_base + stage * stage_bytes;
+                    const uint64_t da = desc_sw128(sa), db = desc_sw128(WRES ? sbase + kb * B_BYTES : sa + A_BYTES);
 #pragma unroll
                     for (int ks = 0; ks < BK / 16; ++ks) mma_ss(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
                     mma_commit(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; ++round; }
+                    if (++stage == stages) { stage = 0; ++round; }
                 }
                 mma_commit(&acc_full[a]);
             }
@@ -191,12 +216,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int quarter = warp & 3, eg = warp >> 2;
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        const uint32_t stage_box = sbase + STAGES * STAGE_BYTES + eg * BOX_BYTES;       // this group's staging box
+        const uint32_t stage_box = staging_base + eg * BOX_BYTES;                        // this group's staging box
         const uint32_t my_row = stage_box + row_in_tile * 128;
         const int sw = row_in_tile & 7;                                                   // SWIZZLE_128B: chunk ^= row % 8
         const bool issuer = quarter == 0 && lane == 0;
         constexpr int NBOX = BN / 64;
-        int it = 0;
         uint32_t res_phase = 0;
         constexpr bool ANY = EPI == EPI_ANY;
         const float* __restrict__ bias = (ANY || (EPI & EPI_BIAS)) ? ep.bias : nullptr;
@@ -204,9 +228,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const bool has_ln = ANY ? ep.ln_stats != nullptr : (EPI & EPI_LN) != 0;
         const bool has_stats = ANY ? ep.stats_out != nullptr : (EPI & EPI_STATS) != 0;
         const int act = ANY ? ep.act : (EPI >> EPI_ACT_SHIFT);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int it = 0; it < n_iter; ++it) {
             const int a = it % NACC;
-            const int mt = tile / num_n_tiles, nt = tile - mt * num_n_tiles;
+            int mt, nt;
+            tile_at(it, mt, nt);
             const int grow = mt * BM + row_in_tile;                      // global output row of this thread
             mbar_wait(&acc_full[a], (uint32_t)((it / NACC) & 1));
             fence_after_sync();
@@ -333,7 +358,9 @@ bool make_map_2d(CUtensorMap* m, const void* base, long long rows, long long col
     return make_map(m, base, 2, dims, strides, box, is_output ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-template <int BN, int EPI>
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+template <int BN, int EPI, bool WRES>
 int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
     CUtensorMap mw, mo, mr;
     if (!make_map_2d(&mw, g.w, g.N, g.K, g.K, BN, false) || !make_map_2d(&mo, g.out, g.M, g.N, g.ldo, BM, true)) return SODT_ERR_CUDA;
@@ -342,25 +369,47 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     const int num_n_tiles = g.N / BN, num_m_tiles = (g.M + BM - 1) / BM;
     const long long tiles = (long long)num_n_tiles * num_m_tiles;
     if (tiles > 2147483647LL) return SODT_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)Cfg<BN>::STAGES * (A_BYTES + BN * BK * 2) + EPI_GROUPS * BOX_BYTES + 1024;
-    auto kern = linear_tc_kernel<BN, EPI>;
+    constexpr int B_BYTES = BN * BK * 2;
+    const int fixed = EPI_GROUPS * BOX_BYTES + 1024 + (WRES ? (g.K / BK) * B_BYTES : 0);
+    int stages = (SMEM_LIMIT - fixed) / (A_BYTES + (WRES ? 0 : B_BYTES));
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) return SODT_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)fixed + (size_t)stages * (A_BYTES + (WRES ? 0 : B_BYTES));
+    auto kern = linear_tc_kernel<BN, EPI, WRES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+    int grid = (int)(tiles < num_sms ? tiles : num_sms);
+    if (WRES) grid = (num_sms / num_n_tiles) * num_n_tiles;      // a multiple of the N-tile count: CTA c keeps N-tile c % num_n_tiles
     Epilogue ep{};
     ep.bias = g.bias; ep.ln_stats = g.ln_stats; ep.ln_colsum = g.ln_colsum; ep.stats_out = g.stats_out;
     ep.M = g.M; ep.has_residual = g.residual != nullptr ? 1 : 0; ep.act = g.act;
     ep.res_tiles = (res_rows + BM - 1) / BM;
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, ep, ad, g.K, num_n_tiles, (int)tiles);
+    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, ep, ad, g.K, num_n_tiles, num_m_tiles, stages);
     return check_launch();
+}
+
+// W stays resident when the CTA's W tile plus >= 3 A stages fit (K <= 192 at BN = 256 / 192) and the M-tiles fill the machine
+template <int BN, int EPI>
+int launch_res(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream, bool wres) {
+    if (wres) return launch<BN, EPI, true>(mx, mx2, ad, g, num_sms, stream);
+    return launch<BN, EPI, false>(mx, mx2, ad, g, num_sms, stream);
 }
 
 template <int EPI>
 int dispatch_bn(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
-    if (g.N % 256 == 0) return launch<256, EPI>(mx, mx2, ad, g, num_sms, stream);
-    if (g.N % 192 == 0) return launch<192, EPI>(mx, mx2, ad, g, num_sms, stream);
-    if (g.N % 128 == 0) return launch<128, EPI>(mx, mx2, ad, g, num_sms, stream);
-    return launch<64, EPI>(mx, mx2, ad, g, num_sms, stream);
+    const int nkb = g.K / BK;
+    const long long m_tiles = (g.M + BM - 1) / BM;
+    auto fits = [&](int bn) {          // resident W tile + 3 A stages + staging within the shared-memory limit, enough M-tiles per CTA
+        const int n_nt = g.N / bn;
+        return g.N % bn == 0 && nkb * bn * BK * 2 + 3 * A_BYTES + EPI_GROUPS * BOX_BYTES + 1024 <= SMEM_LIMIT && n_nt <= num_sms &&
+               m_tiles >= 4LL * (num_sms / n_nt);
+    };
+    // the tile width is the widest that divides N; W stays resident only if it fits at that width (narrower resident
+    // tiles re-read A more often than the W re-fetches they save: measured slower at K = 384)
+    if (g.N % 256 == 0) return launch_res<256, EPI>(mx, mx2, ad, g, num_sms, stream, fits(256));
+    if (g.N % 192 == 0) return launch_res<192, EPI>(mx, mx2, ad, g, num_sms, stream, fits(192));
+    if (g.N % 128 == 0) return launch_res<128, EPI>(mx, mx2, ad, g, num_sms, stream, fits(128));
+    return launch_res<64, EPI>(mx, mx2, ad, g, num_sms, stream, fits(64));
 }
 
 int dispatch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
