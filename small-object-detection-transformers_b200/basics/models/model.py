@@ -69,7 +69,8 @@ class Detect(nn.Module):
         z = torch.empty((bs, sum(rows), self.no), dtype=torch.float32, device=raws[0].device)
         off = 0
         for i, r in enumerate(raws):
-            _, x[i] = ops.detect_decode(r, self.anchor_grid[i], float(self.stride[i]), want_perm=True, z=z,
+            anchors = ops.cached_derived(self.anchor_grid, ("level", i), lambda t, i=i: t[i].detach().float().reshape(-1, 2).contiguous())
+            _, x[i] = ops.detect_decode(r, anchors, float(self.stride[i]), want_perm=True, z=z,
                                         rows_total=z.shape[1], row_offset=off)
             off += rows[i]
         return z, x

@@ -106,7 +106,7 @@ def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=No
     if tuple(bias_table.shape) != (span, heads):
         raise ValueError(f"bias_table must be [{span}, {heads}], got {tuple(bias_table.shape)}")
     qkv = qkv.contiguous()
-    table = bias_table.detach().to(torch.float32).contiguous()
+    table = _as_f32(bias_table)          # cached fp32 copy (the parameter is bf16 in a bf16 model)
     if pad_qkv is not None:
         pad_qkv = pad_qkv.detach().to(qkv.dtype).contiguous()
         if pad_qkv.numel() != C3:
@@ -263,7 +263,7 @@ def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=No
     if raw.dim() != 4 or raw.dtype not in _DT:
         raise ValueError("raw must be a 4-D f32 / bf16 tensor")
     B, ch, ny, nx = raw.shape
-    anchors_px = anchors_px.detach().to(torch.float32).reshape(-1, 2).contiguous()
+    anchors_px = _as_f32(anchors_px).reshape(-1, 2)
     na = anchors_px.shape[0]
     if ch % na:
         raise ValueError("channels must be divisible by the number of anchors")
