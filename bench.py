@@ -8,8 +8,8 @@ One "step" = one pass of the detector (uint8 RGB+IR -> /255 -> backbone with the
 cross-channel attention kernels -> head -> Detect decode kernel -> NMS kernels) over one batch of
 32 synthetic 1024x1024 image pairs per GPU, random-init weights, bf16 storage with fp32
 softmax / LayerNorm statistics / decode / NMS.  `value` times it with inputs resident in HBM;
-`e2e` times the public API (`Detector.detect`) with pinned HOST uint8 inputs, the host->device
-copies and the device->host read of the detections inside the timed region.
+`e2e` times the public API (`Detector.detect_stream` / `ShardedDetector.detect_stream`) with pinned HOST
+uint8 inputs, the host->device copies and the device->host read of the detections inside the timed region.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -190,15 +190,6 @@ def run_sodt(args):
             return sharded.detect_device(rgb, ir)
         return det.detect_device(rgb, ir)
 
-    def step_e2e(i):
-        rgb, ir = host[i % n_host]
-        if sharded is not None:
-            buf = det.detect_device(rgb.to(dev, non_blocking=True), ir.to(dev, non_blocking=True))
-            from sodt_b200.runtime import allgather_detections
-            d, c = allgather_detections(buf)
-            return d.cpu(), c.cpu()
-        return det.detect(rgb, ir)
-
     def timed(fn, n):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -264,11 +255,8 @@ def run_sodt(args):
     # ---- end-to-end arm: public API, host uint8 in, host detections out.  Detector.detect_stream pipelines the
     # uploads / read-backs of neighbouring steps on a copy stream; every step's H2D and D2H copy is inside the timed region.
     def run_stream(n):
-        if sharded is not None:
-            for i in range(n):
-                step_e2e(i)
-            return
-        for _ in det.detect_stream(host[i % n_host] for i in range(n)):
+        src = sharded if sharded is not None else det
+        for _ in src.detect_stream(host[i % n_host] for i in range(n)):
             pass
 
     run_stream(3)           # warm-up: pinned result rings, copy stream

@@ -152,19 +152,23 @@ class Detector:
         flat = buf.flat.to("cpu")
         return DetectionBuffer.split(flat, buf.batch, buf.max_det)
 
-    def _rings(self, batch, depth=3):
-        key = ("ring", batch)
+    def _rings(self, batch, depth=3, world=1):
+        key = ("ring", batch, world)
         if key not in self._bufs:
             dev = [DetectionBuffer(batch, self.device) for _ in range(depth)]
-            host = [torch.empty(dev[0].flat.shape, dtype=dev[0].flat.dtype).pin_memory() for _ in range(depth)]
-            self._bufs[key] = (dev, host)
+            n = dev[0].flat.numel() * world
+            gathered = [torch.empty(n, dtype=torch.float32, device=self.device) for _ in range(depth)] if world > 1 else None
+            host = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(depth)]
+            self._bufs[key] = (dev, host, gathered)
         return self._bufs[key]
 
-    def detect_stream(self, batches):
+    def detect_stream(self, batches, group=None, world=1):
         """Pipelined inference over an iterable of (rgb_u8_host, ir_u8_host) pinned batches: the host->device copy of
         batch i+1 runs on a copy stream while batch i is computed, and the detections of batch i are read back while
         batch i+1 is computed.  Device / pinned host result buffers come from small preallocated rings (a yielded result
-        stays valid until two more results have been taken).  Yields (det [B,300,6], counts [B]) host tensors in order."""
+        stays valid until two more results have been taken).  Yields (det [B,300,6], counts [B]) host tensors in order.
+        With ``world`` > 1 (ShardedDetector.detect_stream) every batch is this rank's shard: the ranks' detections are
+        all-gathered on the device before the read-back and the yielded tensors cover all ``world * B`` images."""
         compute = torch.cuda.current_stream(self.device)
         copy = self.copy_stream
 
@@ -176,6 +180,13 @@ class Detector:
                 ev.record(copy)
             return rgb, ir, ev
 
+        def split(flat, batch):
+            if world == 1:
+                return DetectionBuffer.split(flat, batch, MAX_DET)
+            n = flat.numel() // world
+            parts = [DetectionBuffer.split(flat[r * n:(r + 1) * n], batch, MAX_DET) for r in range(world)]
+            return torch.cat([d for d, _ in parts]), torch.cat([c for _, c in parts])
+
         it = iter(batches)
         nxt = next(it, None)
         staged = upload(nxt) if nxt is not None else None
@@ -185,27 +196,31 @@ class Detector:
             rgb, ir, ev = staged
             nxt = next(it, None)
             staged = upload(nxt) if nxt is not None else None      # overlaps with the compute below
-            dev_ring, host_ring = self._rings(rgb.shape[0])
+            dev_ring, host_ring, gather_ring = self._rings(rgb.shape[0], world=world)
             buf, host = dev_ring[i % len(dev_ring)], host_ring[i % len(host_ring)]
             compute.wait_event(ev)
             self.detect_device(rgb, ir, buf)
             rgb.record_stream(compute)
             ir.record_stream(compute)
+            src = buf.flat
+            if world > 1:                                           # the only collective of the path: padded detections
+                src = gather_ring[i % len(gather_ring)]
+                dist.all_gather_into_tensor(src, buf.flat, group=group)
             done = torch.cuda.Event()
             done.record(compute)
             with torch.cuda.stream(copy):
                 copy.wait_event(done)
-                host.copy_(buf.flat, non_blocking=True)
+                host.copy_(src, non_blocking=True)
                 hev = torch.cuda.Event()
                 hev.record(copy)
             if pending is not None:
                 pending[1].synchronize()
-                yield DetectionBuffer.split(pending[0], pending[2], MAX_DET)
+                yield split(pending[0], pending[2])
             pending = (host, hev, buf.batch)
             i += 1
         if pending is not None:
             pending[1].synchronize()
-            yield DetectionBuffer.split(pending[0], pending[2], MAX_DET)
+            yield split(pending[0], pending[2])
 
     def __call__(self, rgb_u8_host, ir_u8_host):
         det, counts = self.detect(rgb_u8_host, ir_u8_host)
@@ -229,3 +244,8 @@ class ShardedDetector:
         """Each rank passes ITS shard (equal sizes); returns the gathered detections of all ranks."""
         buf = self.detector.detect_device(rgb_u8_local, ir_u8_local)
         return allgather_detections(buf, self.group)
+
+    def detect_stream(self, local_batches):
+        """Pipelined host API (see Detector.detect_stream): each rank feeds its own shard of every batch and receives the
+        detections of all ranks' images, in rank order."""
+        return self.detector.detect_stream(local_batches, group=self.group, world=self.world)
