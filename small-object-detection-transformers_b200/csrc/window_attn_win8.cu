@@ -29,6 +29,14 @@ namespace {
 
 using namespace tc;
 
+// Timeline instrumentation for tests/probes/win8_trace.cu (compiled only there): clock64 at the hand-offs of CTA 0.
+#ifdef SODT_WIN8_TRACE
+__device__ long long g_trace[4][96][12];
+#define TRACE(role, unit, ev) do { if (blockIdx.x == 0 && (unit) < 96) g_trace[role][unit][ev] = clock64(); } while (0)
+#else
+#define TRACE(role, unit, ev) do { } while (0)
+#endif
+
 constexpr int WS = 8;
 constexpr int NTOK = 64;                 // tokens per window
 constexpr int ROWS = 128;                // rows per tile = 2 windows
@@ -134,7 +142,9 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
             }
             __syncwarp();
             for (int gi = 0; gi < groups; ++gi) {
+                if (which == 0 && lane == 0) TRACE(3, (int)((tile - blockIdx.x) / gridDim.x) * groups + gi, 0);
                 if (round > 0) mbar_wait(&stage_empty[stage], (uint32_t)((round - 1) & 1));
+                if (which == 0 && lane == 0) TRACE(3, (int)((tile - blockIdx.x) / gridDim.x) * groups + gi, 1);
                 unsigned char* dst = smem + stage * STAGE_BYTES + which * OPERAND_BYTES + r4 * 16 +
                                      (which < 2 ? (pg >> 1) * PAIR_BYTES + pc * PLANE2 + (pg & 1) * (NTOK * 16) : (pg * CPH + pc) * PLANE);
                 const int wskip = which < 2 ? NTOK * 16 : 0;        // q, k: window 1 rows start after both heads of window 0
@@ -148,6 +158,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                     for (int i = 0; i < 16; ++i) *reinterpret_cast<uint4*>(dst + (b0 + i) * 64 + (b0 >> 4) * wskip) = v[i];
                 }
                 fence_proxy_async();
+                if (which == 0 && lane == 0) TRACE(3, (int)((tile - blockIdx.x) / gridDim.x) * groups + gi, 2);
                 mbar_arrive(&stage_full[stage]);
                 if (++stage == STAGES) { stage = 0; ++round; }
             }
@@ -167,8 +178,11 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
             // ---- cursor of the next unit whose scores are to be issued
             int qn = 0, q_us = 0, q_stage = 0, q_stage_par = 0, q_g = 0, q_k = 0;
             auto issue_qk = [&]() {
+                TRACE(2, qn, 0);
                 if (q_us == 0) mbar_wait(&stage_full[q_stage], (uint32_t)q_stage_par);
+                TRACE(2, qn, 1);
                 if (q_k > 0) mbar_wait(&s_free[q_g], (uint32_t)((q_k - 1) & 1));
+                TRACE(2, qn, 2);
                 fence_after_sync();
 #pragma unroll
                 for (int hh = 0; hh < HPB; ++hh) {
@@ -184,6 +198,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                                       ALL, ALL, 0u, 0u);
                 }
                 mma_commit(&s_full[q_g]);
+                TRACE(2, qn, 3);
                 ++qn;
                 if (++q_us == UPS) { q_us = 0; if (++q_stage == STAGES) { q_stage = 0; q_stage_par ^= 1; } }
                 if (++q_g == NG) { q_g = 0; ++q_k; }
@@ -194,7 +209,9 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                 // S[g] is free as soon as softmax(n) has copied it to registers, so the group's next scores are
                 // computed while softmax(n) is still running
                 if (qn < nt) issue_qk();
+                TRACE(2, n, 4);
                 mbar_wait(&p_full[g], (uint32_t)(k & 1));
+                TRACE(2, n, 5);
                 fence_after_sync();
                 // O[128 x 2hd] = P [V_even | V_odd] per head pair; the pairs' chains are interleaved (independent accumulators)
 #pragma unroll
@@ -207,6 +224,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                     }
                 }
                 mma_commit(&pv_done[g]);
+                TRACE(2, n, 6);
                 if (++us == UPS) { us = 0; mma_commit(&stage_empty[stage]); if (++stage == STAGES) stage = 0; }
                 if (++g == NG) { g = 0; ++k; }
             }
@@ -237,6 +255,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
         long long prev_stage = 0;                       // global stage index of the previous unit (tile_iter*groups + gi)
         float prev_inv[HPB] = {};
         const int st_tid = tid;                         // 0..255 among the softmax threads
+        [[maybe_unused]] int trace_n = 0;
         auto epilogue = [&]() {
             unsigned char* tile = ot + (prev_stage & 1) * OT_BYTES;
 #pragma unroll
@@ -244,6 +263,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                 uint32_t o[HD];
                 if constexpr (HD == 16) tmem_ld16(tO + hh * (2 * HD), o); else tmem_ld32(tO + hh * (2 * HD), o);
                 tmem_wait_ld();
+                if (row == 0 && hh == 0) TRACE(g, trace_n, 9);
                 const float inv = prev_inv[hh];
 #pragma unroll
                 for (int j = 0; j < HD; j += 8) {
@@ -255,6 +275,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                     *reinterpret_cast<uint4*>(tile + (g * NTOK + ti) * OT_LD + (2 * hh + hp) * HD * 2 + j * 2) = v;
                 }
             }
+            if (row == 0) TRACE(g, trace_n, 10);
             asm volatile("bar.sync 2, 256;" ::: "memory");           // both groups' halves of the stage tile are in smem
             const long long tile_it = prev_stage / groups;
             const int gcol = (int)(prev_stage - tile_it * groups) * 64;
@@ -291,7 +312,9 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                 }
                 any_mask = __any_sync(0xffffffffu, mbits != 0);
             }
+            if (row == 0) TRACE(g, (int)n, 0);
             mbar_wait(&s_full[g], (uint32_t)(k & 1));
+            if (row == 0) TRACE(g, (int)n, 1);
             fence_after_sync();
             float inv_cur[HPB];
 #pragma unroll
@@ -303,6 +326,7 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                     tmem_ld32(tS + hh * 64, r0);
                     tmem_ld32(tS + hh * 64 + 32, r1);
                     tmem_wait_ld();
+                    if (row == 0) TRACE(g, (int)n, 2 + hh * 4);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) { s2[j] = __uint_as_float(r0[j]); s2[32 + j] = __uint_as_float(r1[j]); }
                 }
@@ -327,16 +351,21 @@ window_attn_win8_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __re
                     pk[j >> 1] = pack_bf16(p0, p1);
                 }
                 inv_cur[hh] = 1.f / sum;
+                if (row == 0) TRACE(g, (int)n, 3 + hh * 4);
                 if (hh == 0 && k > 0) {                // previous unit of this group: its P / O columns are free again
                     mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
+                    if (row == 0) TRACE(g, (int)n, 4);
                     fence_after_sync();
+                    trace_n = (int)n;
                     epilogue();
+                    if (row == 0) TRACE(g, (int)n, 5);
                 }
                 tmem_st32(tP + hh * 32, pk);
             }
             tmem_wait_st();
             fence_before_sync();
             mbar_arrive(&p_full[g]);
+            if (row == 0) TRACE(g, (int)n, 8);
             have_prev = true;
             prev_stage = it * groups + (ut >> 1);
 #pragma unroll
