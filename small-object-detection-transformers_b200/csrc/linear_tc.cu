@@ -228,11 +228,26 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const bool has_ln = ANY ? ep.ln_stats != nullptr : (EPI & EPI_LN) != 0;
         const bool has_stats = ANY ? ep.stats_out != nullptr : (EPI & EPI_STATS) != 0;
         const int act = ANY ? ep.act : (EPI >> EPI_ACT_SHIFT);
+        // (mean, rstd) of this thread's A row for a folded LayerNorm, fetched one tile ahead: issued per box, the L2 latency of
+        // this load was exposed in every box (+0.25 ms on the fc1 GEMM)
+        auto load_mr = [&](int i) {
+            float2 r = make_float2(0.f, 1.f);
+            if (has_ln && i < n_iter) {
+                int mt_, nt_;
+                tile_at(i, mt_, nt_);
+                const int gr = mt_ * BM + row_in_tile;
+                if (gr < ep.M) r = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + gr);
+            }
+            return r;
+        };
+        float2 mr_next = load_mr(0);
         for (int it = 0; it < n_iter; ++it) {
             const int a = it % NACC;
             int mt, nt;
             tile_at(it, mt, nt);
             const int grow = mt * BM + row_in_tile;                      // global output row of this thread
+            const float2 mr = mr_next;
+            mr_next = load_mr(it + 1);
             mbar_wait(&acc_full[a], (uint32_t)((it / NACC) & 1));
             fence_after_sync();
 #pragma unroll 1
@@ -246,9 +261,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, (mt % ep.res_tiles) * BM);
                     }
                 }
-                // (mean, rstd) of this thread's A row for a folded LayerNorm; the load is issued ahead of the TMEM load
-                float2 mr = make_float2(0.f, 1.f);
-                if (has_ln && grow < ep.M) mr = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + grow);
                 // accumulator columns in chunks of 16, the next chunk in flight while this one is processed (the kernel
                 // runs at the register cap of 576 threads: two 32-column loads spilled once the LayerNorm terms were added)
                 uint32_t ra[16], rb[16];
@@ -283,9 +295,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] += bb[e];
                     }
-                    if (act == 1) {
+                    if (act == 1) {                               // two elements per instruction: the GELU epilogue is issue-bound
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = gelu_fast(v[e]);
+                        for (int e = 0; e < 8; e += 2) gelu_fast2(v[e], v[e + 1]);
                     } else if (act == 2) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);

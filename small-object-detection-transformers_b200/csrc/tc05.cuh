@@ -196,6 +196,24 @@ __device__ __forceinline__ float gelu_fast(float x) {
     const float hx = 0.5f * x;
     return fmaf(hx, fast_tanh(x * q), hx);
 }
+// The same GELU on a PAIR of values in packed fp16 arithmetic (HMUL2 / HFMA2 / one MUFU.TANH.F16x2 for both): half the
+// instructions per element.  fp16's 11-bit significand keeps the result within ~2^-11 of the fp32 evaluation, the same
+// class as the MUFU.TANH error above; x^2 saturating to +inf for |x| > 255 is absorbed by the clamp.
+__device__ __forceinline__ void gelu_fast2(float& a, float& b) {
+    uint32_t x, s, q, t, hx, y;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(b), "f"(a));
+    asm("mul.f16x2 %0, %1, %1;" : "=r"(s) : "r"(x));
+    asm("min.f16x2 %0, %1, %2;" : "=r"(s) : "r"(s), "r"(0x54005400u));                   // 64.0
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(s), "r"(0x8DC28DC2u), "r"(0x28BD28BDu));   // -0.0003515, 0.037006
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(q), "r"(s), "r"(0x3A613A61u));             // 0.797508
+    asm("mul.f16x2 %0, %1, %2;" : "=r"(q) : "r"(x), "r"(q));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(q));
+    asm("mul.f16x2 %0, %1, %2;" : "=r"(hx) : "r"(x), "r"(0x38003800u));                  // 0.5
+    asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hx), "r"(t));
+    const __half2 h = *reinterpret_cast<const __half2*>(&y);
+    a = __low2float(h);
+    b = __high2float(h);
+}
 // SiLU for bf16 outputs: x sigmoid(x) = 0.5 x (1 + tanh(x / 2)) exactly; one MUFU
 __device__ __forceinline__ float silu_fast(float x) {
     const float hx = 0.5f * x;
