@@ -221,6 +221,14 @@ int sodt_conv2d_nhwc_supported(int B, int H, int W, int Cin, int Cout, int kh, i
 int sodt_conv2d_nhwc_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo,
                          int B, int H, int W, int Cin, int Cout, int kh, int kw, int pad_t, int pad_l,
                          int act, int dtype, void* stream);
+/* 1x1 convolution over cat(nearest_upsample_2x(low), skip) on the channel axis -- the head's "nn.Upsample, Concat, C3.cv1/cv2"
+ * rows (models/model.yaml head rows 1-3 and 5-7; common.py:114-126) -- without the upsampled or the concatenated tensor:
+ * the first C1 input channels of pixel (y, x) are read from low[b, y/2, x/2, :] through a TMA map with zero-stride
+ * duplicate dimensions, the other C2 from skip[b, y, x, :].  low [B, H/2, W/2, C1], skip [B, H, W, C2], w [Cout, C1 + C2],
+ * out [B, H, W, Cout] (row stride ldo), all bf16 channels-last; H, W = the output size. */
+int sodt_upcat_conv1x1_supported(int B, int H, int W, int C1, int C2, int Cout, int dtype);
+int sodt_upcat_conv1x1_fwd(const void* low, const void* skip, const void* w, const float* bias, void* out, int ldo,
+                           int B, int H, int W, int C1, int C2, int Cout, int act, int dtype, void* stream);
 int sodt_patch_merge_linear_supported(int B, int H, int W, int C, int N, int dtype);
 int sodt_patch_merge_linear_fwd(const void* x, const void* w, const float* bias, void* out, int B, int H, int W,
                                 int C, int N, int dtype, void* stream);

@@ -40,6 +40,8 @@ SIGNATURES = {
     "sodt_stats_finalize": (_i, [_p, _i, _p, _ll, _i, _f, _p]),
     "sodt_conv2d_nhwc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "sodt_conv2d_nhwc_fwd": (_i, [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "sodt_upcat_conv1x1_supported": (_i, [_i, _i, _i, _i, _i, _i, _i]),
+    "sodt_upcat_conv1x1_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_patch_merge_linear_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "sodt_patch_merge_linear_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_bias_act_crop_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -101,22 +101,34 @@ class C3(nn.Module):
         return self._bw
 
     def forward(self, x):
+        """``x``: NCHW-shaped tensor, or an ops.UpCat (upsample + concat not materialised: read through TMA addressing)."""
+        from ... import ops
+        lazy = x if isinstance(x, ops.UpCat) else None
         convs = (self.cv1, self.cv2, self.cv3)
         if (x.is_cuda and x.dtype == torch.bfloat16 and all(not hasattr(c, "bn") and isinstance(c.act, nn.SiLU)
                                                             and c.conv.kernel_size == (1, 1) and c.conv.bias is not None for c in convs)):
-            from ... import ops
-            xh = x.permute(0, 2, 3, 1)
             c_ = self.cv1.conv.out_channels
-            if ops.conv2d_nhwc_supported(xh, 2 * c_, 1, 1):
+            buf = None
+            if lazy is not None and ops.upcat_conv1x1_supported(lazy, 2 * c_):
+                w12, b12 = self._branch_weights()
+                buf = ops.upcat_conv1x1(lazy, w12, b12, "silu")
+            else:
+                if lazy is not None:
+                    x, lazy = lazy.materialize(), None
+                xh = x.permute(0, 2, 3, 1)
+                if ops.conv2d_nhwc_supported(xh, 2 * c_, 1, 1):
+                    w12, b12 = self._branch_weights()
+                    buf = ops.conv2d_nhwc(xh, w12, b12, (1, 1), (0, 0), "silu")
+            if buf is not None:
                 # both branches land in the halves of one [B,H,W,2c_] buffer: no torch.cat, the bottleneck chain's last
                 # conv writes over the cv1 half it no longer needs
-                w12, b12 = self._branch_weights()
-                buf = ops.conv2d_nhwc(xh, w12, b12, (1, 1), (0, 0), "silu")
                 half = buf[..., :c_]
                 t = half.permute(0, 3, 1, 2)
                 for i, m in enumerate(self.m):
                     t = m(t, out=half) if i == len(self.m) - 1 else m(t)
                 return self.cv3(buf.permute(0, 3, 1, 2))
+        if lazy is not None:
+            x = lazy.materialize()
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), dim=1))
 
 

@@ -246,13 +246,19 @@ class Model(nn.Module):
                     and m.scale_factor in (2, 2.0) and isinstance(nxt.f, list) and len(nxt.f) == 2 and nxt.f[0] == -1
                     and x.is_cuda and (x.shape[1] * x.element_size()) % 16 == 0
                     and (y[nxt.f[1]].shape[1] * x.element_size()) % 16 == 0):
-                # nn.Upsample(2, nearest) + Concat([-1, k]) in one pass; the upsampled tensor itself is not kept
-                x = ops.upsample2x_concat(x, y[nxt.f[1]])
+                # nn.Upsample(2, nearest) + Concat([-1, k]) are not executed: the following C3 reads the two sources through TMA
+                # addressing (ops.UpCat); any other consumer materialises the concatenation in one fused pass
+                x = ops.UpCat(x, y[nxt.f[1]])
                 y.append(None)
                 y.append(x)
                 i += 2
                 continue
+            if isinstance(x, ops.UpCat) and not isinstance(m, C3):
+                x = x.materialize()
             if m.f != -1:
+                for j in ([m.f] if isinstance(m.f, int) else m.f):          # a later consumer of a lazy concatenation
+                    if j != -1 and isinstance(y[j], ops.UpCat):
+                        y[j] = y[j].materialize()
                 x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
             x = m(x)
             y.append(x)

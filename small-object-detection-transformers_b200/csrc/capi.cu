@@ -87,6 +87,19 @@ extern "C" int sodt_conv2d_nhwc_fwd(const void* x, int ldx, const void* w, const
     return conv_tc(x, ldx, w, bias, out, ldo, B, H, W, Cin, Cout, kh, kw, pad_t, pad_l, act, sm_count(), static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int sodt_upcat_conv1x1_supported(int B, int H, int W, int C1, int C2, int Cout, int dtype) {
+    return dtype == SODT_BF16 && sodt::upcat_tc_supported(B, H, W, C1, C2, Cout) ? 1 : 0;
+}
+
+extern "C" int sodt_upcat_conv1x1_fwd(const void* low, const void* skip, const void* w, const float* bias, void* out, int ldo,
+                                      int B, int H, int W, int C1, int C2, int Cout, int act, int dtype, void* stream) {
+    using namespace sodt;
+    if (!low || !skip || !w || !out || B <= 0 || H <= 0 || W <= 0 || act < 0 || act > 2) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_BF16 || !upcat_tc_supported(B, H, W, C1, C2, Cout)) return SODT_ERR_UNSUPPORTED;
+    if (!aligned16(low) || !aligned16(skip) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias))) return SODT_ERR_ALIGNMENT;
+    return upcat_tc(low, skip, w, bias, out, ldo, B, H, W, C1, C2, Cout, act, sm_count(), static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int sodt_patch_merge_linear_supported(int B, int H, int W, int C, int N, int dtype) {
     return dtype == SODT_BF16 && sodt::merge_tc_supported(B, H, W, C, N) ? 1 : 0;
 }

@@ -284,8 +284,8 @@ extern "C" int sodt_stats_finalize(const float* partials, int boxes, float* mean
     using namespace sodt;
     if (!partials || !mean_rstd || rows <= 0 || boxes <= 0 || C <= 0 || eps < 0.f) return SODT_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(partials) & 7) || (reinterpret_cast<uintptr_t>(mean_rstd) & 7)) return SODT_ERR_ALIGNMENT;
-    long long blocks = (rows + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    long long blocks = (rows + 255) / 256;             // one row per thread: latency-bound with fewer threads
+    if (blocks > 148 * 64) blocks = 148 * 64;
     stats_finalize_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(partials), reinterpret_cast<float2*>(mean_rstd), rows, boxes, 1.f / (float)C, eps);
     return check_launch();

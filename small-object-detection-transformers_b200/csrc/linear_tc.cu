@@ -43,7 +43,7 @@ constexpr int EPI_WARPS = EPI_GROUPS * 4;
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 
-enum { MODE_PLAIN = 0, MODE_CONV = 1, MODE_MERGE = 2 };
+enum { MODE_PLAIN = 0, MODE_CONV = 1, MODE_MERGE = 2, MODE_UPCAT = 3 };
 
 struct Epilogue {
     const float* bias;
@@ -160,7 +160,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 tile_at(it, mt, nt);
                 const int row0 = mt * BM;
                 int p0 = 0, p1 = 0, p2 = 0;                      // conv: x0, y0, b;  merge: j0, bi0
-                if (ad.mode == MODE_CONV) {
+                if (ad.mode == MODE_CONV || ad.mode == MODE_UPCAT) {
                     p2 = row0 / ad.HW;
                     const int rem = row0 - p2 * ad.HW;
                     p1 = rem / ad.W;
@@ -180,6 +180,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     } else if (ad.mode == MODE_CONV) {
                         const int ky = tap / ad.kw, kx = tap - ky * ad.kw;
                         tma_load_4d(sa, &tmap_x, &full[stage], cc * BK, p0 + kx - ad.pad_l, p1 + ky - ad.pad_t, p2);
+                    } else if (ad.mode == MODE_UPCAT) {
+                        // channels [0, k_split * 64): nearest-neighbour 2x upsample of the low-resolution tensor -- pixel (y, x) reads
+                        // (y / 2, x / 2) through two zero-stride "duplicate" dimensions of the map; the rest: the skip tensor
+                        if (kb < ad.k_split) tma_load_5d(sa, &tmap_x, &full[stage], kb * BK, 0, p0 >> 1, 0, p2 * (ad.pad_t >> 1) + (p1 >> 1));
+                        else tma_load_4d(sa, &tmap_x2, &full[stage], (kb - ad.k_split) * BK, p0, p1, p2);
                     } else {                                     // K order of the reference concat: (dy,dx) = (0,0),(1,0),(0,1),(1,1)
                         tma_load_5d(sa, &tmap_x, &full[stage], cc * BK, tap >> 1, p0, tap & 1, p1);
                     }
@@ -497,6 +502,35 @@ int conv_tc(const void* x, int ldx, const void* w, const float* bias, void* out,
     CUtensorMap mx;
     if (!make_map(&mx, x, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return SODT_ERR_CUDA;
     return dispatch(mx, mx, ad, g, num_sms, stream);
+}
+
+// 1x1 conv over cat(upsample2x_nearest(low), skip) without the concatenated tensor (head rows "Upsample, Concat, C3")
+bool upcat_tc_supported(int B, int H, int W, int C1, int C2, int Cout) {
+    int bw, bh;
+    return B > 0 && H % 2 == 0 && W % 2 == 0 && C1 % BK == 0 && C1 >= BK && C2 % BK == 0 && C2 >= BK && Cout % 64 == 0 && Cout >= 64 &&
+           tile_geometry(H, W, &bw, &bh) && bw % 2 == 0 && (bh == 1 || bh % 2 == 0) && (long long)B * H * W < 2147483647LL;
+}
+
+int upcat_tc(const void* low, const void* skip, const void* w, const float* bias, void* out, int ldo, int B, int H, int W, int C1, int C2,
+             int Cout, int act, int num_sms, cudaStream_t stream) {
+    int bw, bh;
+    if (!upcat_tc_supported(B, H, W, C1, C2, Cout) || !tile_geometry(H, W, &bw, &bh)) return SODT_ERR_UNSUPPORTED;
+    if (ldo % 8 || ldo < Cout) return SODT_ERR_INVALID_ARG;
+    LinearTcArgs g{};
+    g.x = low; g.ldx = C1; g.w = w; g.bias = bias; g.residual = nullptr; g.ldr = 0; g.res_rows = 0; g.out = out; g.ldo = ldo;
+    g.M = B * H * W; g.N = Cout; g.K = C1 + C2; g.act = act;
+    Addressing ad{};
+    ad.mode = MODE_UPCAT; ad.k_split = C1 / BK; ad.cpb = 1 << 30; ad.kw = 1; ad.pad_t = H; ad.pad_l = 0; ad.HW = H * W; ad.W = W;   // pad_t carries H
+    // low [B, H/2, W/2, C1] as (c, dup_x, x/2, dup_y, b * H/2 + y/2) with zero strides on the duplicate dimensions
+    const long long dl[5] = {C1, 2, W / 2, 2, (long long)B * (H / 2)};
+    const long long sl[4] = {0, C1, 0, (long long)(W / 2) * C1};
+    const int bl[5] = {64, 2, bw / 2, bh == 1 ? 1 : 2, bh == 1 ? 1 : bh / 2};
+    const long long ds[4] = {C2, W, H, B}, ss[3] = {C2, (long long)W * C2, (long long)H * W * C2};
+    const int bs[4] = {64, bw, bh, 1};
+    CUtensorMap ml, ms;
+    if (!make_map(&ml, low, 5, dl, sl, bl, CU_TENSOR_MAP_L2_PROMOTION_L2_256B) ||
+        !make_map(&ms, skip, 4, ds, ss, bs, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return SODT_ERR_CUDA;
+    return dispatch(ml, ms, ad, g, num_sms, stream);
 }
 
 bool merge_tc_supported(int B, int H, int W, int C, int N) {

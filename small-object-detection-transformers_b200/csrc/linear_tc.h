@@ -31,6 +31,10 @@ bool conv_tc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw);
 int conv_tc(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int H, int W, int Cin, int Cout,
             int kh, int kw, int pad_t, int pad_l, int act, int num_sms, cudaStream_t stream);
 
+bool upcat_tc_supported(int B, int H, int W, int C1, int C2, int Cout);
+int upcat_tc(const void* low, const void* skip, const void* w, const float* bias, void* out, int ldo, int B, int H, int W, int C1, int C2,
+             int Cout, int act, int num_sms, cudaStream_t stream);
+
 bool merge_tc_supported(int B, int H, int W, int C, int N);
 int merge_tc(const void* x, const void* w, const float* bias, void* out, int B, int H, int W, int C, int N, int num_sms,
              cudaStream_t stream);

@@ -556,6 +556,45 @@ def upsample2x_concat(low, skip):
     return out.permute(0, 3, 1, 2)
 
 
+class UpCat:
+    """cat([nearest_upsample_2x(low), skip], dim=1) that has not been materialised: NCHW-shaped channels-last tensors
+    ``low`` [B,C1,H/2,W/2] and ``skip`` [B,C2,H,W].  The head's C3 reads it through TMA addressing (upcat_conv1x1);
+    anything else calls ``materialize()``."""
+
+    def __init__(self, low, skip):
+        self.low, self.skip = low, skip
+        self.shape = (skip.shape[0], low.shape[1] + skip.shape[1], skip.shape[2], skip.shape[3])
+        self.dtype, self.device, self.is_cuda = skip.dtype, skip.device, skip.is_cuda
+
+    def materialize(self):
+        return upsample2x_concat(self.low, self.skip)
+
+
+def upcat_conv1x1_supported(uc, cout):
+    B, _, H, W = uc.shape
+    return bool(USE_TC_LINEAR and uc.is_cuda and uc.dtype == torch.bfloat16 and uc.low.dtype == torch.bfloat16
+                and _capi.lib().sodt_upcat_conv1x1_supported(B, H, W, uc.low.shape[1], uc.skip.shape[1], cout, 1))
+
+
+def upcat_conv1x1(uc, weight, bias, act=None):
+    """act(conv1x1(cat(up2x(low), skip)) + bias) -> [B,H,W,Cout] without the upsampled / concatenated tensors.
+    weight [Cout, C1 + C2] bf16 (input channel order: upsampled first)."""
+    _require_cuda(uc.low, uc.skip, weight, bias)
+    B, _, H, W = uc.shape
+    lo = uc.low.permute(0, 2, 3, 1).contiguous()          # no copy when already channels-last
+    sk = uc.skip.permute(0, 2, 3, 1).contiguous()
+    C1, C2, Cout = lo.shape[-1], sk.shape[-1], weight.shape[0]
+    if weight.shape[1] != C1 + C2 or weight.dtype != torch.bfloat16:
+        raise ValueError("weight must be bf16 [Cout, C1 + C2]")
+    out = torch.empty((B, H, W, Cout), dtype=torch.bfloat16, device=sk.device)
+    b32 = _as_f32(bias)
+    with torch.cuda.device(sk.device), _Timed(f"upcat_conv1x1[B={B},H={H},W={W},C1={C1},C2={C2},Cout={Cout},act={act}]"):
+        st = _capi.lib().sodt_upcat_conv1x1_fwd(lo.data_ptr(), sk.data_ptr(), weight.data_ptr(), _ptr(b32), out.data_ptr(), Cout,
+                                                B, H, W, C1, C2, Cout, _LIN_ACT[act], 1, _stream())
+    _capi.check(st, "sodt_upcat_conv1x1_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------------- NMS
 _workspaces = {}
 

@@ -243,6 +243,24 @@ def test_conv2d_nhwc_tap_gemm_vs_torch(B, H, W, Cin, Cout, k, pad, act):
     assert rel_err(out, ref.permute(0, 2, 3, 1)) < 4e-3
 
 
+@pytest.mark.parametrize("B,H,W,C1,C2,Cout,act", [(2, 8, 256, 128, 256, 128, "silu"), (2, 16, 128, 256, 256, 256, "silu"),
+                                                     (1, 32, 64, 64, 128, 64, None), (3, 16, 32, 128, 64, 128, "silu")])
+def test_conv2d_nhwc_upsample_concat_as_operand_addressing(B, H, W, C1, C2, Cout, act):
+    """1x1 conv over cat(up2x(low), skip) through zero-stride TMA dimensions == the materialised upsample + concat + conv."""
+    low = fx.det_input(f"uc_low:{B}:{H}:{W}:{C1}", (B, H // 2, W // 2, C1)).to("cuda", torch.bfloat16)
+    skip = fx.det_input(f"uc_skip:{B}:{H}:{W}:{C2}", (B, H, W, C2)).to("cuda", torch.bfloat16)
+    w = (fx.det_input(f"uc_w:{Cout}:{C1 + C2}", (Cout, C1 + C2)) / (C1 + C2) ** 0.5).to("cuda", torch.bfloat16)
+    b = 0.2 * fx.det_input(f"uc_b:{Cout}", (Cout,))
+    uc = ops().UpCat(low.permute(0, 3, 1, 2), skip.permute(0, 3, 1, 2))
+    assert ops().upcat_conv1x1_supported(uc, Cout)
+    out = ops().upcat_conv1x1(uc, w, b.cuda(), act)
+    up = low.double().cpu().repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    ref = torch.cat((up, skip.double().cpu()), -1) @ w.double().cpu().t() + b.double()
+    ref = torch.nn.functional.silu(ref) if act == "silu" else ref
+    assert out.shape == (B, H, W, Cout) and rel_err(out, ref) < 4e-3
+    assert torch.equal(uc.materialize().permute(0, 2, 3, 1), torch.cat((up, skip.double().cpu()), -1).to(torch.bfloat16).cuda())
+
+
 def test_conv2d_nhwc_channel_slices():
     """Input and output as channel slices of wider NHWC buffers (the head's C3 without torch.cat)."""
     B, H, W, C = 2, 32, 128, 64
