@@ -25,6 +25,7 @@ class Detect(nn.Module):
     """YOLOv5 detection layer (reference model.py:32-70)."""
     stride = None   # set by Model
     export = False
+    want_raw = True   # eval mode returns (z, x) like the reference; runtime.Detector only needs z and turns the second output off
 
     def __init__(self, nc=80, anchors=(), ch=()):
         super().__init__()
@@ -70,10 +71,10 @@ class Detect(nn.Module):
         off = 0
         for i, r in enumerate(raws):
             anchors = ops.cached_derived(self.anchor_grid, ("level", i), lambda t, i=i: t[i].detach().float().reshape(-1, 2).contiguous())
-            _, x[i] = ops.detect_decode(r, anchors, float(self.stride[i]), want_perm=True, z=z,
+            _, x[i] = ops.detect_decode(r, anchors, float(self.stride[i]), want_perm=self.want_raw, z=z,
                                         rows_total=z.shape[1], row_offset=off)
             off += rows[i]
-        return z, x
+        return z, (x if self.want_raw else None)
 
 
 _MODULES = {

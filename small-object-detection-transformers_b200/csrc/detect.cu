@@ -13,12 +13,15 @@ namespace {
 constexpr int XT = 64;
 constexpr int THREADS = 256;
 
-template <typename T>
+// NA_ / NO_ > 0: compile-time anchor / output counts (the detector's 3 x 13: the index arithmetic below divides by them
+// for every element, and a run-time divisor costs ~20 instructions); 0: run-time values.
+template <typename T, int NA_, int NO_>
 __global__ void __launch_bounds__(THREADS)
 detect_decode_kernel(const T* __restrict__ raw, long long sb, long long sc, long long sy, long long sx,
                      const float* __restrict__ anchors_px, float* __restrict__ z, T* __restrict__ x_perm,
-                     int na, int no, int ny, int nx, float stride, long long rows_total, long long row_offset) {
+                     int na_rt, int no_rt, int ny, int nx, float stride, long long rows_total, long long row_offset) {
     extern __shared__ float tile[];  // [na*no][XT+1]
+    const int na = NA_ > 0 ? NA_ : na_rt, no = NO_ > 0 ? NO_ : no_rt;
     const int CH = na * no;
     const int x0 = blockIdx.x * XT;
     const int y = blockIdx.y;
@@ -76,10 +79,15 @@ extern "C" int sodt_detect_decode(const void* raw, long long sb, long long sc, l
     dim3 grid((nx + XT - 1) / XT, ny, B);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == SODT_F32)
-        detect_decode_kernel<float><<<grid, THREADS, smem, s>>>(static_cast<const float*>(raw), sb, sc, sy, sx, anchors_px, z,
-                                                               static_cast<float*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
+        detect_decode_kernel<float, 0, 0><<<grid, THREADS, smem, s>>>(static_cast<const float*>(raw), sb, sc, sy, sx, anchors_px, z,
+                                                                     static_cast<float*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
+    else if (na == 3 && no == 13)
+        detect_decode_kernel<__nv_bfloat16, 3, 13><<<grid, THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx, anchors_px,
+                                                                              z, static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride,
+                                                                              rows_total, row_offset);
     else
-        detect_decode_kernel<__nv_bfloat16><<<grid, THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx, anchors_px, z,
-                                                                       static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
+        detect_decode_kernel<__nv_bfloat16, 0, 0><<<grid, THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx, anchors_px, z,
+                                                                             static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride,
+                                                                             rows_total, row_offset);
     return check_launch();
 }

@@ -4,7 +4,7 @@
 // (CAttentionBlock, :469-561: with one token per window attention returns v, so x_i = LayerNorm_i(e_i + e_partner) for
 // the pairs R<-G, G<-B, B<-IR, IR<-G) and the channel concatenation of :210.
 //
-// Work split: 8 lanes per token (lane q owns output channels 6q..6q+5 of every stream), 2 tokens per thread, 32 tokens
+// Work split: 8 lanes per token (lane q owns output channels 6q..6q+5 of every stream), 4 tokens per thread, 64 tokens
 // per 128-thread block.  The block first stages the 4 x 16 pixels of its tokens in shared memory (fp32); conv weights sit
 // in shared memory transposed to [stream][tap][channel] so that the 8 lanes of a token read 8 distinct banks and the four
 // token groups of a warp broadcast.  The add + LayerNorm statistics are reduced over the 8 lanes with shuffles.  The four
@@ -17,8 +17,8 @@ namespace {
 constexpr int KS = 4;            // kernel size = stride
 constexpr int E = 48;            // embedding channels per stream
 constexpr int CPL = 6;           // channels per lane (8 lanes x 6 = 48)
-constexpr int TPT = 2;           // tokens per thread
-constexpr int TOK_PER_BLOCK = 32;
+constexpr int TPT = 4;           // tokens per thread: every weight read from shared memory feeds TPT x 6 FMAs (the kernel is LDS-bound)
+constexpr int TOK_PER_BLOCK = 16 * TPT;
 
 template <typename T>
 __device__ __forceinline__ void store6(T* dst, const float (&y)[CPL]) {
@@ -64,8 +64,8 @@ frontend_kernel(const TI* __restrict__ x, long long sb, long long sc, long long 
     for (long long grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const long long tok0 = grp * TOK_PER_BLOCK;
     __syncthreads();                                                  // previous group's pixels are no longer read
-    {   // stage: thread -> (token tid/4, channel tid%4)
-        const int tl = tid >> 2, s = tid & 3;
+    for (int half = 0; half < TOK_PER_BLOCK / 32; ++half) {   // stage: thread -> (token tid/4 + 32*half, channel tid%4)
+        const int tl = (tid >> 2) + 32 * half, s = tid & 3;
         const long long tok = tok0 + tl;
         float px[16];
 #pragma unroll

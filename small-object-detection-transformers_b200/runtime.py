@@ -74,6 +74,9 @@ class Detector:
             model.load_state_dict(state_dict, strict=False)
         # like the reference's inference loader (models/experimental.py:118-120): fold BatchNorm into the convs
         self.model = model.eval().fuse().to(self.device, dtype)
+        for m in self.model.modules():                  # the runtime reads only the decoded predictions
+            if hasattr(m, "want_raw"):
+                m.want_raw = False
         self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._bufs = {}
         # one CUDA graph per input shape: the ~1400 launches of a step are replayed with one driver call
