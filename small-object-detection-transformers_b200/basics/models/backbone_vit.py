@@ -98,6 +98,8 @@ class PatchEmbed(nn.Module):
         w = w.reshape(w.shape[0], w.shape[1])
         if x.is_cuda and x.dtype == torch.bfloat16 and (pos is None or (tuple(pos.shape[1:]) == tuple(x.shape[1:3]) + (w.shape[0],)
                                                                         and (pos.shape[1] * pos.shape[2]) % 128 == 0)):
+            if want_stats and ops.linear_ln_supported(x, w.shape[0]):
+                return ops.linear(x, w, self.proj.bias, residual=pos, want_stats=True)    # row statistics for the first norm1
             y = ops.linear(x, w, self.proj.bias, residual=pos)
             return (y, None) if want_stats else y
         y = F.linear(x, w, self.proj.bias)
@@ -470,10 +472,10 @@ class ImageEncoderViT(nn.Module):
         pos = self.pos_embed                                     # silently skipped on a size mismatch, like the reference
         if pos is not None and x.shape[1] != pos.shape[1]:
             pos = None
-        x = self.patch_embed.forward_tokens(x, pos)
+        x, st = self.patch_embed.forward_tokens(x, pos, want_stats=True)
         B, h, w, C = x.shape
         x = x.reshape(B, h * w, C)
-        kept, st = [], None
+        kept = []
         for n, blk in enumerate(self.stage1):
             x, st = blk(x, (h, w), stats=st, want_stats=True)
             if n in (4, 5):

@@ -419,8 +419,8 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
             o2, ldo = _rows(out)
             if o2 is not out or out.dtype != torch.bfloat16 or out.numel() != M * N:
                 raise ValueError("out must be a bf16 row-strided view with M*N elements")
-        if (ln is not None or want_stats) and (x2 is not None or res_rows):
-            raise ValueError("ln / want_stats cannot be combined with x2 or a broadcast residual")
+        if (ln is not None or want_stats) and x2 is not None:
+            raise ValueError("ln / want_stats cannot be combined with x2")
         mr, ln_w, ln_b = ln if ln is not None else (None, None, None)
         if mr is not None and (mr.dtype != torch.float32 or not mr.is_contiguous() or tuple(mr.shape) != (M, 2)):
             raise ValueError("ln mean_rstd must be contiguous fp32 [M, 2]")
@@ -431,7 +431,7 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
                               else (weight.detach().contiguous(), None, _as_f32(bias)))
             with torch.cuda.device(x.device), _Timed(label):
                 st = _capi.lib().sodt_linear_ln_fwd(xa.data_ptr(), ldx, _ptr(mr), _ptr(colsum), w.data_ptr(), _ptr(b32),
-                                                    _ptr(res), ldr, out.data_ptr(), ldo, _ptr(stats_out), M, N, K,
+                                                    _ptr(res), ldr, res_rows, out.data_ptr(), ldo, _ptr(stats_out), M, N, K,
                                                     _LIN_ACT[act], 1, _stream())
             _capi.check(st, "sodt_linear_ln_fwd")
         else:

@@ -48,6 +48,12 @@ for _ in range(reps):
     ops.row_stats(xt, 1e-5)
     del hid, x1, part, mr
 del xt
+# head: 1x1 conv over cat(up2x(low), skip) through zero-stride TMA dimensions
+low = torch.randn(B, 128, 128, 128, device=dev, generator=g).to(torch.bfloat16)
+skip = torch.randn(B, 256, 256, 256, device=dev, generator=g).to(torch.bfloat16)
+for _ in range(reps):
+    ops.upcat_conv1x1(ops.UpCat(low.permute(0, 3, 1, 2), skip.permute(0, 3, 1, 2)), w(128, 384), bias(128), "silu")
+del low, skip
 img = torch.rand(B, 4, 1024, 1024, device=dev, generator=g).to(torch.bfloat16)
 cw, cb = 0.3 * torch.randn(4, 48, 16, device=dev, generator=g), 0.1 * torch.randn(4, 48, device=dev, generator=g)
 for _ in range(reps):
