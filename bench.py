@@ -212,7 +212,7 @@ def run_sodt(args):
     with ClockSampler(local_rank) as clk:
         ms = timed(step_device, steps)
     launches = ops.launch_count()
-    if det.cuda_graph:      # the step is replayed from a CUDA graph: kernels in the captured step x replays (+ eager launches, if any)
+    if det.cuda_graph:      # (False if the capture failed and the detector fell back to eager launches: then they were counted above)      # the step is replayed from a CUDA graph: kernels in the captured step x replays (+ eager launches, if any)
         launches += det.launches_per_step(*devin[0]) * steps
     clocks = clk.summary()
     value = world * B * steps / (ms / 1e3)

@@ -128,8 +128,8 @@ class Detector:
         return entry
 
     def launches_per_step(self, rgb_u8, ir_u8):
-        """sodt kernels one step launches (counted while the step's CUDA graph was captured)."""
-        return self._graph_for(rgb_u8, ir_u8)[4]
+        """sodt kernels one step launches (counted while the step's CUDA graph was captured; 0 if graphs are off)."""
+        return self._graph_for(rgb_u8, ir_u8)[4] if self.cuda_graph else 0
 
     @torch.no_grad()
     def detect_device(self, rgb_u8, ir_u8, buf=None):
@@ -137,7 +137,14 @@ class Detector:
         is reused by the next call with the same batch size."""
         if (self.cuda_graph and rgb_u8.dtype == torch.uint8 and ir_u8.dtype == torch.uint8 and not ops.kernel_timing_enabled()
                 and not torch.cuda.is_current_stream_capturing()):
-            graph, srgb, sir, gbuf, _ = self._graph_for(rgb_u8, ir_u8)
+            try:
+                graph, srgb, sir, gbuf, _ = self._graph_for(rgb_u8, ir_u8)
+            except RuntimeError as e:       # capture not possible here (still the CUDA path: every kernel is launched eagerly)
+                import warnings
+                warnings.warn(f"CUDA graph capture failed ({e}); launching the step eagerly")
+                self.cuda_graph = False
+                torch.cuda.synchronize(self.device)
+                return self._detect_eager(rgb_u8, ir_u8, buf or self.buffer(rgb_u8.shape[0]))
             srgb.copy_(rgb_u8)
             sir.copy_(ir_u8)
             graph.replay()
