@@ -156,7 +156,7 @@ class Mlp(nn.Module):
         w1, b1, fold = self.fc1.weight, self.fc1.bias, None
         if ln is not None:
             norm, stats = ln
-            fold = (stats, norm.weight, norm.bias)
+            fold = (stats, norm.weight, norm.bias, norm.eps)
         if self.linear:
             if exact_gelu and x.is_cuda:
                 return ops.linear(x, w1, b1, act="gelu", ln=fold)    # GELU fused into the GEMM epilogue (bf16)
@@ -278,13 +278,15 @@ class SwinTransformerBlock(nn.Module):
         if x.dtype == torch.bfloat16 and ops.USE_TC_LINEAR and ops.linear_ln_supported(x, C):
             # bf16, LayerNorms folded: qkv and fc1 read the raw residual stream and normalise in their epilogues from the row
             # statistics that the proj / fc2 GEMM (or the producer of x) emitted with its result
-            mr = ops.finalize_stats(stats, C, self.norm1.eps) if stats is not None else ops.row_stats(x, self.norm1.eps)
-            qkv = ops.linear(x, attn.qkv.weight, attn.qkv.bias, ln=(mr, self.norm1.weight, self.norm1.bias))
+            # row statistics: up to 3 partial pairs per row go to the GEMM as they are, more are reduced by a small kernel first
+            prep = lambda st, eps: st if st.shape[0] <= 3 else ops.finalize_stats(st, C, eps)
+            mr = prep(stats, self.norm1.eps) if stats is not None else ops.row_stats(x, self.norm1.eps)
+            qkv = ops.linear(x, attn.qkv.weight, attn.qkv.bias, ln=(mr, self.norm1.weight, self.norm1.bias, self.norm1.eps))
             o = ops.window_attention(qkv.view(B, H, W, 3 * C), attn.relative_position_bias_table, attn.num_heads,
                                      self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
                                      mask_value=MASK_VALUE)
             x, st = ops.linear(o.view(B, L, C), attn.proj.weight, attn.proj.bias, residual=x, want_stats=True)
-            h = mlp.hidden(x, H, W, ln=(self.norm2, ops.finalize_stats(st, C, self.norm2.eps)))
+            h = mlp.hidden(x, H, W, ln=(self.norm2, prep(st, self.norm2.eps)))
             if want_stats:
                 return ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x, want_stats=True)
             return ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x)

@@ -59,17 +59,17 @@ extern "C" int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, i
     return linear_tc(g, x2, ldx2, k_split, sm_count(), static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, const float* ln_colsum,
+extern "C" int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, int ln_boxes, float ln_eps, const float* ln_colsum,
                                   const void* w, const float* bias, const void* residual, int ldr, int res_rows, void* out, int ldo,
                                   float* stats_out, int M, int N, int K, int act, int dtype, void* stream) {
     using namespace sodt;
     if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0 || act < 0 || act > 2) return SODT_ERR_INVALID_ARG;
-    if ((ln_mean_rstd && !ln_colsum) || res_rows < 0) return SODT_ERR_INVALID_ARG;
+    if ((ln_mean_rstd && !ln_colsum) || res_rows < 0 || ln_boxes < 0 || ln_boxes > 3 || ln_eps < 0.f) return SODT_ERR_INVALID_ARG;
     if (dtype != SODT_BF16 || !linear_tc_supported(M, N, K)) return SODT_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)) ||
         (ln_colsum && !aligned16(ln_colsum)) || (reinterpret_cast<uintptr_t>(ln_mean_rstd) & 7) || (reinterpret_cast<uintptr_t>(stats_out) & 7))
         return SODT_ERR_ALIGNMENT;
-    LinearTcArgs g{x, ldx, w, bias, residual, ldr, res_rows, out, ldo, M, N, K, act, ln_mean_rstd, ln_colsum, stats_out};
+    LinearTcArgs g{x, ldx, w, bias, residual, ldr, res_rows, out, ldo, M, N, K, act, ln_mean_rstd, ln_colsum, stats_out, ln_boxes, ln_eps};
     return linear_tc(g, nullptr, 0, 0, sm_count(), static_cast<cudaStream_t>(stream));
 }
 

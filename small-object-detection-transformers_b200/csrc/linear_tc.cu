@@ -51,6 +51,8 @@ struct Epilogue {
     const float* ln_colsum;
     float* stats_out;
     int M, has_residual, act, res_tiles;
+    int ln_boxes;               // > 0: ln_stats holds partial (sum, sum of squares) pairs, [ln_boxes][M][2]
+    float ln_inv_k, ln_eps;
 };
 
 struct Addressing {
@@ -241,7 +243,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 int mt_, nt_;
                 tile_at(i, mt_, nt_);
                 const int gr = mt_ * BM + row_in_tile;
-                if (gr < ep.M) r = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + gr);
+                if (gr < ep.M) {
+                    if (ep.ln_boxes == 0) {
+                        r = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + gr);
+                    } else {        // up to three partial (sum, sum of squares) pairs from the GEMM that wrote the row: no finalize pass
+                        const float2* p = reinterpret_cast<const float2*>(ep.ln_stats) + gr;
+                        const float2 p0 = __ldg(p);
+                        const float2 p1 = ep.ln_boxes > 1 ? __ldg(p + ep.M) : make_float2(0.f, 0.f);
+                        const float2 p2 = ep.ln_boxes > 2 ? __ldg(p + 2 * (size_t)ep.M) : make_float2(0.f, 0.f);
+                        const float mean = (p0.x + p1.x + p2.x) * ep.ln_inv_k;
+                        r = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, (p0.y + p1.y + p2.y) * ep.ln_inv_k), 0.f) + ep.ln_eps));
+                    }
+                }
             }
             return r;
         };
@@ -401,6 +414,7 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     ep.bias = g.bias; ep.ln_stats = g.ln_stats; ep.ln_colsum = g.ln_colsum; ep.stats_out = g.stats_out;
     ep.M = g.M; ep.has_residual = g.residual != nullptr ? 1 : 0; ep.act = g.act;
     ep.res_tiles = (res_rows + BM - 1) / BM;
+    ep.ln_boxes = g.ln_boxes; ep.ln_inv_k = 1.f / (float)g.K; ep.ln_eps = g.ln_eps;
     kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, ep, ad, g.K, num_n_tiles, num_m_tiles, stages);
     return check_launch();
 }
@@ -454,7 +468,7 @@ bool linear_tc_supported(int M, int N, int K) { return M > 0 && K % BK == 0 && K
 
 int linear_tc(const LinearTcArgs& g, const void* x2, int ldx2, int k_split, int num_sms, cudaStream_t stream) {
     if (!linear_tc_supported(g.M, g.N, g.K)) return SODT_ERR_UNSUPPORTED;
-    if (g.ln_stats && (!g.ln_colsum || x2 != nullptr)) return SODT_ERR_INVALID_ARG;
+    if (g.ln_stats && (!g.ln_colsum || x2 != nullptr || g.ln_boxes < 0 || g.ln_boxes > 3)) return SODT_ERR_INVALID_ARG;
     if (g.residual && g.res_rows > 0 && g.res_rows != g.M && (g.res_rows % BM || g.M % g.res_rows)) return SODT_ERR_INVALID_ARG;
     if (g.ldx % 8 || g.ldo % 8 || (g.residual && g.ldr % 8) || g.ldx < (x2 ? k_split : g.K) || g.ldo < g.N) return SODT_ERR_INVALID_ARG;
     Addressing ad{};

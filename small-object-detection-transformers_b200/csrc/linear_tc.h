@@ -18,10 +18,12 @@ struct LinearTcArgs {
     int act;                // 0 identity, 1 GELU, 2 SiLU
     // LayerNorm folded into the GEMM (optional): A holds the raw rows, w the weights pre-multiplied by the LayerNorm gain,
     // bias = bias + w . ln_bias; the epilogue applies out = rstd (acc - mean colsum[n]) + bias[n] per row.
-    const float* ln_stats;  // [M][2] (mean, rstd) of every A row, or null
+    const float* ln_stats;  // [M][2] (mean, rstd) of every A row, or (ln_boxes > 0) [ln_boxes][M][2] partial (sum, sum of squares); or null
     const float* ln_colsum; // fp32 [N]: sum over k of the (bf16) folded weights
     // optional: partial (sum, sum of squares) of the bf16 OUTPUT rows per 64-column box, [N/64][M][2]
     float* stats_out;
+    int ln_boxes;           // 0, or 1..3: ln_stats holds that many partial pairs per row, reduced in the epilogue with ln_eps
+    float ln_eps;
 };
 
 bool linear_tc_supported(int M, int N, int K);

@@ -382,8 +382,9 @@ def linear_ln_supported(x, n_out):
 
 def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=None, want_stats=False):
     """act(cat(x, x2) @ weight.T + bias) (+ residual) over the last dim.
-    ``ln=(mean_rstd, ln_weight, ln_bias)``: computes ``Linear(LayerNorm(x))`` from the raw rows ``x`` and their statistics
-    ``mean_rstd`` [M, 2] (row_stats / finalize_stats); the LayerNorm is folded into the weights (cached) and the epilogue.
+    ``ln=(stats, ln_weight, ln_bias[, eps])``: computes ``Linear(LayerNorm(x))`` from the raw rows ``x`` and their statistics:
+    ``stats`` = [M, 2] (mean, rstd) from row_stats / finalize_stats, or the [boxes <= 3, M, 2] partial sums a ``want_stats``
+    GEMM emitted (reduced in the epilogue with ``eps``); the LayerNorm is folded into the weights (cached) and the epilogue.
     ``want_stats``: also return the [N/64, M, 2] partial (sum, sum of squares) of the result rows -> (out, partials).
     Both need a shape for which linear_ln_supported() holds.  bf16 shapes the tcgen05 kernel supports run there with the
     activation / residual fused into the epilogue; ``x``, ``x2``, ``residual`` and ``out`` may be column slices of wider
@@ -421,16 +422,22 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
                 raise ValueError("out must be a bf16 row-strided view with M*N elements")
         if (ln is not None or want_stats) and x2 is not None:
             raise ValueError("ln / want_stats cannot be combined with x2")
-        mr, ln_w, ln_b = ln if ln is not None else (None, None, None)
-        if mr is not None and (mr.dtype != torch.float32 or not mr.is_contiguous() or tuple(mr.shape) != (M, 2)):
-            raise ValueError("ln mean_rstd must be contiguous fp32 [M, 2]")
+        mr, ln_w, ln_b, ln_eps = (tuple(ln) + (1e-5,))[:4] if ln is not None else (None, None, None, 0.0)
+        ln_boxes = 0
+        if mr is not None:
+            if mr.dtype != torch.float32 or not mr.is_contiguous() or tuple(mr.shape[-2:]) != (M, 2) or mr.dim() > 3:
+                raise ValueError("ln statistics must be contiguous fp32 [M, 2] or [boxes, M, 2]")
+            if mr.dim() == 3:
+                ln_boxes = mr.shape[0]
+                if ln_boxes > 3:
+                    raise ValueError("more than 3 partial pairs per row: reduce them with finalize_stats first")
         stats_out = torch.empty((N // 64, M, 2), dtype=torch.float32, device=x.device) if want_stats else None
         label = f"linear[M={M},N={N},K={K},act={act},res={residual is not None},ln={ln is not None},stats={want_stats}]"
         if ln is not None or want_stats:
             w, colsum, b32 = (fold_layernorm(weight, bias, ln_w, ln_b) if ln is not None
                               else (weight.detach().contiguous(), None, _as_f32(bias)))
             with torch.cuda.device(x.device), _Timed(label):
-                st = _capi.lib().sodt_linear_ln_fwd(xa.data_ptr(), ldx, _ptr(mr), _ptr(colsum), w.data_ptr(), _ptr(b32),
+                st = _capi.lib().sodt_linear_ln_fwd(xa.data_ptr(), ldx, _ptr(mr), ln_boxes, float(ln_eps), _ptr(colsum), w.data_ptr(), _ptr(b32),
                                                     _ptr(res), ldr, res_rows, out.data_ptr(), ldo, _ptr(stats_out), M, N, K,
                                                     _LIN_ACT[act], 1, _stream())
             _capi.check(st, "sodt_linear_ln_fwd")
