@@ -222,9 +222,19 @@ class WindowAttention(nn.Module):
     def forward(self, x, mask=None):
         """Reference signature: x [num_windows*B, N, C] already partitioned (backbone_vit.py:961)."""
         if mask is not None:
-            raise NotImplementedError(
-                "explicit mask tensors are not taken: SwinTransformerBlock passes the shift to the kernel, "
-                "which evaluates the shifted-window mask in closed form")
+            # An explicit mask [nW, N, N] (reference backbone_vit.py:979-984).  Inside the detector this never happens:
+            # SwinTransformerBlock passes the shift to the kernel, which evaluates the shifted-window mask in closed form.
+            # Standalone callers get the reference's arithmetic as library math (fp32 scores and softmax) on x's device.
+            B_, N, C = x.shape
+            h = self.num_heads
+            qkv = self.qkv(x).reshape(B_, N, 3, h, C // h).permute(2, 0, 3, 1, 4).float()
+            attn = (qkv[0] * self.scale) @ qkv[1].transpose(-2, -1)
+            bias = self.relative_position_bias_table[self.relative_position_index.view(-1)].view(N, N, h).permute(2, 0, 1)
+            attn = attn + bias.float().unsqueeze(0)
+            nW = mask.shape[0]
+            attn = (attn.view(B_ // nW, nW, h, N, N) + mask.float()[None, :, None]).view(B_, h, N, N)
+            o = (torch.softmax(attn, dim=-1) @ qkv[2]).transpose(1, 2).reshape(B_, N, C).to(x.dtype)
+            return self.proj(o)
         wh, ww = self.window_size
         if wh != ww:
             raise NotImplementedError("square windows only")
@@ -330,6 +340,22 @@ class CAttention(nn.Module):
         super().__init__()
         self.embedding_dim = embedding_dim
         self.num_heads = num_heads
+
+    def forward(self, q, k, v, dimensions=None, mask=None):
+        """q, k, v [B_, N, C] (+ mask [nW, N, N]) -> [B_, N, C] with the reference's order of operations (scores, + mask
+        BEFORE scaling, / sqrt(C / heads), softmax; backbone_vit.py:589-616).  Standalone use only: inside the detector
+        CAttentionBlock runs the four cross attentions and their LayerNorms in one kernel, this method is library math in
+        fp32 on the tensors' device."""
+        B_, N, C = q.shape
+        h = self.num_heads
+        c = C // h
+        split = lambda t: t.float().reshape(B_, N, h, c).transpose(1, 2)
+        s = split(q) @ split(k).transpose(-1, -2)
+        if mask is not None:
+            nW = mask.shape[0]
+            s = (s.reshape(B_ // nW, nW, h, N, N) + mask.float()[None, :, None]).reshape(B_, h, N, N)
+        o = torch.softmax(s / math.sqrt(c), dim=-1) @ split(v)
+        return o.transpose(1, 2).reshape(B_, N, C).to(q.dtype)
 
 
 class CAttentionBlock(nn.Module):

@@ -106,3 +106,32 @@ def test_forward_without_cuda_fails_loudly():
     blk = bv.SwinTransformerBlock(48, (8, 8), 3, window_size=8).eval()
     with pytest.raises(_capi.SodtError):
         blk(torch.randn(1, 64, 48))
+
+
+def test_cattention_module_forward_matches_reference_golden(golden):
+    """CAttention.forward(q, k, v, dimensions, mask) (reference backbone_vit.py:589-616) as a standalone module: host-side
+    library math with the reference's order of operations, checked against the reference's own output (masked case)."""
+    from oracle import fixtures as fx
+    q, k, v = (fx.det_input(f"cattn:masked:{i}", (2 * 4, 16, 48)) for i in range(3))
+    mask = A.shift_attn_mask(8, 8, 4, 2)
+    y = bv.CAttention(48, 12)(q, k, v, (8, 8), mask)
+    ref = torch.as_tensor(golden("cattn")["masked/y"])
+    assert y.shape == ref.shape and ((y.double() - ref.double()).norm() / ref.double().norm()).item() < 2e-6
+    assert torch.equal(bv.CAttention(48, 12)(q[:, :1], k[:, :1], v[:, :1]), v[:, :1])      # one token per window: returns v
+
+
+def test_window_attention_module_with_explicit_mask_matches_oracle():
+    """WindowAttention.forward(x, mask) with a dense mask tensor (reference backbone_vit.py:961-990): library math with the
+    reference's arithmetic; the detector itself never takes this path (the kernel evaluates the shift mask in closed form)."""
+    torch.manual_seed(0)
+    m = bv.WindowAttention(48, (4, 4), 12).double()
+    with torch.no_grad():
+        m.relative_position_bias_table.normal_(0.0, 0.5)
+    x = torch.randn(2 * 4, 16, 48, dtype=torch.double)
+    mask = A.shift_attn_mask(8, 8, 4, 2).double()
+    with torch.no_grad():
+        y = m(x, mask)
+        qkv = m.qkv(x).reshape(8, 16, 3, 12, 4).permute(2, 0, 3, 1, 4)               # [3, B_, heads, N, hd]
+        core = A.window_attention_core(qkv[0], qkv[1], qkv[2], m.relative_position_bias_table, 4, 4, m.scale, mask)
+        ref = m.proj(core.transpose(1, 2).reshape(8, 16, 48))
+    assert ((y - ref).norm() / ref.norm()).item() < 1e-10
