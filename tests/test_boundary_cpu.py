@@ -134,4 +134,4 @@ def test_window_attention_module_with_explicit_mask_matches_oracle():
         qkv = m.qkv(x).reshape(8, 16, 3, 12, 4).permute(2, 0, 3, 1, 4)               # [3, B_, heads, N, hd]
         core = A.window_attention_core(qkv[0], qkv[1], qkv[2], m.relative_position_bias_table, 4, 4, m.scale, mask)
         ref = m.proj(core.transpose(1, 2).reshape(8, 16, 48))
-    assert ((y - ref).norm() / ref.norm()).item() < 1e-10
+    assert ((y - ref).norm() / ref.norm()).item() < 1e-6          # the module computes scores and softmax in fp32
