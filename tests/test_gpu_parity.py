@@ -129,6 +129,26 @@ def test_window_attention_full_size_properties(dtype):
     assert rel_err(o0[:1, 40:48, 80:88], ref) < TOL[dtype]
 
 
+@pytest.mark.parametrize("H,C,ws,shift", [(512, 192, 8, 0), (512, 192, 8, 2), (512, 192, 8, 4), (128, 384, 8, 2), (64, 768, 32, 0)])
+def test_window_attention_microbench_geometries(H, C, ws, shift):
+    """The window-attention microbenchmark geometries of SURVEY.md section 8(d) C3 (2048^2 px at stride 4: 512^2 tokens, C=192;
+    128^2 tokens with C=384; the stage-3 geometry N=1024, head_dim 64), bf16, batch 1: interior windows are independent crops
+    of the image shifted by `shift`, so sampled windows are checked against the oracle; constant-v gives the row-sum check."""
+    heads, B = 12, 1
+    g = torch.Generator(device="cuda").manual_seed(3)
+    qkv = torch.randn(B, H, H, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
+    table = 0.5 * torch.randn((2 * ws - 1) ** 2, heads, device="cuda", generator=g)
+    out = ops().window_attention(qkv, table, heads, ws, shift)
+    for wy, wx in ((0, 0), (3 % (H // ws - 1), 5 % (H // ws - 1)), (H // ws - 2, H // ws - 2)):      # never the last (masked) row / column
+        y0, x0 = wy * ws + shift, wx * ws + shift
+        crop = qkv[:1, y0:y0 + ws, x0:x0 + ws].float().cpu()
+        ref = A.attention_on_qkv_image(crop, table.cpu(), heads, ws, 0)
+        assert rel_err(out[:1, y0:y0 + ws, x0:x0 + ws], ref) < TOL[torch.bfloat16], (wy, wx)
+    q1 = qkv.clone()
+    q1[..., 2 * C:] = -1.25
+    assert (ops().window_attention(q1, table, heads, ws, shift).float() + 1.25).abs().max() < 1.6e-2
+
+
 # ------------------------------------------------------------------------------------ fused Linear
 @pytest.mark.parametrize("M,N,K,act,res", [(1000, 576, 192, None, False), (777, 768, 192, "gelu", False), (4096, 192, 768, None, True),
                                            (300, 192, 192, None, True), (129, 1152, 384, None, False), (2048, 1536, 384, "gelu", False),
