@@ -1,10 +1,11 @@
 """Host-side mirror of the reference backbone (basics/models/backbone_vit.py) for the hot path.
 
 Same class names, constructor arguments, parameter / buffer names and shapes as the reference,
-so its state_dicts and pickled checkpoints resolve here.  The attention math does not run in
-torch: ``SwinTransformerBlock`` and ``CAttentionBlock`` call the sm_100a kernels through the
-C ABI (``ops.window_attention`` / ``ops.cattn_block``); LayerNorm, the Linear / conv GEMMs and
-GELU around them stay torch library calls (cuBLAS / cuDNN), as scoped in SURVEY.md section 8a.
+so its state_dicts and pickled checkpoints resolve here.  The math does not run in torch: in bf16
+every layer of the backbone calls the sm_100a kernels through the C ABI (``ops.window_attention``,
+``ops.linear`` with LayerNorm / GELU / residual folded into the GEMM, ``ops.conv2d_nhwc`` for the
+conv-MLP's taps, ``ops.patch_merge_linear``, ``ops.frontend_u8``); fp32 (the 1e-5 exactness mode) uses
+the exact attention / LayerNorm / front-end kernels with cuBLAS / cuDNN for the GEMMs and convs.
 
 Differences from the reference, all deliberate:
   * the token grid follows the input instead of the hard-coded 128x128
@@ -130,7 +131,7 @@ class PatchMerging(nn.Module):
 
 class Mlp(nn.Module):
     """Linear MLP, or the conv-enhanced variant fc1 -> 2x2 conv -> GELU -> fc2
-    (reference backbone_vit.py:863).  Not part of the attention hot path: torch library calls."""
+    (reference backbone_vit.py:863).  bf16: tcgen05 GEMMs (the 2x2 conv as a tap GEMM with TMA-addressed taps)."""
 
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, linear_mlp=True, drop=0.):
         super().__init__()

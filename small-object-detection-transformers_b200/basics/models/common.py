@@ -1,7 +1,8 @@
 """YOLOv5 head modules used by models/model.yaml (reference basics/models/common.py).
 
-Only the conv stack the detector's head needs; these are cuDNN library calls and are not
-part of the attention hot path.  Module / parameter names follow the
+Only the conv stack the detector's head needs (SURVEY.md section 8a lists it as a caller of the hot path, 8f as "next").
+After Model.fuse() the bf16 convs run as tap GEMMs on the tcgen05 kernel with bias + SiLU in the epilogue
+(ops.conv2d_nhwc, ops.upcat_conv1x1); otherwise they are cuDNN calls.  Module / parameter names follow the
 reference so that state_dict keys (detect.N.cv1.conv.weight ...) match.
 """
 import math

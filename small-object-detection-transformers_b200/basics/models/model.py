@@ -2,8 +2,8 @@
 (reference basics/models/model.py).  The yaml schema ([from, number, module, args] rows,
 depth / width multiples, anchors) and the resulting state_dict keys are unchanged.
 
-Detect's decode runs in one sm_100a kernel (ops.detect_decode); the backbone's attention runs in
-the window / cross-channel kernels (see backbone_vit.py); everything else is torch library code.
+Detect's 1x1 conv and decode run in sm_100a kernels (ops.conv2d_nhwc, ops.detect_decode); the backbone and the head
+call the kernels described in backbone_vit.py / common.py; nn.Upsample + Concat are folded into the next C3 (ops.UpCat).
 """
 import logging
 import math
