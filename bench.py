@@ -66,7 +66,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """Keep only the samples that arrived inside [t0, t1] (the sampler is started early: nvidia-smi takes ~0.3 s to
+        deliver its first line, longer than a short timed region)."""
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        self.rows = inside if inside else self.rows[-1:]
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -80,7 +86,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        for _, r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -206,11 +212,14 @@ def run_sodt(args):
         return ms
 
     # ---- kernel-only arm: inputs resident in HBM
-    for i in range(warmup):
-        step_device(i)
-    ops.reset_launch_count()
     with ClockSampler(local_rank) as clk:
+        for i in range(warmup):
+            step_device(i)
+        torch.cuda.synchronize()
+        ops.reset_launch_count()
+        t_begin = time.perf_counter()
         ms = timed(step_device, steps)
+        clk.window(t_begin, time.perf_counter())
     launches = ops.launch_count()
     if det.cuda_graph:      # (False if the capture failed and the detector fell back to eager launches: then they were counted above)      # the step is replayed from a CUDA graph: kernels in the captured step x replays (+ eager launches, if any)
         launches += det.launches_per_step(*devin[0]) * steps
