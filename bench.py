@@ -25,7 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "images/sec SRyolo_MF fwd RGB+IR 1024^2"
+METRIC = "images/sec SRyolo_MF fwd RGB+IR 1024\u00b2 at 1/2/4/8 B200; attn tensor-pipe %"      # BASELINE.json's metric, verbatim
+try:
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+except (OSError, ValueError, KeyError):
+    pass
 IMG = 1024
 PER_GPU_BATCH = 32
 
@@ -246,9 +250,10 @@ def run_sodt(args):
     C1 = 192
     esize = 2 if dtype == torch.bfloat16 else 4
     stage1 = [v for k, v in per_kernel.items() if k.startswith("window_attn[") and f"C={C1}," in k]
-    traffic = None
-    try:      # DRAM bytes of one stage-1 launch from the committed ncu --set full capture (tools/make_profiles.py)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))["traffic_bytes"]
+    traffic, attn_tensor_pct = None, None
+    try:      # DRAM bytes of one stage-1 launch and the attention kernels' tensor-pipe % from the committed ncu --set full capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))
+        traffic, attn_tensor_pct = prof["traffic_bytes"], prof.get("attention_tensor_pipe_pct")
     except (OSError, ValueError, KeyError):
         pass
     if stage1:
@@ -306,6 +311,7 @@ def run_sodt(args):
                     "ms_per_step": ms_e2e / steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "attn_tensor_pipe_pct": attn_tensor_pct,      # the second half of BASELINE's metric: from profiles/ (ncu), not measured live
             "kernel_shares": shares,
             "cpu_baseline": cpu_baseline,
         }

@@ -59,6 +59,7 @@ lines = [f"# ncu --set full, one launch per kernel ({os.path.basename(rep)}; B =
          "| kernel | " + " | ".join(f"{n} [{units[col[c]]}]" if units[col[c]] else n for c, n in cols) + " | stalls |",
          "|---|" + "---|" * (len(cols) + 1)]
 traffic = None
+tensor_pct = {}
 for r in data:
     name = r[col["Kernel Name"]].replace("void ", "").replace("sodt::<unnamed>::", "").split("(")[0]
     cells = []
@@ -70,6 +71,9 @@ for r in data:
     tot = sum(v for v, _ in st) or 1.0
     stalls = ", ".join(f"{n} {100 * v / tot:.0f}%" for v, n in st[:5])
     lines.append(f"| `{name[:60]}` | " + " | ".join(cells) + f" | {stalls} |")
+    tp = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
+    if tp in col and ("window_attn" in name or "cattn" in name) and "prep" not in name:
+        tensor_pct.setdefault(name.split("::")[-1], num(r[col[tp]]))
     if traffic is None and "window_attn_win8_kernel<16>" in name:
         rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
         wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
@@ -78,6 +82,7 @@ for r in data:
                    "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}, first stage-1 launch (B=32, 256x256 tokens, C=192)"}
 open(os.path.join(out_dir, f"{rnd}_kernels_ncu.md"), "w").write("\n".join(lines) + "\n")
 if traffic:
+    traffic["attention_tensor_pipe_pct"] = tensor_pct       # BASELINE.json's "attn tensor-pipe %" (sm__pipe_tensor_cycles_active)
     json.dump(traffic, open(os.path.join(out_dir, f"{rnd}_roofline_traffic.json"), "w"), indent=1)
 shutil.copy(launches, os.path.join(out_dir, f"{rnd}_bench_launches.csv"))
 summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), launches], capture_output=True, text=True).stdout
