@@ -84,10 +84,20 @@ open(os.path.join(out_dir, f"{rnd}_kernels_ncu.md"), "w").write("\n".join(lines)
 if traffic:
     traffic["attention_tensor_pipe_pct"] = tensor_pct       # BASELINE.json's "attn tensor-pipe %" (sm__pipe_tensor_cycles_active)
     json.dump(traffic, open(os.path.join(out_dir, f"{rnd}_roofline_traffic.json"), "w"), indent=1)
-shutil.copy(launches, os.path.join(out_dir, f"{rnd}_bench_launches.csv"))
+# trim the launch list to whole steps: from the first front-end launch to the last one (exclusive)
+lrows = open(launches).read().splitlines()
+hi = next(i for i, l in enumerate(lrows) if l.startswith('"ID"'))
+body = lrows[hi + 1:]
+fe = [i for i, l in enumerate(body) if "frontend_kernel" in l]
+if len(fe) >= 2:
+    body = body[fe[0]:fe[-1]]
+launches_trimmed = os.path.join(out_dir, f"{rnd}_bench_launches.csv")
+open(launches_trimmed, "w").write("\n".join(lrows[:hi + 1] + body) + "\n")
+n_steps = max(1, len(fe) - 1)
+launches = launches_trimmed
 summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"), launches], capture_output=True, text=True).stdout
 open(os.path.join(out_dir, f"{rnd}_bench_launches_summary.md"), "w").write(
-    "# Kernel launches of two eager bench steps (`bench.py --steps 2 --warmup 3 --no-graph` under "
+    f"# Kernel launches of {n_steps} eager bench step(s), trimmed to whole steps (`bench.py --steps 2 --warmup 3 --no-graph` under "
     "`ncu --metrics gpu__time_duration.sum --clock-control none`)\n\nPer-launch times are cold-cache and serialised: compare shares.\n\n" + summ)
 print("\n".join(lines[:3]))
 print(traffic)
