@@ -173,6 +173,7 @@ def run_sodt(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version / debug lines must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
