@@ -158,6 +158,12 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------- GPU arm
 def run_sodt(args):
+    # stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 (NCCL prints its version banner there)
+    # is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -173,7 +179,6 @@ def run_sodt(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version / debug lines must not precede the JSON line on stdout
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -316,7 +321,8 @@ def run_sodt(args):
             "kernel_shares": shares,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
