@@ -161,6 +161,8 @@ class Mlp(nn.Module):
         if self.linear:
             if exact_gelu and x.is_cuda:
                 return ops.linear(x, w1, b1, act="gelu", ln=fold)    # GELU fused into the GEMM epilogue (bf16)
+            if fold is not None:                                     # any other activation: norm2 still folds into fc1
+                return self.act(ops.linear(x, w1, b1, ln=fold))
             return self.act(self.fc1(x))
         B, L, C = x.shape
         h = ops.linear(x, w1, b1, ln=fold) if x.is_cuda else self.fc1(x)

@@ -616,10 +616,34 @@ def _nms_workspace(device, B, R, nc, multi_label):
     return ws
 
 
+_class_filters = {}
+
+
+def class_filter(classes, device):
+    """The ``classes`` filter of non_max_suppression as a device int32 tensor.  A list / tuple is uploaded ONCE per
+    (values, device) and cached, so repeated calls enqueue no host-to-device copy (a pageable copy blocks the host and is
+    illegal inside CUDA-graph capture); a device int32 tensor is used as it is."""
+    if classes is None:
+        return None
+    if isinstance(classes, torch.Tensor):
+        if classes.dtype != torch.int32 or classes.device != device or not classes.is_contiguous():
+            raise ValueError("a tensor class filter must be a contiguous int32 tensor on the predictions' device")
+        return classes
+    key = (tuple(int(c) for c in classes), device.index)
+    hit = _class_filters.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise _capi.SodtError("class filter not uploaded before CUDA-graph capture: call ops.class_filter(classes, device) first")
+        hit = torch.tensor(list(key[0]), dtype=torch.int32).to(device)
+        _class_filters[key] = hit
+    return hit
+
+
 def nms(pred, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, merge=True,
         redundant=True, max_det=300, max_nms=30000, max_wh=4096.0, out=None, counts=None, want_keep_idx=False):
     """pred [B,R,5+nc] fp32 -> (out [B,max_det,6] fp32, counts [B] int32, keep_idx [B,max_det] int32 | None).
-    ``out`` / ``counts`` may be caller-provided (e.g. slices of a communication buffer)."""
+    ``out`` / ``counts`` may be caller-provided (e.g. slices of a communication buffer).  ``classes``: list / tuple of class
+    ids (uploaded once and cached, see class_filter) or a device int32 tensor."""
     _require_cuda(pred, out, counts)
     if pred.dim() != 3 or pred.shape[2] < 6 or pred.dtype != torch.float32:
         raise ValueError("pred must be fp32 [B, R, 5+nc] with nc >= 1")
@@ -634,9 +658,7 @@ def nms(pred, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, mul
     if not (out.is_contiguous() and counts.is_contiguous()) or out.dtype != torch.float32 or counts.dtype != torch.int32:
         raise ValueError("out must be contiguous fp32 [B,max_det,6] and counts contiguous int32 [B]")
     keep = torch.empty((B, max_det), dtype=torch.int32, device=dev) if want_keep_idx else None
-    cls_t = None
-    if classes is not None:
-        cls_t = torch.as_tensor(list(classes), dtype=torch.int32, device=dev)
+    cls_t = class_filter(classes, dev)
     ws = _nms_workspace(dev, B, R, nc, multi_label)
     with torch.cuda.device(dev), _Timed(f"nms[B={B},R={R},nc={nc}]"):
         st = _capi.lib().sodt_nms(pred.data_ptr(), _ptr(cls_t), 0 if cls_t is None else cls_t.numel(), out.data_ptr(),

@@ -66,22 +66,49 @@ class Detector:
                  iou_thres=0.45, multi_label=False, agnostic=False, classes=None, nc=8, seed=0, cuda_graph=True):
         self.device = torch.device(device)
         self.dtype = dtype
+        if classes is not None and self.device.type == "cuda":
+            # uploaded once: ops.nms then enqueues no host-to-device copy (none is allowed inside CUDA-graph capture)
+            classes = ops.class_filter(classes, torch.device("cuda", torch.cuda.current_device())
+                                       if self.device.index is None else self.device)
         self.nms_args = dict(conf_thres=conf_thres, iou_thres=iou_thres, multi_label=multi_label, agnostic=agnostic,
                              classes=classes)
         torch.manual_seed(seed)
         model = Model(cfg, input_mode="RGB+IR", ch_steam=3, ch=128, nc=nc)
         if state_dict is not None:
-            model.load_state_dict(state_dict, strict=False)
+            self._load_checked(model, state_dict)
         # like the reference's inference loader (models/experimental.py:118-120): fold BatchNorm into the convs
         self.model = model.eval().fuse().to(self.device, dtype)
-        for m in self.model.modules():                  # the runtime reads only the decoded predictions
-            if hasattr(m, "want_raw"):
+        for m in self.model.modules():
+            if hasattr(m, "want_raw"):                  # the runtime reads only the decoded predictions
                 m.want_raw = False
+            if hasattr(m, "anchor_grid"):               # Detect decodes in fp32: its anchors must not be rounded to bf16
+                m.anchors = m.anchors.float()
+                m.anchor_grid = m.anchor_grid.float()
         self.copy_stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
         self._bufs = {}
         # one CUDA graph per input shape: the ~1400 launches of a step are replayed with one driver call
         self.cuda_graph = bool(cuda_graph) and self.device.type == "cuda"
         self._graphs = {}
+
+    # buffers whose shape follows the token grid, not the weights: the only keys a checkpoint may lack / add
+    _GRID_KEYS = ("attn_mask", "relative_position_index", "pos_embed")
+
+    @classmethod
+    def _load_checked(cls, model, state_dict):
+        """load_state_dict that fails on any missing / unexpected key except the resolution-dependent buffers: a
+        mis-keyed checkpoint must not leave random-init weights behind silently."""
+        res = model.load_state_dict(state_dict, strict=False)
+        bad = [k for k in list(res.missing_keys) + list(res.unexpected_keys) if not k.endswith(cls._GRID_KEYS)]
+        if bad:
+            raise RuntimeError(f"checkpoint does not match the model: {len(bad)} missing / unexpected keys, e.g. {bad[:5]}")
+        return res
+
+    def load_state_dict(self, state_dict):
+        """Replaces the weights of the (fused, device-resident) model.  Captured CUDA graphs hold pointers to cached folded
+        weights, so they are dropped and re-captured on the next call."""
+        res = self._load_checked(self.model, state_dict)
+        self._graphs.clear()
+        return res
 
     def buffer(self, batch):
         if batch not in self._bufs:
