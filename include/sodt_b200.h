@@ -65,7 +65,7 @@ int sodt_built_for_sm(void);                    /* 100 (sm_100a) */
  *              used by the tensor-core kernels for a transposed, log2(e)-scaled copy of the bias table.
  * Supported: C % heads == 0, head_dim <= 64, any ws >= 1 (tokens per window unbounded).
  * Kernel selection (by shape, one code path per shape): bf16, head_dim 64, ws 32, no shift -> tcgen05
- * flash kernel; bf16, ws 8, head_dim 16 / 32, H and W multiples of 8 -> tcgen05 window-pair kernel;
+ * flash kernel; bf16, ws 8, head_dim 16 / 32, C % 64 == 0, H and W multiples of 8 -> TMA-fed tcgen05 window-pair kernel;
  * everything else (and all of SODT_F32) -> the exact fp32 CUDA-core kernel.
  */
 size_t sodt_window_attn_workspace_bytes(int C, int heads, int ws);
@@ -73,6 +73,21 @@ int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* p
                          int B, int H, int W, int C, int heads, int ws, int shift,
                          int dtype, float scale, float mask_value,
                          void* workspace, size_t workspace_bytes, void* stream);
+/*
+ * The same with the bias-table image prepared once per weight version instead of once per call (the reference gathers
+ * table[index] on every forward, backbone_vit.py:974-977): sodt_window_attn_prepare fills `workspace` for the kernel that the
+ * shape (B, H, W, C, heads, ws, shift, dtype) selects; sodt_window_attn_fwd_prepared then only reads it (same arguments, same
+ * shape).  A workspace prepared for one shape class must not be used with another.
+ */
+/* 0 = exact CUDA-core kernel (no workspace image), 1 = tcgen05 flash kernel, 2 = TMA-fed tcgen05 window-pair kernel; < 0 = error.
+ * Workspaces prepared by sodt_window_attn_prepare are interchangeable between shapes of the same class, heads and ws. */
+int sodt_window_attn_kernel_class(int B, int H, int W, int C, int heads, int ws, int shift, int dtype);
+int sodt_window_attn_prepare(const float* bias_table, int B, int H, int W, int C, int heads, int ws, int shift, int dtype,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int sodt_window_attn_fwd_prepared(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
+                                  int B, int H, int W, int C, int heads, int ws, int shift,
+                                  int dtype, float scale, float mask_value,
+                                  const void* prepared_workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Fused (residual add +) LayerNorm over the channels of token rows.

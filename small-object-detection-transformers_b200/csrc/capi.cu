@@ -13,13 +13,15 @@ int window_attn_generic(const void* qkv, const float* table, const void* pad_qkv
 
 size_t window_attn_flash_workspace(int heads, int ws);
 bool window_attn_flash_supported(int H, int W, int C, int heads, int ws, int shift, int dtype);
+int window_attn_flash_prepare(const float* table, void* workspace, int heads, int ws, cudaStream_t stream);
 int window_attn_flash(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
-                      int heads, int ws, float scale, cudaStream_t stream);
+                      int heads, int ws, float scale, bool prepared, cudaStream_t stream);
 
 size_t window_attn_win8_workspace(int heads);
 bool window_attn_win8_supported(int H, int W, int C, int heads, int ws, int shift, int dtype);
+int window_attn_win8_prepare(const float* table, void* workspace, int heads, cudaStream_t stream);
 int window_attn_win8(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
-                     int heads, int shift, float scale, float mask_value, int num_sms, cudaStream_t stream);
+                     int heads, int shift, float scale, float mask_value, int num_sms, bool prepared, cudaStream_t stream);
 
 static int sm_count() {
     int dev = 0, n = 0;
@@ -132,28 +134,68 @@ extern "C" const char* sodt_last_cuda_error(void) { return cudaGetErrorString(so
 extern "C" long long sodt_launch_count(void) { return sodt::g_launches; }
 extern "C" void sodt_reset_launch_count(void) { sodt::g_launches = 0; }
 
-extern "C" int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
-                                    int B, int H, int W, int C, int heads, int ws, int shift,
-                                    int dtype, float scale, float mask_value,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+static int window_attn_dispatch(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
+                                int B, int H, int W, int C, int heads, int ws, int shift,
+                                int dtype, float scale, float mask_value,
+                                void* workspace, size_t workspace_bytes, bool prepared, void* stream) {
     using namespace sodt;
     if (!qkv || !bias_table || !out) return SODT_ERR_INVALID_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0) return SODT_ERR_INVALID_ARG;
     if (shift < 0 || shift >= ws) return SODT_ERR_INVALID_ARG;
     if (dtype != SODT_F32 && dtype != SODT_BF16) return SODT_ERR_INVALID_ARG;
     if (!aligned16(qkv) || !aligned16(out) || (pad_qkv && !aligned16(pad_qkv))) return SODT_ERR_ALIGNMENT;
-    if (window_attn_flash_supported(H, W, C, heads, ws, shift, dtype)) {
+    if (window_attn_flash_supported(H, W, C, heads, ws, shift, dtype) && (long long)B * (H / ws) * (W / ws) <= 65535) {
         if (!workspace || !aligned16(workspace) || workspace_bytes < window_attn_flash_workspace(heads, ws))
             return SODT_ERR_WORKSPACE;
-        return window_attn_flash(qkv, bias_table, out, workspace, B, H, W, C, heads, ws, scale,
+        return window_attn_flash(qkv, bias_table, out, workspace, B, H, W, C, heads, ws, scale, prepared,
                                  static_cast<cudaStream_t>(stream));
     }
     if (window_attn_win8_supported(H, W, C, heads, ws, shift, dtype)) {
         if (!workspace || !aligned16(workspace) || workspace_bytes < window_attn_win8_workspace(heads))
             return SODT_ERR_WORKSPACE;
-        return window_attn_win8(qkv, bias_table, out, workspace, B, H, W, C, heads, shift, scale, mask_value, sm_count(),
+        return window_attn_win8(qkv, bias_table, out, workspace, B, H, W, C, heads, shift, scale, mask_value, sm_count(), prepared,
                                 static_cast<cudaStream_t>(stream));
     }
     return window_attn_generic(qkv, bias_table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value,
                                static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sodt_window_attn_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
+                                    int B, int H, int W, int C, int heads, int ws, int shift,
+                                    int dtype, float scale, float mask_value,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    return window_attn_dispatch(qkv, bias_table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value, workspace,
+                                workspace_bytes, false, stream);
+}
+
+extern "C" int sodt_window_attn_kernel_class(int B, int H, int W, int C, int heads, int ws, int shift, int dtype) {
+    using namespace sodt;
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0 || shift < 0 || shift >= ws) return SODT_ERR_INVALID_ARG;
+    if (window_attn_flash_supported(H, W, C, heads, ws, shift, dtype) && (long long)B * (H / ws) * (W / ws) <= 65535) return 1;
+    if (window_attn_win8_supported(H, W, C, heads, ws, shift, dtype)) return 2;
+    return 0;
+}
+
+extern "C" int sodt_window_attn_prepare(const float* bias_table, int B, int H, int W, int C, int heads, int ws, int shift, int dtype,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace sodt;
+    if (!bias_table || B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0 || shift < 0 || shift >= ws)
+        return SODT_ERR_INVALID_ARG;
+    if (window_attn_flash_supported(H, W, C, heads, ws, shift, dtype) && (long long)B * (H / ws) * (W / ws) <= 65535) {
+        if (!workspace || !aligned16(workspace) || workspace_bytes < window_attn_flash_workspace(heads, ws)) return SODT_ERR_WORKSPACE;
+        return window_attn_flash_prepare(bias_table, workspace, heads, ws, static_cast<cudaStream_t>(stream));
+    }
+    if (window_attn_win8_supported(H, W, C, heads, ws, shift, dtype)) {
+        if (!workspace || !aligned16(workspace) || workspace_bytes < window_attn_win8_workspace(heads)) return SODT_ERR_WORKSPACE;
+        return window_attn_win8_prepare(bias_table, workspace, heads, static_cast<cudaStream_t>(stream));
+    }
+    return SODT_OK;          // the exact kernel reads the parameter itself
+}
+
+extern "C" int sodt_window_attn_fwd_prepared(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
+                                             int B, int H, int W, int C, int heads, int ws, int shift,
+                                             int dtype, float scale, float mask_value,
+                                             const void* prepared_workspace, size_t workspace_bytes, void* stream) {
+    return window_attn_dispatch(qkv, bias_table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value,
+                                const_cast<void*>(prepared_workspace), workspace_bytes, true, stream);
 }

@@ -274,20 +274,27 @@ bool window_attn_flash_supported(int H, int W, int C, int heads, int ws, int shi
     return dtype == SODT_BF16 && shift == 0 && ws == 32 && C == heads * HD && H % ws == 0 && W % ws == 0 && C % 8 == 0;
 }
 
+int window_attn_flash_prepare(const float* table, void* workspace, int heads, int ws, cudaStream_t stream) {
+    const int entries = (2 * ws - 1) * (2 * ws - 1);
+    prep_table_kernel<<<(entries * heads + 255) / 256, 256, 0, stream>>>(table, static_cast<float*>(workspace), entries, heads);
+    return check_launch();
+}
+
 int window_attn_flash(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
-                      int heads, int ws, float scale, cudaStream_t stream) {
+                      int heads, int ws, float scale, bool prepared, cudaStream_t stream) {
     constexpr int WS = 32;
     const int entries = (2 * ws - 1) * (2 * ws - 1);
     float* table_t = static_cast<float*>(workspace);
-    prep_table_kernel<<<(entries * heads + 255) / 256, 256, 0, stream>>>(table, table_t, entries, heads);
-    int st = check_launch();
-    if (st != SODT_OK) return st;
+    if (!prepared) {
+        const int st = window_attn_flash_prepare(table, workspace, heads, ws, stream);
+        if (st != SODT_OK) return st;
+    }
     const size_t smem = SmemLayout::TAB + (size_t)entries * sizeof(float);
     auto kern = window_attn_flash_kernel<WS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const long long nwin = (long long)B * (H / ws) * (W / ws);
-    if (nwin > 65535 * 32LL) return SODT_ERR_UNSUPPORTED;
+    if (nwin > 65535) return SODT_ERR_UNSUPPORTED;      // grid.z limit; the dispatcher routes larger batches to another kernel
     dim3 grid(ws * ws / TM, heads, (unsigned)nwin);
     kern<<<grid, NTHREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), table_t,
                                            static_cast<__nv_bfloat16*>(out), H, W, C, heads, scale);

@@ -91,6 +91,9 @@ def _scratch(tag, device, nbytes):
 
 
 # ------------------------------------------------------------------------------ window attention
+CACHE_BIAS_TABLE = True     # prepare the kernels' bias-table image once per weight version (False: once per call)
+
+
 def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=None, mask_value=-100.0):
     """qkv [B,H,W,3C] (f32 / bf16) -> [B,H,W,C].  See sodt_window_attn_fwd."""
     _require_cuda(qkv, bias_table, pad_qkv)
@@ -114,11 +117,34 @@ def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=No
     out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
     if scale is None:
         scale = (C // heads) ** -0.5
-    wsp = _scratch("wattn", qkv.device, _capi.lib().sodt_window_attn_workspace_bytes(C, heads, ws))
-    with torch.cuda.device(qkv.device), _Timed(f"window_attn[B={B},H={H},W={W},C={C},heads={heads},ws={ws},shift={shift}]"):
-        st = _capi.lib().sodt_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), _ptr(pad_qkv), out.data_ptr(),
-                                              B, H, W, C, heads, ws, shift, _DT[qkv.dtype], float(scale),
-                                              float(mask_value), wsp.data_ptr(), wsp.numel(), _stream())
+    lib = _capi.lib()
+    dt = _DT[qkv.dtype]
+    kclass = lib.sodt_window_attn_kernel_class(B, H, W, C, heads, ws, shift, dt)
+    if kclass < 0:
+        _capi.check(kclass, "sodt_window_attn_kernel_class")
+    label = f"window_attn[B={B},H={H},W={W},C={C},heads={heads},ws={ws},shift={shift}]"
+    if kclass > 0 and CACHE_BIAS_TABLE:
+        # the tensor-core kernels' image of the bias table is prepared once per weight version (and kernel class), not per call
+        def prepare(t):
+            t32 = _as_f32(t)
+            buf = torch.empty(max(int(lib.sodt_window_attn_workspace_bytes(C, heads, ws)), 16), dtype=torch.uint8, device=t.device)
+            with torch.cuda.device(t.device):
+                _capi.check(lib.sodt_window_attn_prepare(t32.data_ptr(), B, H, W, C, heads, ws, shift, dt, buf.data_ptr(), buf.numel(),
+                                                         _stream()), "sodt_window_attn_prepare")
+            buf.record_stream(torch.cuda.current_stream(t.device))
+            return buf
+        wsp = cached_derived(bias_table, ("wattn_image", kclass, ws), prepare)
+        with torch.cuda.device(qkv.device), _Timed(label):
+            st = lib.sodt_window_attn_fwd_prepared(qkv.data_ptr(), table.data_ptr(), _ptr(pad_qkv), out.data_ptr(),
+                                                   B, H, W, C, heads, ws, shift, dt, float(scale),
+                                                   float(mask_value), wsp.data_ptr(), wsp.numel(), _stream())
+        _capi.check(st, "sodt_window_attn_fwd_prepared")
+        return out
+    wsp = _scratch("wattn", qkv.device, lib.sodt_window_attn_workspace_bytes(C, heads, ws))
+    with torch.cuda.device(qkv.device), _Timed(label):
+        st = lib.sodt_window_attn_fwd(qkv.data_ptr(), table.data_ptr(), _ptr(pad_qkv), out.data_ptr(),
+                                      B, H, W, C, heads, ws, shift, dt, float(scale),
+                                      float(mask_value), wsp.data_ptr(), wsp.numel(), _stream())
     _capi.check(st, "sodt_window_attn_fwd")
     return out
 
