@@ -90,6 +90,22 @@ int sodt_window_attn_fwd_prepared(const void* qkv, const float* bias_table, cons
                                   const void* prepared_workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Window attention with a non-standard score epilogue, always on the exact fp32-math kernel:
+ *   dense_mask   [mask_windows, N, N] fp32 additive mask or NULL, added after the bias; window w of image b uses entry
+ *                (b * nW + w) % mask_windows -- WindowAttention.forward(x, mask) of the reference (backbone_vit.py:979-984,
+ *                x = [num_windows * B, N, C] is the image stack [B_, ws, ws, C] of one-window images)
+ *   head_scale   [heads] fp32 or NULL: per-head multiplier of the scores instead of `scale`
+ *   normalize_qk 1: q and k are L2-normalised over head_dim (eps 1e-12) first.  head_scale + normalize_qk = the SwinV2 cosine
+ *                attention, backbone_swinv2.py:895-921, with head_scale = exp(min(logit_scale, ln 100)) and bias_table =
+ *                16 sigmoid(cpb_mlp(relative_coords_table)) evaluated once per weight version by the host.
+ */
+int sodt_window_attn_ex_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
+                            int B, int H, int W, int C, int heads, int ws, int shift,
+                            int dtype, float scale, float mask_value,
+                            const float* dense_mask, int mask_windows, const float* head_scale, int normalize_qk,
+                            void* stream);
+
+/*
  * Fused (residual add +) LayerNorm over the channels of token rows.
  * Replaces the norm1 / norm2 LayerNorms and the residual adds of SwinTransformerBlock.forward
  * (backbone_vit.py:1089-1090,1125,1128) and PatchMerging.norm (backbone_vit.py:858); eps as given, biased variance,

@@ -225,19 +225,18 @@ class WindowAttention(nn.Module):
     def forward(self, x, mask=None):
         """Reference signature: x [num_windows*B, N, C] already partitioned (backbone_vit.py:961)."""
         if mask is not None:
-            # An explicit mask [nW, N, N] (reference backbone_vit.py:979-984).  Inside the detector this never happens:
-            # SwinTransformerBlock passes the shift to the kernel, which evaluates the shifted-window mask in closed form.
-            # Standalone callers get the reference's arithmetic as library math (fp32 scores and softmax) on x's device.
+            # An explicit mask [nW, N, N] (reference backbone_vit.py:979-984): every partitioned window is a one-window image and
+            # window b_ reads mask[b_ % nW], evaluated inside the exact attention kernel (sodt_window_attn_ex_fwd).  Inside the
+            # detector this never happens: SwinTransformerBlock passes the shift to the kernel, which evaluates the
+            # shifted-window mask in closed form.
+            wh, ww = self.window_size
+            if wh != ww or not x.is_cuda:
+                raise NotImplementedError("explicit masks: square windows on CUDA tensors")
             B_, N, C = x.shape
-            h = self.num_heads
-            qkv = self.qkv(x).reshape(B_, N, 3, h, C // h).permute(2, 0, 3, 1, 4).float()
-            attn = (qkv[0] * self.scale) @ qkv[1].transpose(-2, -1)
-            bias = self.relative_position_bias_table[self.relative_position_index.view(-1)].view(N, N, h).permute(2, 0, 1)
-            attn = attn + bias.float().unsqueeze(0)
-            nW = mask.shape[0]
-            attn = (attn.view(B_ // nW, nW, h, N, N) + mask.float()[None, :, None]).view(B_, h, N, N)
-            o = (torch.softmax(attn, dim=-1) @ qkv[2]).transpose(1, 2).reshape(B_, N, C).to(x.dtype)
-            return self.proj(o)
+            qkv = self.qkv(x).view(B_, wh, ww, 3 * C)
+            o = ops.window_attention_ex(qkv, self.relative_position_bias_table, self.num_heads, wh, 0, scale=self.scale,
+                                        mask_value=MASK_VALUE, dense_mask=mask)
+            return self.proj(o.view(B_, N, C))
         wh, ww = self.window_size
         if wh != ww:
             raise NotImplementedError("square windows only")

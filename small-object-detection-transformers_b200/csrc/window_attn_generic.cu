@@ -8,6 +8,9 @@
 //
 // Reference semantics: basics/models/backbone_vit.py:971-989 (scale on q, + bias, + mask, softmax, AV),
 // :1094-1123 (roll / partition / unpartition), :1058-1079 (mask).
+// Score variants (struct ScoreExtras): an explicit dense additive mask [mask_windows, N, N] (WindowAttention.forward(x, mask),
+// backbone_vit.py:979-984); the SwinV2 cosine attention (backbone_swinv2.py:895-921): q and k L2-normalised per head
+// (F.normalize, eps 1e-12) and a per-head logit scale instead of head_dim^-0.5.
 #include "common.cuh"
 
 namespace sodt {
@@ -67,12 +70,19 @@ __device__ __forceinline__ void stage_tile(float* dst, const T* __restrict__ qkv
     }
 }
 
+struct ScoreExtras {
+    const float* dense_mask;   // [mask_windows][N][N] additive, or null; window id = (b * nW + win) % mask_windows
+    int mask_windows;
+    const float* head_scale;   // [heads] multiplier of the (normalised) scores, or null (use `scale`)
+    int normalize_qk;          // 1: q, k rows are L2-normalised over head_dim before the dot product
+};
+
 template <typename T, int HDP, bool kExact>
 __global__ void __launch_bounds__(THREADS)
 window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ table,
                            const T* __restrict__ pad_qkv, T* __restrict__ out,
                            int H, int W, int C, int heads, int hd, int ws, int shift,
-                           float scale, float mask_value, int table_in_smem, int vec_ok) {
+                           float scale, float mask_value, int table_in_smem, int vec_ok, ScoreExtras ex) {
     constexpr int LD = HDP + 4;
     constexpr int DPT = HDP / 4;  // output dims per thread
     extern __shared__ __align__(16) float smem[];
@@ -80,7 +90,8 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
     float* vs = ks + BK * LD;          // [BK][LD]
     float* ps = vs + BK * LD;          // [BQ][BK+1]
     int* kmeta = reinterpret_cast<int*>(ps + BQ * (BK + 1));  // [BK] ty | tx<<10 | region<<20
-    float* tab = reinterpret_cast<float*>(kmeta + BK);        // [(2ws-1)^2] this head's bias column
+    float* knorm = reinterpret_cast<float*>(kmeta + BK);      // [BK] 1 / |k| (cosine attention only)
+    float* tab = knorm + BK;                                  // [(2ws-1)^2] this head's bias column
 
     const WinGeom g(H, W, ws, shift);
     const int N = ws * ws;
@@ -99,8 +110,17 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
     stage_tile<T, HDP>(ks, qkv, pad_qkv, g, b, win, blockIdx.x * BQ, N, C, hd, head, 0, vec_ok != 0);
     __syncthreads();
     float q[HDP];
+    {
+        float qs = ex.head_scale != nullptr ? ex.head_scale[head] : scale;
+        if (ex.normalize_qk) {
+            float n2 = 0.f;
 #pragma unroll
-    for (int d = 0; d < HDP; ++d) q[d] = ks[i * LD + d] * scale;  // reference scales q first (:971)
+            for (int d = 0; d < HDP; ++d) n2 = fmaf(ks[i * LD + d], ks[i * LD + d], n2);
+            qs /= fmaxf(sqrtf(n2), 1e-12f);
+        }
+#pragma unroll
+        for (int d = 0; d < HDP; ++d) q[d] = ks[i * LD + d] * qs;  // reference scales q first (:971)
+    }
     int yq = 0, xq = 0;
     const bool q_real = tq < N && g.rolled(win, tq, yq, xq);
     const int tq_c = tq < N ? tq : N - 1;   // rows past the window only pad the tile; keep their bias index in range
@@ -116,6 +136,15 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
     for (int k0 = 0; k0 < N; k0 += BK) {
         stage_tile<T, HDP>(ks, qkv, pad_qkv, g, b, win, k0, N, C, hd, head, 1, vec_ok != 0);
         stage_tile<T, HDP>(vs, qkv, pad_qkv, g, b, win, k0, N, C, hd, head, 2, vec_ok != 0);
+        if (ex.normalize_qk) {
+            __syncthreads();
+            if (tid < BK) {
+                float n2 = 0.f;
+#pragma unroll
+                for (int d = 0; d < HDP; ++d) n2 = fmaf(ks[tid * LD + d], ks[tid * LD + d], n2);
+                knorm[tid] = 1.f / fmaxf(sqrtf(n2), 1e-12f);
+            }
+        }
         if (tid < BK) {
             int t = k0 + tid, yr = 0, xr = 0;
             int ty = t / ws, tx = t - ty * ws;
@@ -140,6 +169,7 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
                 acc = fmaf(q[d + 2], kv.z, acc);
                 acc = fmaf(q[d + 3], kv.w, acc);
             }
+            if (ex.normalize_qk) acc *= knorm[j];
             if (k0 + j < N) {
                 const int meta = kmeta[j];
                 const int tyk = meta & 1023, txk = (meta >> 10) & 1023, rk = meta >> 20;
@@ -147,6 +177,8 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
                 const float bias = table_in_smem ? tab[bidx] : __ldg(table + (long long)bidx * heads + head);
                 acc += bias;
                 if (rk != rq) acc += mask_value;
+                if (ex.dense_mask != nullptr)
+                    acc += __ldg(ex.dense_mask + ((long long)(blockIdx.z % ex.mask_windows) * N + tq_c) * N + (k0 + j));
             } else {
                 acc = -INFINITY;
             }
@@ -208,12 +240,12 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
 
 template <typename T, int HDP, bool kExact>
 int launch(const void* qkv, const float* table, const void* pad_qkv, void* out, int B, int H, int W, int C,
-           int heads, int hd, int ws, int shift, float scale, float mask_value, cudaStream_t stream) {
+           int heads, int hd, int ws, int shift, float scale, float mask_value, const ScoreExtras& ex, cudaStream_t stream) {
     const WinGeom g(H, W, ws, shift);
     const int N = ws * ws;
     const int span = 2 * ws - 1;
     const int table_in_smem = span * span <= MAX_TABLE_SMEM;
-    size_t smem = (size_t)(2 * BK * (HDP + 4) + BQ * (BK + 1)) * sizeof(float) + BK * sizeof(int) +
+    size_t smem = (size_t)(2 * BK * (HDP + 4) + BQ * (BK + 1)) * sizeof(float) + BK * (sizeof(int) + sizeof(float)) +
                   (table_in_smem ? (size_t)span * span * sizeof(float) : 0);
     auto kern = window_attn_generic_kernel<T, HDP, kExact>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -224,29 +256,39 @@ int launch(const void* qkv, const float* table, const void* pad_qkv, void* out, 
     dim3 grid((N + BQ - 1) / BQ, heads, (unsigned)nwin);
     kern<<<grid, THREADS, smem, stream>>>(static_cast<const T*>(qkv), table, static_cast<const T*>(pad_qkv),
                                           static_cast<T*>(out), H, W, C, heads, hd, ws, shift, scale, mask_value,
-                                          table_in_smem, vec_ok);
+                                          table_in_smem, vec_ok, ex);
     return check_launch();
 }
 
 template <typename T, bool kExact>
 int dispatch_hd(const void* qkv, const float* table, const void* pad_qkv, void* out, int B, int H, int W, int C,
-                int heads, int hd, int ws, int shift, float scale, float mask_value, cudaStream_t stream) {
-    if (hd <= 8) return launch<T, 8, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, stream);
-    if (hd <= 16) return launch<T, 16, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, stream);
-    if (hd <= 32) return launch<T, 32, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, stream);
-    return launch<T, 64, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, stream);
+                int heads, int hd, int ws, int shift, float scale, float mask_value, const ScoreExtras& ex, cudaStream_t stream) {
+    if (hd <= 8) return launch<T, 8, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
+    if (hd <= 16) return launch<T, 16, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
+    if (hd <= 32) return launch<T, 32, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
+    return launch<T, 64, kExact>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
 }
 
 }  // namespace
 
+int window_attn_generic_ex(const void* qkv, const float* table, const void* pad_qkv, void* out, int B, int H, int W,
+                           int C, int heads, int ws, int shift, int dtype, float scale, float mask_value,
+                           const float* dense_mask, int mask_windows, const float* head_scale, int normalize_qk,
+                           cudaStream_t stream) {
+    const int hd = C / heads;
+    if (hd > 64 || ws > 1023) return SODT_ERR_UNSUPPORTED;
+    if (dense_mask != nullptr && mask_windows <= 0) return SODT_ERR_INVALID_ARG;
+    const ScoreExtras ex{dense_mask, dense_mask ? mask_windows : 1, head_scale, normalize_qk ? 1 : 0};
+    if (dtype == SODT_F32)
+        return dispatch_hd<float, true>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
+    return dispatch_hd<__nv_bfloat16, false>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
+}
+
 int window_attn_generic(const void* qkv, const float* table, const void* pad_qkv, void* out, int B, int H, int W,
                         int C, int heads, int ws, int shift, int dtype, float scale, float mask_value,
                         cudaStream_t stream) {
-    const int hd = C / heads;
-    if (hd > 64 || ws > 1023) return SODT_ERR_UNSUPPORTED;
-    if (dtype == SODT_F32)
-        return dispatch_hd<float, true>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, stream);
-    return dispatch_hd<__nv_bfloat16, false>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, stream);
+    return window_attn_generic_ex(qkv, table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value, nullptr, 0, nullptr, 0,
+                                  stream);
 }
 
 }  // namespace sodt

@@ -149,6 +149,43 @@ def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=No
     return out
 
 
+def window_attention_ex(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=None, mask_value=-100.0, dense_mask=None,
+                        head_scale=None, normalize_qk=False):
+    """window_attention with a non-standard score epilogue (see sodt_window_attn_ex_fwd): an explicit dense additive mask
+    [mask_windows, N, N], a per-head score multiplier, L2-normalised q / k (SwinV2 cosine attention).  Exact fp32-math kernel."""
+    _require_cuda(qkv, bias_table, pad_qkv, dense_mask, head_scale)
+    if qkv.dim() != 4 or qkv.shape[-1] % 3 or qkv.dtype not in _DT:
+        raise ValueError("qkv must be [B, H, W, 3*C] in fp32 / bf16")
+    B, H, W, C3 = qkv.shape
+    C = C3 // 3
+    if C % heads or tuple(bias_table.shape) != ((2 * ws - 1) ** 2, heads):
+        raise ValueError("bias_table must be [(2*ws-1)^2, heads] and C divisible by heads")
+    qkv = qkv.contiguous()
+    table = _as_f32(bias_table)
+    if pad_qkv is not None:
+        pad_qkv = pad_qkv.detach().to(qkv.dtype).contiguous()
+    mask_windows = 0
+    if dense_mask is not None:
+        N = ws * ws
+        if dense_mask.dim() != 3 or tuple(dense_mask.shape[1:]) != (N, N):
+            raise ValueError(f"dense_mask must be [mask_windows, {N}, {N}]")
+        dense_mask = dense_mask.detach().to(torch.float32).contiguous()
+        mask_windows = dense_mask.shape[0]
+    if head_scale is not None:
+        head_scale = head_scale.detach().to(torch.float32).reshape(-1).contiguous()
+        if head_scale.numel() != heads:
+            raise ValueError("head_scale must have one entry per head")
+    out = torch.empty((B, H, W, C), dtype=qkv.dtype, device=qkv.device)
+    if scale is None:
+        scale = (C // heads) ** -0.5
+    with torch.cuda.device(qkv.device), _Timed(f"window_attn_ex[B={B},H={H},W={W},C={C},heads={heads},ws={ws},shift={shift}]"):
+        st = _capi.lib().sodt_window_attn_ex_fwd(qkv.data_ptr(), table.data_ptr(), _ptr(pad_qkv), out.data_ptr(), B, H, W, C, heads, ws,
+                                                 shift, _DT[qkv.dtype], float(scale), float(mask_value), _ptr(dense_mask), mask_windows,
+                                                 _ptr(head_scale), int(bool(normalize_qk)), _stream())
+    _capi.check(st, "sodt_window_attn_ex_fwd")
+    return out
+
+
 # ------------------------------------------------------------------------------------ LayerNorm
 _f32_cache = {}
 
@@ -722,6 +759,15 @@ def _register_custom_ops():
     @lib.custom_op("sodt::detect_decode", mutates_args=())
     def detect_decode_op(raw: torch.Tensor, anchors_px: torch.Tensor, stride: float) -> torch.Tensor:
         return detect_decode(raw, anchors_px, stride, want_perm=False)[0]
+
+    @lib.custom_op("sodt::nms", mutates_args=())
+    def nms_op(pred: torch.Tensor, conf_thres: float, iou_thres: float, agnostic: bool, multi_label: bool) -> tuple[torch.Tensor, torch.Tensor]:
+        out, counts, _ = nms(pred, conf_thres, iou_thres, None, agnostic, multi_label)
+        return out, counts
+
+    @nms_op.register_fake
+    def _(pred, conf_thres, iou_thres, agnostic, multi_label):
+        return pred.new_empty((pred.shape[0], 300, 6), dtype=torch.float32), pred.new_empty((pred.shape[0],), dtype=torch.int32)
 
     @detect_decode_op.register_fake
     def _(raw, anchors_px, stride):

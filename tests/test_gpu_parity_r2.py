@@ -1,0 +1,247 @@
+"""Round-2 parity tests: the BENCHMARKED configuration end to end (bf16, 1024x1024, batch 2, runtime.Detector with the
+uint8 front end and the CUDA-graph replay) against the oracle, masked border windows at full size, the cross-channel sweep
+of SURVEY.md section 8(d) C4, boundary odds and ends.  Tolerances as in tests/test_gpu_parity.py (BASELINE.json north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention_ref as A
+from oracle import fixtures as fx
+from oracle import model_ref, nms_ref
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+YAML = os.path.join(ROOT, "small-object-detection-transformers_b200", "models", "model.yaml")
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def ops():
+    from sodt_b200 import ops as o
+    return o
+
+
+def det_state_dict():
+    """Deterministic weights of the detector (pure functions of the state_dict keys), as fp32 CPU tensors."""
+    from sodt_b200.basics.models.model import Model
+    m = Model(YAML, input_mode="RGB+IR", ch_steam=3, ch=128, nc=8)
+    return fx.fill_state_dict(m.state_dict(), seed=0)
+
+
+# ------------------------------------------------------------------ the benchmarked configuration, end to end
+def test_detector_1024_bf16_graph_path_vs_oracle():
+    """BASELINE config 2 geometry (1024x1024 RGB+IR, bf16) through runtime.Detector: uint8 front end, every tcgen05 kernel at
+    its production shape (M = B * 65536 rows), the CUDA-graph replay.  Batch 2 keeps the CPU oracle to a few seconds.
+      * raw head output of the bf16 model <= 2e-2 (relative, vs the fp32 oracle on the same /255 inputs)
+      * the graph replay, the eager step and the decoded predictions are consistent with each other
+      * NMS fed the ORACLE's fp32 predictions keeps bit-identical sets to the reference restatement."""
+    from sodt_b200.runtime import Detector
+    sd = det_state_dict()
+    B, S = 2, 1024
+    g = torch.Generator().manual_seed(11)
+    rgb8 = torch.randint(0, 256, (B, 3, S, S), dtype=torch.uint8, generator=g)
+    ir8 = torch.randint(0, 256, (B, 3, S, S), dtype=torch.uint8, generator=g)
+    det = Detector(state_dict=sd, device="cuda", dtype=torch.bfloat16, conf_thres=1e-4, iou_thres=0.45, cuda_graph=True)
+    with torch.no_grad():
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        pred_ref, raw_ref = model_ref.model_forward(rgb8.float() / 255, ir8.float() / 255, sd)
+    # (1) raw head output through the production path (same kernels as the graph: frontend_u8, resident-W GEMMs, win8 / flash attention)
+    detect_layer = [m for m in det.model.modules() if hasattr(m, "want_raw")][0]
+    detect_layer.want_raw = True
+    with torch.no_grad():
+        pred, raw, _ = det.model(rgb8.cuda(), ir8.cuda(), "RGB+IR")
+    detect_layer.want_raw = False
+    assert raw[0].shape == raw_ref[0].shape
+    assert rel_err(raw[0], raw_ref[0]) < 2e-2
+    # decoded predictions: fp32 decode of the bf16 raw output; box centres within 1e-3 of the image size, sizes within bf16 error
+    got, ref = pred.double().cpu(), pred_ref.double()
+    assert (got[..., :2] - ref[..., :2]).abs().max() < 0.05 * 4            # 5 % of one stride (sigmoid of a bf16 logit)
+    assert ((got[..., 2:4] - ref[..., 2:4]).abs() / ref[..., 2:4]).max() < 0.05
+    assert (got[..., 4:] - ref[..., 4:]).abs().max() < 2e-2
+    # (2) graph replay == eager step, bit for bit, and it produces detections at this threshold
+    buf_graph = det.detect_device(rgb8.cuda(), ir8.cuda())
+    flat_graph = buf_graph.flat.clone()
+    assert det.launches_per_step(rgb8.cuda(), ir8.cuda()) > 90
+    eager = Detector(state_dict=sd, device="cuda", dtype=torch.bfloat16, conf_thres=1e-4, iou_thres=0.45, cuda_graph=False)
+    buf_eager = eager.detect_device(rgb8.cuda(), ir8.cuda())
+    assert torch.equal(flat_graph, buf_eager.flat)
+    assert int(buf_eager.counts.sum()) > 0
+    # (3) NMS on the oracle's predictions: kept sets bit-exact (both operating points of the reference's test.py / detect default)
+    pr = pred_ref.float().contiguous()
+    for kw in (dict(conf_thres=2e-4, iou_thres=0.45), dict(conf_thres=1.5e-4, iou_thres=0.6, multi_label=True)):
+        out, counts, keep = ops().nms(pr.cuda(), want_keep_idx=True, **kw)
+        want = nms_ref.non_max_suppression(pr.numpy(), kw["conf_thres"], kw["iou_thres"], multi_label=kw.get("multi_label", False))
+        for i in range(B):
+            n = int(counts[i])
+            assert n == want[i].shape[0] and n > 0, (kw, i, n, want[i].shape)
+            d = out[i, :n].cpu().numpy()
+            assert np.array_equal(d[:, 4:], want[i][:, 4:])               # scores and classes bit-exact, same order
+            assert np.abs(d[:, :4] - want[i][:, :4]).max() < 1e-3
+
+
+def test_model_512_bf16_tight_vs_reference_golden(golden):
+    """bf16 model at 512x512 against the UNMODIFIED reference's outputs at north_star's 2e-2 (features, raw head output) and
+    its decoded predictions."""
+    from sodt_b200.basics.models.model import Model
+    g = golden("model_512")
+    m = Model(YAML, input_mode="RGB+IR", ch_steam=3, ch=128, nc=8).eval()
+    m.load_state_dict(det_state_dict(), strict=False)
+    m = m.cuda().to(torch.bfloat16)
+    rgb = fx.det_input("model:rgb", (1, 3, 512, 512), kind="uniform").cuda().to(torch.bfloat16)
+    ir = fx.det_input("model:ir", (1, 3, 512, 512), kind="uniform").cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        pred, raw, feats = m(rgb, ir, "RGB+IR")
+    for i in range(3):
+        assert rel_err(feats[i][0, ::7, ::5, ::3], g[f"feat{i}_sub"]) < 2e-2, i
+    assert rel_err(raw[0][0].reshape(-1, 13)[::61], g["raw_rows"]) < 2e-2
+    ref = torch.from_numpy(g["pred_rows"]).double()
+    got = pred[0, ::61].double().cpu()
+    assert (got[:, :2] - ref[:, :2]).abs().max() < 0.05 * 4
+    assert (got[:, 4:] - ref[:, 4:]).abs().max() < 2e-2
+
+
+# ----------------------------------------------------------------------- masked border windows at full size
+@pytest.mark.parametrize("H,C,heads,shift", [(256, 192, 12, 2), (128, 384, 12, 2), (256, 192, 12, 7), (512, 192, 12, 4)])
+def test_window_attention_full_size_border_windows(H, C, heads, shift):
+    """Windows of the last window row / column of a full-size shifted grid wrap around the image and carry the shift mask.
+    A 16x16 image assembled from 16 rows / columns of the big one has the same border window (same tokens, same region
+    pattern): along a wrapped axis it takes the image's first and last 8 rows, along the other axis 16 consecutive rows from a
+    window boundary.  The oracle on that small image checks the border windows at BASELINE size."""
+    ws, B = 8, 2
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = torch.randn(B, H, H, 3 * C, device="cuda", generator=g).to(torch.bfloat16)
+    table = 0.5 * torch.randn((2 * ws - 1) ** 2, heads, device="cuda", generator=g)
+    out = ops().window_attention(qkv, table, heads, ws, shift)
+
+    def axis(kind, k):          # rows (columns) of the big image that make up the small one
+        return list(range(8)) + list(range(H - 8, H)) if kind == "last" else list(range(8 * k, 8 * k + 16))
+
+    def src(kind):              # source rows of the small image's window under test: window 1 (wraps) or window 0
+        return [(8 + t + shift) % 16 for t in range(8)] if kind == "last" else [t + shift for t in range(8)]
+
+    for k in (0, 5, H // 8 - 2):
+        for ky, kx in (("mid", "last"), ("last", "mid"), ("last", "last")):
+            R, Cm = torch.tensor(axis(ky, k)), torch.tensor(axis(kx, k))
+            small = qkv[1][R.cuda()][:, Cm.cuda()].unsqueeze(0).float().cpu()
+            ref = A.attention_on_qkv_image(small, table.cpu(), heads, ws, shift)[0]          # [16,16,C]
+            ys, xs = torch.tensor(src(ky)), torch.tensor(src(kx))
+            got = out[1][R[ys].cuda()][:, Cm[xs].cuda()]
+            assert rel_err(got, ref[ys][:, xs]) < TOL[torch.bfloat16], (k, ky, kx)
+
+
+# --------------------------------------------------------------------------------- cross-channel sweep (C4)
+C4_GRID = [(hw, C, heads, ws) for hw in (128, 256) for C in (24, 48, 96) for heads in (1, 2, 3, 4, 6, 12) for ws in (1, 2, 3, 7, 8)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("hw,C,heads,ws", C4_GRID)
+def test_cattn_block_sweep_vs_oracle(hw, C, heads, ws, dtype):
+    """(h, w) in {128^2, 256^2} x C in {24, 48, 96} x heads in {1, 2, 3, 4, 6, 12} x window in
+    {1, 2, 3, 7, 8} (3 and 7 pad the grid), fp32 and bf16.  Windows are independent without a shift, so the oracle runs on two
+    crops aligned to the window grid: the top-left corner and the bottom-right corner (which holds the padded windows)."""
+    g = torch.Generator(device="cuda").manual_seed(hw + C + heads + ws)
+    streams = [torch.randn(1, hw, hw, C, device="cuda", generator=g).to(dtype) for _ in range(4)]
+    ln_w = 1.0 + 0.1 * torch.randn(4, C, device="cuda", generator=g)
+    ln_b = 0.1 * torch.randn(4, C, device="cuda", generator=g)
+    out = ops().cattn_block(*streams, ln_w, ln_b, heads, ws=ws)
+    assert out.shape == (1, hw, hw, 4 * C)
+    n = 2 * ws
+    lo = (hw // ws - 1) * ws                      # first row / column of the last FULL-or-padded window row
+    lo = min(lo, ((hw - 1) // ws) * ws)           # with padding: start of the window that contains the last row
+    lo -= ws if lo + n > hw + ws else 0
+    for y0, x0 in ((0, 0), (lo, lo)):
+        crop = [s[:, y0:y0 + n, x0:x0 + n].float().cpu() for s in streams]
+        ref = torch.cat(A.cattention_block(crop, list(ln_w.cpu()), list(ln_b.cpu()), heads, ws, 0), -1)
+        got = out[:, y0:y0 + n, x0:x0 + n]
+        assert got.shape == ref.shape
+        assert rel_err(got, ref) < TOL[dtype], (y0, x0)
+
+
+# ----------------------------------------------------------------------------------------- boundary pieces
+def test_detector_graph_capture_with_class_filter():
+    """the class filter is uploaded once, so the step with classes=[...] captures into a CUDA graph."""
+    from sodt_b200.runtime import Detector
+    g = torch.Generator().manual_seed(2)
+    rgb = torch.randint(0, 256, (1, 3, 512, 512), dtype=torch.uint8, generator=g).cuda()
+    ir = torch.randint(0, 256, (1, 3, 512, 512), dtype=torch.uint8, generator=g).cuda()
+    det = Detector(device="cuda", dtype=torch.bfloat16, seed=3, conf_thres=1e-6, classes=[1, 5], cuda_graph=True)
+    buf = det.detect_device(rgb, ir)
+    assert det.cuda_graph, "capture must not fall back to eager launches"
+    n = int(buf.counts[0])
+    assert n > 0 and set(buf.det[0, :n, 5].tolist()) <= {1.0, 5.0}
+    eager = Detector(device="cuda", dtype=torch.bfloat16, seed=3, conf_thres=1e-6, classes=[1, 5], cuda_graph=False)
+    assert torch.equal(eager.detect_device(rgb, ir).flat, buf.flat)
+
+
+def test_pickled_model_loads_through_reference_paths(tmp_path):
+    """Checkpoints of the reference are pickled Model objects recorded under `basics.models.*` (Train.py:528-546,
+    experimental.py:118-120).  With sodt_b200.install_reference_aliases() (the recipe of INTEGRATION.md) such a pickle
+    resolves to this package's classes, fuses and runs."""
+    import sys
+    import sodt_b200
+    from sodt_b200.basics.models.model import Model
+    ours = [m for name, m in list(sys.modules.items()) if name.startswith("sodt_b200.basics") and m is not None]
+    classes = [c for m in ours for c in vars(m).values() if isinstance(c, type) and c.__module__.startswith("sodt_b200.basics")]
+    sodt_b200.install_reference_aliases()
+    try:
+        import basics.models.model as ref_path                       # the reference's dotted path
+        assert ref_path.Model is Model
+        m = Model(YAML, input_mode="RGB+IR", ch_steam=3, ch=128, nc=8)
+        m.load_state_dict(det_state_dict(), strict=False)
+        path = tmp_path / "ckpt.pt"
+        for c in classes:                                            # write the pickle the way the reference would have
+            c.__module__ = c.__module__.replace("sodt_b200.basics", "basics", 1)
+        try:
+            torch.save({"model": m.half(), "epoch": -1}, path)
+        finally:
+            for c in classes:
+                c.__module__ = "sodt_b200." + c.__module__
+        blob = path.read_bytes()
+        assert b"cbasics.models.model\nModel" in blob and b"csodt_b200." not in blob        # every class GLOBAL is a reference path
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        model = ckpt["model"]
+        assert type(model) is Model
+        model = model.float().fuse().eval().cuda().to(torch.bfloat16)
+        rgb = fx.det_input("pickle:rgb", (1, 3, 512, 512), kind="uniform").cuda().to(torch.bfloat16)
+        with torch.no_grad():
+            pred, _, _ = model(rgb, rgb, "RGB+IR")
+        assert pred.shape == (1, 3 * 128 * 128, 13) and torch.isfinite(pred).all()
+    finally:
+        sodt_b200.remove_reference_aliases()
+
+
+def test_torch_ops_sodt_nms_registered():
+    pred = torch.from_numpy(fx.synthetic_predictions(2, 4096, 8, 256, 0.2, seed=0)).cuda()
+    out, counts = torch.ops.sodt.nms(pred, 0.25, 0.45, False, False)
+    ref, cref, _ = ops().nms(pred, 0.25, 0.45)
+    assert torch.equal(out, ref) and torch.equal(counts, cref)
+
+
+def test_window_attention_module_dense_mask_kernel_path():
+    """WindowAttention.forward(x, mask) with an arbitrary dense [nW, N, N] mask runs on the CUDA kernel (mask pointer of the
+    exact kernel), reference backbone_vit.py:979-984."""
+    from sodt_b200.basics.models.backbone_vit import WindowAttention
+    torch.manual_seed(0)
+    dim, heads, ws, nW, Bn = 64, 4, 4, 6, 3
+    attn = WindowAttention(dim, (ws, ws), heads).eval()
+    p = {k: fx.deterministic_tensor("wa_mask." + k, v.shape, seed=4) for k, v in attn.state_dict().items() if torch.is_floating_point(v)}
+    attn.load_state_dict(p, strict=False)
+    x = fx.det_input("wa_mask:x", (Bn * nW, ws * ws, dim))
+    mask = torch.where(fx.det_input("wa_mask:m", (nW, ws * ws, ws * ws)) > 0.3, -100.0, 0.0)
+    ref = A.window_attention(x.double(), {("a." + k): v for k, v in attn.state_dict().items()}, "a.", heads, ws, ws, mask=mask.double())
+    for dtype in (torch.float32, torch.bfloat16):
+        m = attn.to("cuda", dtype)
+        n0 = ops().launch_count()
+        with torch.no_grad():
+            y = m(x.to("cuda", dtype), mask.cuda())
+        assert ops().launch_count() > n0, "the dense-mask path must run a sodt kernel"
+        assert rel_err(y, ref) < (2e-5 if dtype == torch.float32 else 2e-2)
