@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--cpu-baseline-images", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly (for ncu launch lists)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the kernel-level legs of BASELINE configs 1, 3, 4 and 5 (N = 1 only)")
     return ap.parse_args()
 
 
@@ -156,6 +157,149 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------- kernel-level legs (BASELINE configs 1, 3, 4, 5)
+def _time_cuda(fn, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def kernel_legs(dev, hbm_peak, tensor_peak, with_cpu=True):
+    """Per-kernel numbers of the configurations BASELINE.json lists beside the headline:
+      c3  window-attention microbenchmark at 2048^2 px: 512^2-token grid, C = 192, shift 0 / 2 / 4, B 1 / 4; 128^2 grid with
+          C = 384; stage-3 geometry (N = 1024, head_dim 64, 16 B windows) -- GB/s of q, k, v, o against the HBM peak,
+          TFLOP/s (QK^T + PV) against the bf16 peak
+      c4  cross-channel block sweep over window sizes, heads and widths, fp32 and bf16 -- GB/s of the 4 streams in + out
+      c5  Detect decode on [32, 39, 256, 256] and NMS on the synthetic predictions of section 8d at both operating points
+          -- images/s, next to the reference restatement's CPU time for the same inputs
+      c1  the reference's CPU forward (oracle port), batch 1, 512 x 512, fp32, all host cores
+    Every tensor set is larger than L2 (or rotated through several copies) so that repetitions do not hit a warm cache."""
+    import numpy as np
+    import torch
+
+    from oracle import fixtures as fx
+    from sodt_b200 import ops
+
+    g = torch.Generator(device=dev).manual_seed(0)
+    bf = torch.bfloat16
+    legs = {}
+    # ---- C3
+    c3 = []
+    for (H, C, heads, ws, shifts, batches) in ((512, 192, 12, 8, (0, 2, 4), (1, 4)), (128, 384, 12, 8, (0, 2), (4, 16)),
+                                                (128, 768, 12, 32, (0,), (1, 4))):
+        table = 0.02 * torch.randn((2 * ws - 1) ** 2, heads, device=dev, generator=g)
+        for B in batches:
+            copies = max(1, int(np.ceil(160e6 / (B * H * H * 4 * C * 2))))       # rotate inputs until > L2 (126 MB)
+            qkvs = [torch.randn(B, H, H, 3 * C, device=dev, generator=g).to(bf) for _ in range(copies)]
+            for shift in shifts:
+                it = [0]
+
+                def run():
+                    ops.window_attention(qkvs[it[0] % copies], table, heads, ws, shift)
+                    it[0] += 1
+                ms = _time_cuda(run, 10)
+                nbytes = B * H * H * 4 * C * 2
+                flops = 4.0 * ws * ws * C * B * H * H
+                row = {"grid": f"{H}x{H}", "C": C, "heads": heads, "ws": ws, "shift": shift, "B": B, "windows": B * (H // ws) ** 2,
+                       "ms": ms, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm_peak,
+                       "TFLOPs": flops / ms / 1e9, "frac_tensor": flops / ms / 1e9 / tensor_peak}
+                c3.append(row)
+            del qkvs
+    legs["c3_window_attention"] = c3
+    # ---- C4
+    c4 = []
+    for dtype, dname in ((bf, "bf16"), (torch.float32, "fp32")):
+        for hw, B in ((128, 32), (256, 8)):
+            for C in (24, 48, 96):
+                streams = [torch.randn(B, hw, hw, C, device=dev, generator=g).to(dtype) for _ in range(4)]
+                ln_w, ln_b = torch.ones(4, C, device=dev), torch.zeros(4, C, device=dev)
+                for ws in (1, 2, 3, 7, 8):
+                    best = []
+                    for heads in (1, 2, 3, 4, 6, 12):
+                        ms = _time_cuda(lambda: ops.cattn_block(*streams, ln_w, ln_b, heads, ws=ws), 5, warm=1)
+                        best.append((heads, ms))
+                    nbytes = 2 * 4 * B * hw * hw * C * (2 if dtype == bf else 4)
+                    ms_all = [m for _, m in best]
+                    c4.append({"dtype": dname, "grid": f"{hw}x{hw}", "B": B, "C": C, "ws": ws, "heads": [h for h, _ in best],
+                               "ms": ms_all, "GBps_median": nbytes / float(np.median(ms_all)) / 1e6,
+                               "frac_hbm_median": nbytes / float(np.median(ms_all)) / 1e6 / hbm_peak})
+                del streams
+    legs["c4_cross_channel"] = c4
+    # ---- C5: decode + NMS on synthetic predictions
+    B, R, nc = 32, 3 * 256 * 256, 8
+    raw = torch.randn(B, 39, 256, 256, device=dev, generator=g).to(bf).contiguous(memory_format=torch.channels_last)
+    anchors = torch.tensor([[10., 13.], [16., 30.], [33., 23.]], device=dev)
+    ms = _time_cuda(lambda: ops.detect_decode(raw, anchors, 4.0, want_perm=False), 10)
+    nbytes = B * 39 * 256 * 256 * 2 + B * R * 13 * 4
+    legs["c5_detect_decode"] = {"B": B, "ms": ms, "GBps": nbytes / ms / 1e6, "frac_hbm": nbytes / ms / 1e6 / hbm_peak,
+                                "images_per_s": B / ms * 1e3}
+    del raw
+    pred_np = fx.synthetic_predictions(B, R, nc, 1024, 0.02, seed=0)
+    pred = torch.from_numpy(pred_np).to(dev)
+    nms = []
+    for name, kw in (("conf 0.25 / IoU 0.45, single label", dict(conf_thres=0.25, iou_thres=0.45)),
+                     ("conf 0.001 / IoU 0.6, multi label", dict(conf_thres=0.001, iou_thres=0.6, multi_label=True))):
+        ms = _time_cuda(lambda: ops.nms(pred, **kw), 5, warm=1)
+        _, counts, _ = ops.nms(pred, **kw)
+        row = {"operating_point": name, "B": B, "rows_per_image": R, "ms_per_batch": ms, "images_per_s": B / ms * 1e3,
+               "scan_GBps": B * R * 13 * 4 / ms / 1e6, "detections_per_image": float(counts.float().mean())}
+        if with_cpu:
+            from oracle import nms_ref
+            t0 = time.perf_counter()
+            n_cpu = 1 if kw.get("multi_label") else 2
+            nms_ref.non_max_suppression(pred_np[:n_cpu], kw["conf_thres"], kw["iou_thres"], multi_label=kw.get("multi_label", False))
+            row["cpu_port_images_per_s"] = n_cpu / (time.perf_counter() - t0)
+        nms.append(row)
+    legs["c5_nms_synthetic"] = nms
+    del pred
+    # ---- C1
+    if with_cpu:
+        c1 = cpu_reference_run(3, 512, warmup=1)
+        cpu_model = ""
+        try:
+            for line in open("/proc/cpuinfo"):
+                if line.startswith("model name"):
+                    cpu_model = line.split(":", 1)[1].strip()
+                    break
+        except OSError:
+            pass
+        legs["c1_cpu_reference_512"] = {"images_per_s": c1["value"], "ms_per_image": c1["ms_per_image"], "cores": c1["cores"],
+                                        "cpu": cpu_model, "kind": "port", "sample": c1["sample"]}
+    return legs
+
+
+def attention_tensor_pipe():
+    """Tensor-pipe utilisation of the attention kernels from the committed ncu capture.  The capture is stamped with the SHA-256
+    of the kernel sources it was taken from; a stale stamp yields None (and a loud line on stderr) instead of an old number."""
+    import hashlib
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")))
+    except (OSError, ValueError):
+        return None, None, "profiles/r2_roofline_traffic.json missing"
+    csrc = os.path.join(ROOT, "small-object-detection-transformers_b200", "csrc")
+    stale = []
+    for name, want in prof.get("source_sha256", {}).items():
+        try:
+            got = hashlib.sha256(open(os.path.join(csrc, name), "rb").read()).hexdigest()
+        except OSError:
+            got = None
+        if got != want:
+            stale.append(name)
+    if stale or not prof.get("source_sha256"):
+        msg = f"ncu capture is stale for {stale or 'unstamped sources'}: attn_tensor_pipe_pct / roofline.traffic withheld"
+        sys.stderr.write("bench.py: WARNING: " + msg + "\n")
+        return None, None, msg
+    return prof.get("traffic_bytes"), prof.get("attention_tensor_pipe_pct"), None
+
 # ----------------------------------------------------------------------------------- GPU arm
 def run_sodt(args):
     # stdout carries exactly one JSON line: whatever libraries write to file descriptor 1 (NCCL prints its version banner there)
@@ -256,12 +400,8 @@ def run_sodt(args):
     C1 = 192
     esize = 2 if dtype == torch.bfloat16 else 4
     stage1 = [v for k, v in per_kernel.items() if k.startswith("window_attn[") and f"C={C1}," in k]
-    traffic, attn_tensor_pct = None, None
-    try:      # DRAM bytes of one stage-1 launch and the attention kernels' tensor-pipe % from the committed ncu --set full capture
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")))
-        traffic, attn_tensor_pct = prof["traffic_bytes"], prof.get("attention_tensor_pipe_pct")
-    except (OSError, ValueError, KeyError):
-        pass
+    # DRAM bytes of one stage-1 launch and the attention kernels' tensor-pipe % from the committed ncu --set full capture
+    traffic, attn_tensor_pct, profile_note = attention_tensor_pipe()
     if stage1:
         durs = [x for v in stage1 for x in v]
         avg_ms = sum(durs) / len(durs)
@@ -299,6 +439,11 @@ def run_sodt(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_reference_run(args.cpu_baseline_images, S)
         cpu_baseline.pop("ms_per_image", None)
+    legs = None
+    if rank == 0 and world == 1 and not args.no_legs:
+        del devin, host
+        torch.cuda.empty_cache()
+        legs = kernel_legs(dev, hbm_peak, float(peaks.get("bf16_tflops", 1590.0)), with_cpu=not args.no_cpu_baseline)
 
     if rank == 0:
         line = {
@@ -317,9 +462,13 @@ def run_sodt(args):
                     "ms_per_step": ms_e2e / steps},
             "gpu_launches": int(launches),
             "roofline": roofline,
-            "attn_tensor_pipe_pct": attn_tensor_pct,      # the second half of BASELINE's metric: from profiles/ (ncu), not measured live
+            # the second half of BASELINE's metric: ncu's sm__pipe_tensor_cycles_active of the attention kernels, from the capture
+            # under profiles/ whose source stamp matches the kernels that ran (None if the capture is stale)
+            "attn_tensor_pipe_pct": attn_tensor_pct,
+            "profile_note": profile_note,
             "kernel_shares": shares,
             "cpu_baseline": cpu_baseline,
+            "legs": legs,
         }
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

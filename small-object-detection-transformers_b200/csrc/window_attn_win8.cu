@@ -4,9 +4,10 @@
 // Window partition, cyclic roll, reverse partition and reverse roll (reference backbone_vit.py:619-672,1096,1118) are TMA
 // tile addressing: a window of the rolled frame is the (64 channels, 8, 8) box of the [B*H, W, 3C] qkv image at
 // (x, y) = (8 wx + shift, 8 wy + shift), landing in shared memory as a SWIZZLE_128B operand tile (64 token rows x 128 B).  The
-// windows of the last window row / column wrap around the image: their boxes are issued per image row ((64, 8, 1), or the two
-// parts (64, 8 - shift, 1) + (64, shift, 1) when the row itself wraps), into the same tile.  The output tile goes back the
-// same way with TMA stores.  No thread of the kernel touches q, k, v or o in global memory.
+// windows of the last window row / column wrap around the image: their boxes are loaded per image row ((64, 8, 1), or the two
+// parts (64, 8 - shift, 1) + (64, shift, 1) when the row itself wraps) into the same tile, the 40 / 80 small copies of a stage
+// spread over the lanes of the producer warp.  The output tile goes back the same way with TMA stores.  No thread of the kernel
+// touches q, k, v or o in global memory.
 //
 // An MMA instruction of these shapes costs ~100 cycles of the tensor pipe whatever N is (64 with independent accumulators;
 // tests/probes/umma_probe.cu), so the kernel is organised around the FEWEST instructions: the 128 TMEM lanes hold TWO HEADS of
@@ -24,8 +25,9 @@
 //   O[128x2hd]  ONE unmasked TS chain (A = P from TMEM, B = the two heads' adjacent V channels, MN-major SWIZZLE_128B at the
 //               pair's column offset, K = 64 keys); lane half p reads its head's hd columns
 //   epilogue    O / rowsum -> bf16 -> SWIZZLE_128B staging tile -> TMA store of the un-rolled image tile
-// Persistent CTAs (one per SM), 12 warps: two softmax groups of 4 warps taking the units (stage, head pair) alternately, with
-// private S / P / O columns in TMEM; one MMA-issuing warp PER GROUP; one TMA-load warp; one TMA-store warp.
+// Persistent CTAs (one per SM), 20 warps: two softmax groups of 8 warps (two threads per score row) taking the units
+// (stage, head pair) alternately, with private S / P / O columns in TMEM; one MMA-issuing warp PER GROUP; one TMA-load warp;
+// one TMA-store warp.
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -46,8 +48,9 @@ constexpr int WS = 8;
 constexpr int NTOK = 64;                 // tokens per window
 constexpr int ROWS = 128;                // TMEM lanes = 2 heads x 64 tokens
 constexpr int NG = 2;                    // softmax groups
-constexpr int NTHREADS = (NG * 4 + NG + 2) * 32;
-constexpr int MMA_WARP0 = NG * 4, TMA_WARP = NG * 4 + NG, STORE_WARP = NG * 4 + NG + 1;   // one MMA-issuing warp per softmax group
+constexpr int SM_WARPS = 8;              // softmax warps per group: two threads per score row
+constexpr int NTHREADS = (NG * SM_WARPS + NG + 2) * 32;
+constexpr int MMA_WARP0 = NG * SM_WARPS, TMA_WARP = MMA_WARP0 + NG, STORE_WARP = TMA_WARP + 1;   // one MMA-issuing warp per softmax group
 constexpr int STAGES = 4;
 constexpr int WIN_BYTES = NTOK * 128;         // one box: 64 token rows x 128 B
 constexpr int STAGE_BYTES = 5 * WIN_BYTES;    // QA QB KA KB V
@@ -65,7 +68,8 @@ __host__ __device__ constexpr int tab_copy_stride(int heads) {         // floats
 constexpr int TAB_COPIES = 2;
 // TMEM columns per group g: S = g*128 (128 columns), P = 256 + g*32, O = 320 + g*64 (2*hd <= 64 columns)
 constexpr uint32_t TM_S = 0, TM_P = 256, TM_O = 320;
-constexpr int EXP_BAR0 = 2;                   // named barriers 2, 3: turn-taking of the two softmax groups' exp phases
+constexpr int XCH_BAR0 = 2;                   // named barriers 2, 3: row-maximum exchange inside a softmax group
+constexpr int XCH_FLOATS = 2 * 2 * NG * 2 * ROWS;    // {max, sum} x unit parity x group x half x row
 
 __global__ void prep_table_win8_kernel(const float* __restrict__ table, float* __restrict__ out, int heads) {
     const int cs = tab_copy_stride(heads);
@@ -110,24 +114,45 @@ struct Maps {
     CUtensorMap full, row8, row_a, row_b;     // boxes (64, 8, 8), (64, 8, 1), (64, 8 - shift, 1), (64, shift, 1)
 };
 
-// One window box (64 channels from c0) <-> the 8 KB tile at shared address `sm`; LOAD = global -> shared (completes on bar)
-template <bool LOAD>
-__device__ __forceinline__ void window_box(const Maps& m, const Geo& geo, const WinBox& b, uint32_t sm, int c0, uint64_t* bar) {
+// The five boxes of a stage (QA, QB, KA, KB, V), issued by the whole producer warp: a window inside the image is one box per
+// operand tile (lanes 0-4); a window that wraps around the image is 8 row boxes per tile, or 16 row parts when the rows
+// themselves wrap (40 / 80 small copies spread over the 32 lanes: one lane needs ~130 cycles per TMA instruction).
+template <int HD>
+__device__ __forceinline__ void load_stage(const Maps& m, const Geo& geo, const WinBox& b, uint32_t st, int c0, int C, uint64_t* bar, int lane) {
+    const int per_box = !b.wrap_x && !b.wrap_y ? 1 : (b.wrap_x ? 2 * WS : WS);
+    for (int item = lane; item < 5 * per_box; item += 32) {
+        const int bi = item / per_box, sub = item - bi * per_box;
+        const uint32_t sm = st + bi * WIN_BYTES;                                 // tiles in the order QA QB KA KB V
+        const int ch = (bi >> 1) * C + c0 + ((bi & 1) && bi < 4 ? HD : 0);        // q, q + hd, k, k + hd, v
+        if (per_box == 1) {
+            tma::load_3d(sm, &m.full, bar, ch, b.x0, b.yg_base + b.y0);
+        } else {
+            const int ty = b.wrap_x ? sub >> 1 : sub;
+            int ys = b.y0 + ty; if (ys >= geo.H) ys -= geo.H;
+            const int yg = b.yg_base + ys;
+            if (!b.wrap_x) tma::load_3d(sm + ty * 1024, &m.row8, bar, ch, b.x0, yg);
+            else if ((sub & 1) == 0) tma::load_3d(sm + ty * 1024, &m.row_a, bar, ch, b.x0, yg);
+            else tma::load_3d(sm + ty * 1024 + (WS - geo.shift) * 128, &m.row_b, bar, ch, 0, yg);
+        }
+    }
+}
+
+// Output tile -> the window's pixels of the un-rolled image, issued by the whole store warp: one box, or the 8 rows / 16 row
+// parts of a wrapped window spread over the lanes.  (Storing a wrapped tile as full boxes at negative coordinates and letting the
+// TMA unit clip them is not an option: a tiled store with a negative coordinate raises an illegal-instruction fault, probed.)
+__device__ __forceinline__ void store_tile(const Maps& m, const Geo& geo, const WinBox& b, uint32_t sm, int c0, int lane) {
     if (!b.wrap_x && !b.wrap_y) {
-        if (LOAD) tma::load_3d(sm, &m.full, bar, c0, b.x0, b.yg_base + b.y0); else tma::store_3d(&m.full, sm, c0, b.x0, b.yg_base + b.y0);
+        if (lane == 0) tma::store_3d(&m.full, sm, c0, b.x0, b.yg_base + b.y0);
         return;
     }
-    for (int ty = 0; ty < WS; ++ty) {
+    const int n = b.wrap_x ? 2 * WS : WS;
+    if (lane < n) {
+        const int ty = b.wrap_x ? lane >> 1 : lane;
         int ys = b.y0 + ty; if (ys >= geo.H) ys -= geo.H;
         const int yg = b.yg_base + ys;
-        const uint32_t d = sm + ty * 1024;
-        if (b.wrap_x) {
-            const uint32_t d2 = d + (WS - geo.shift) * 128;
-            if (LOAD) { tma::load_3d(d, &m.row_a, bar, c0, b.x0, yg); tma::load_3d(d2, &m.row_b, bar, c0, 0, yg); }
-            else { tma::store_3d(&m.row_a, d, c0, b.x0, yg); tma::store_3d(&m.row_b, d2, c0, 0, yg); }
-        } else {
-            if (LOAD) tma::load_3d(d, &m.row8, bar, c0, b.x0, yg); else tma::store_3d(&m.row8, d, c0, b.x0, yg);
-        }
+        if (!b.wrap_x) tma::store_3d(&m.row8, sm + ty * 1024, c0, b.x0, yg);
+        else if ((lane & 1) == 0) tma::store_3d(&m.row_a, sm + ty * 1024, c0, b.x0, yg);
+        else tma::store_3d(&m.row_b, sm + ty * 1024 + (WS - geo.shift) * 128, c0, 0, yg);
     }
 }
 
@@ -166,7 +191,8 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t ot_base = sbase + STAGES * STAGE_BYTES;                            // ring of output staging tiles
-    float* tab = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + OT_RING * OT_BYTES);
+    float* xch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + OT_RING * OT_BYTES);
+    float* tab = xch + XCH_FLOATS;
     const int groups = C / 64;                                                         // stages per window
     long long my_windows = 0;
     if ((long long)blockIdx.x < geo.total_windows) my_windows = (geo.total_windows - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -175,8 +201,8 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], UPS); }     // one commit per head pair of the stage
-        for (int s = 0; s < OT_RING; ++s) { mbar_init(&ot_full[s], UPS * ROWS); mbar_init(&ot_free[s], 1); }
-        for (int g = 0; g < NG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], ROWS); mbar_init(&p_full[g], ROWS); mbar_init(&pv_done[g], 1); }
+        for (int s = 0; s < OT_RING; ++s) { mbar_init(&ot_full[s], UPS * 2 * ROWS); mbar_init(&ot_free[s], 1); }
+        for (int g = 0; g < NG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 2 * ROWS); mbar_init(&p_full[g], 2 * ROWS); mbar_init(&pv_done[g], 1); }
         fence_barrier_init();
     }
     if (warp == MMA_WARP0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
@@ -192,51 +218,46 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
     const uint32_t tm = tmem_slot;
 
     if (warp == TMA_WARP) {
-        // ============================================================ producer: one lane issues every box of every stage
-        if (lane == 0) {
-            tma::prefetch_map(&in_maps.full);
-            int stage = 0, round = 0;
-            [[maybe_unused]] int tr_stage = 0;
-            for (long long wdx = blockIdx.x; wdx < geo.total_windows; wdx += gridDim.x) {
-                const WinBox b = win_box(geo, wdx);
-                for (int gi = 0; gi < groups; ++gi) {
+        // ============================================================ producer: the warp issues the boxes of every stage
+        if (lane == 0) tma::prefetch_map(&in_maps.full);
+        int stage = 0, round = 0;
+        [[maybe_unused]] int tr_stage = 0;
+        for (long long wdx = blockIdx.x; wdx < geo.total_windows; wdx += gridDim.x) {
+            const WinBox b = win_box(geo, wdx);
+            for (int gi = 0; gi < groups; ++gi) {
+                if (lane == 0) {
                     TRACE(3, tr_stage, 0);
                     if (round > 0) mbar_wait(&stage_empty[stage], (uint32_t)((round - 1) & 1));
                     TRACE(3, tr_stage, 1);
                     tma::expect_tx(&stage_full[stage], STAGE_BYTES);
-                    const uint32_t st = sbase + stage * STAGE_BYTES;
-                    const int c0 = gi * 64;
-                    window_box<true>(in_maps, geo, b, st + OFF_Q, c0, &stage_full[stage]);
-                    window_box<true>(in_maps, geo, b, st + OFF_Q + WIN_BYTES, c0 + HD, &stage_full[stage]);
-                    window_box<true>(in_maps, geo, b, st + OFF_K, C + c0, &stage_full[stage]);
-                    window_box<true>(in_maps, geo, b, st + OFF_K + WIN_BYTES, C + c0 + HD, &stage_full[stage]);
-                    window_box<true>(in_maps, geo, b, st + OFF_V, 2 * C + c0, &stage_full[stage]);
-                    TRACE(3, tr_stage, 2);
-                    ++tr_stage;
-                    if (++stage == STAGES) { stage = 0; ++round; }
                 }
+                __syncwarp();
+                load_stage<HD>(in_maps, geo, b, sbase + stage * STAGE_BYTES, gi * 64, C, &stage_full[stage], lane);
+                if (lane == 0) TRACE(3, tr_stage, 2);
+                ++tr_stage;
+                if (++stage == STAGES) { stage = 0; ++round; }
             }
         }
     } else if (warp == STORE_WARP) {
-        // ============================================================ output stores: one lane stores every finished staging tile
-        if (lane == 0) {
-            tma::prefetch_map(&out_maps.full);
-            long long st = 0;
-            for (long long wdx = blockIdx.x; wdx < geo.total_windows; wdx += gridDim.x) {
-                const WinBox b = win_box(geo, wdx);
-                for (int gi = 0; gi < groups; ++gi, ++st) {
-                    const int slot = (int)(st & (OT_RING - 1));
-                    mbar_wait(&ot_full[slot], (uint32_t)((st / OT_RING) & 1));           // both head pairs' columns are in the tile
-                    window_box<false>(out_maps, geo, b, ot_base + slot * OT_BYTES, gi * 64, nullptr);
-                    tma::store_commit();
-                    if (st > 0) {                                                        // the previous tile has been read: its slot is free
-                        tma::store_wait_read<1>();
-                        mbar_arrive(&ot_free[(int)((st - 1) & (OT_RING - 1))]);
-                    }
+        // ============================================================ output stores: the warp stores every finished staging tile
+        if (lane == 0) tma::prefetch_map(&out_maps.full);
+        long long st = 0;
+        for (long long wdx = blockIdx.x; wdx < geo.total_windows; wdx += gridDim.x) {
+            const WinBox b = win_box(geo, wdx);
+            for (int gi = 0; gi < groups; ++gi, ++st) {
+                const int slot = (int)(st & (OT_RING - 1));
+                if (lane == 0) mbar_wait(&ot_full[slot], (uint32_t)((st / OT_RING) & 1));        // every head pair's columns are in the tile
+                __syncwarp();
+                store_tile(out_maps, geo, b, ot_base + slot * OT_BYTES, gi * 64, lane);
+                tma::store_commit();                                                     // per lane: each lane tracks its own copies
+                if (st > 0) {                                                            // the previous tile has been read: its slot is free
+                    tma::store_wait_read<1>();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ot_free[(int)((st - 1) & (OT_RING - 1))]);
                 }
             }
-            tma::store_wait_all();
         }
+        tma::store_wait_all();
     } else if (warp >= MMA_WARP0) {
         // =============================================================== MMA issuers: one thread per softmax group
         // (a single issuer serialised the groups: the scores of one group waited behind the other group's P)
@@ -287,45 +308,53 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         }
     } else {
         // ====================================================== softmax + epilogue groups
-        const int g = warp >> 2;                       // group g takes units g, g + NG, ...
-        const int row = tid & 127;                     // TMEM lane = 64 * (head parity) + query token
+        // Two threads per score row: warps w and w + 4 of a group own the same 32 TMEM lanes (a warp reaches lane quarter
+        // warp % 4 only) and split the 64 keys, so 16 softmax warps (4 per SM sub-partition) cover one another's tensor-memory,
+        // shared-memory and MUFU latencies; row maximum and row sum are exchanged through shared memory.
+        const int g = warp >> 3;                       // group g takes units g, g + NG, ...
+        const int half = (warp >> 2) & 1;              // keys [32 half, 32 half + 32) = key rows yj in [4 half, 4 half + 4)
+        const int row = (warp & 3) * 32 + lane;        // TMEM lane = 64 * (head parity) + query token
         const int hp = row >> 6, ti = row & 63, ty = ti >> 3, tx = ti & 7;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tS = tm + TM_S + g * 128 + hp * 64 + lane_addr;
-        const uint32_t tP = tm + TM_P + g * 32 + lane_addr;
-        const uint32_t tO = tm + TM_O + g * 64 + hp * HD + lane_addr;
+        const uint32_t tS = tm + TM_S + g * 128 + hp * 64 + half * 32 + lane_addr;
+        const uint32_t tP = tm + TM_P + g * 32 + half * 16 + lane_addr;
+        const uint32_t tO = tm + TM_O + g * 64 + hp * HD + half * (HD / 2) + lane_addr;
         const float c = scale * LOG2E, mv2 = mask_value * LOG2E;
         const uint64_t c2 = pack2(c, c);
-        // bias row of key row yj = 0 for this thread: copy (7 - tx) % 2 at entry (7 - tx) - copy (even), table row dy = ty + 7
+        // bias row of this thread's first key row: copy (7 - tx) % 2 at entry (7 - tx) - copy (even), table row dy = ty + 7 - yj
         const int r0 = WS - 1 - tx, cp = r0 & 1;
-        const float* tab_row = tab + cp * tab_copy_stride(heads) + (ty + WS - 1) * TAB_ROW + (r0 - cp);
+        const float* tab_row = tab + cp * tab_copy_stride(heads) + (ty + WS - 1 - 4 * half) * TAB_ROW + (r0 - cp);
         const int s_ = geo.shift;
         const uint64_t yhi = s_ > 0 ? (~0ull << (8 * (WS - s_))) : 0ull;                       // keys with ty >= ws - shift
         const uint64_t xhi = s_ > 0 ? 0x0101010101010101ull * (uint64_t)((0xFFu << (WS - s_)) & 0xFFu) : 0ull;  // tx >= ws - shift
         const uint32_t srow = (uint32_t)ti * 128, sw = (uint32_t)(ti & 7);
+        float* my_max = xch + (g * 2 + half) * ROWS + row;            // [parity k & 1][group][half][row]; partner: half ^ 1
+        float* pt_max = xch + (g * 2 + (half ^ 1)) * ROWS + row;
+        float* my_sum = my_max + 2 * NG * 2 * ROWS;
+        float* pt_sum = pt_max + 2 * NG * 2 * ROWS;
         long long cur_win_it = -1;
-        uint64_t mbits = 0;
+        uint32_t mbits = 0;
         WinBox wb = {};                                // geometry of the window of the current unit
-        float prev_inv = 0.f;
+        float prev_sum = 0.f;
         int prev_pr = 0;
-        long long prev_stage = 0;
+        long long prev_stage = 0, prev_k = 0;
         [[maybe_unused]] int tr_u = 0;
 
-        // Epilogue of the group's previous unit: O / rowsum -> this head's columns of the stage's staging tile; the store warp
-        // sends the tile off when every head pair of the stage has delivered.
+        // Epilogue of the group's previous unit: this thread's half of its head's O columns / rowsum -> staging tile of the stage;
+        // the store warp sends the tile off when every head pair of the stage has delivered.
         auto epilogue = [&]() {
             const int slot = (int)(prev_stage & (OT_RING - 1));
             const uint32_t tile_s = ot_base + (uint32_t)slot * OT_BYTES;
-            uint32_t o[HD];
-            if constexpr (HD == 16) tmem_ld16(tO, o); else tmem_ld32(tO, o);
+            uint32_t o[HD / 2];
+            if constexpr (HD == 16) tmem_ld8(tO, o); else tmem_ld16(tO, o);
+            const float inv = 1.f / (prev_sum + pt_sum[(prev_k & 1) * (NG * 2 * ROWS)]);     // written before the partner's p_full arrival
             tmem_wait_ld();
-            if (row == 0) TRACE(g, tr_u, 7);
+            if (row == 0 && half == 0) TRACE(g, tr_u, 7);
             if (prev_stage >= OT_RING) mbar_wait(&ot_free[slot], (uint32_t)(((prev_stage / OT_RING) - 1) & 1));   // the slot's previous tile has left
-            if (row == 0) TRACE(g, tr_u, 8);
-            const float inv = prev_inv;
+            if (row == 0 && half == 0) TRACE(g, tr_u, 8);
 #pragma unroll
-            for (int j = 0; j < HD; j += 8) {
-                const uint32_t chunk = (uint32_t)(((2 * prev_pr + hp) * HD + j) >> 3) ^ sw;
+            for (int j = 0; j < HD / 2; j += 8) {
+                const uint32_t chunk = (uint32_t)(((2 * prev_pr + hp) * HD + half * (HD / 2) + j) >> 3) ^ sw;
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
                              "r"(pack_bf16(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv)),
                              "r"(pack_bf16(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv)),
@@ -334,58 +363,60 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
             }
             fence_proxy_async();                                          // staging writes -> visible to the TMA store
             mbar_arrive(&ot_full[slot]);
-            if (row == 0) TRACE(g, tr_u, 9);
+            if (row == 0 && half == 0) TRACE(g, tr_u, 9);
         };
 
-        if (g == 1 && n_units > 0) asm volatile("bar.arrive %0, 256;" ::"r"(EXP_BAR0) : "memory");   // group 0 takes the first turn
         long long k = 0, stg = 0, win_it = 0;          // this CTA's stage / window counters of the current unit
         int pr = 0, gi = 0;
         auto advance = [&]() { if (++pr == UPS) { pr = 0; ++stg; if (++gi == groups) { gi = 0; ++win_it; } } };
         for (int i = 0; i < g; ++i) advance();
         for (long long u = g; u < n_units; u += NG, ++k) {
-            if (win_it != cur_win_it) {                // new window: geometry, shifted-window mask bits
+            if (win_it != cur_win_it) {                // new window: geometry, shifted-window mask bits of this thread's 32 keys
                 cur_win_it = win_it;
                 wb = win_box(geo, (long long)blockIdx.x + win_it * gridDim.x);
-                mbits = 0;
+                uint64_t mb = 0;
                 if (s_ > 0) {
-                    if (wb.last_row) mbits |= (ty >= WS - s_) ? ~yhi : yhi;
-                    if (wb.last_col) mbits |= (tx >= WS - s_) ? ~xhi : xhi;
+                    if (wb.last_row) mb |= (ty >= WS - s_) ? ~yhi : yhi;
+                    if (wb.last_col) mb |= (tx >= WS - s_) ? ~xhi : xhi;
                 }
+                mbits = (uint32_t)(mb >> (32 * half));
             }
             const bool any_mask = s_ > 0 && (wb.last_row || wb.last_col);
             tr_u = (int)u;
-            if (row == 0) TRACE(g, tr_u, 0);
+            if (row == 0 && half == 0) TRACE(g, tr_u, 0);
             mbar_wait(&s_full[g], (uint32_t)(k & 1));
-            if (row == 0) TRACE(g, tr_u, 1);
+            if (row == 0 && half == 0) TRACE(g, tr_u, 1);
             fence_after_sync();
             const int h = gi * G + 2 * pr + hp;
-            uint64_t t[NTOK / 2];
+            uint64_t t[NTOK / 4];
             {
-                uint32_t ra[32], rb[32];
+                uint32_t ra[32];
                 tmem_ld32(tS, ra);
-                tmem_ld32(tS + 32, rb);
                 tmem_wait_ld();
                 fence_before_sync();
                 mbar_arrive(&s_free[g]);                // the unit's scores are in registers
-                if (row == 0) TRACE(g, tr_u, 2);
+                if (row == 0 && half == 0) TRACE(g, tr_u, 2);
                 const float* tb = tab_row + h * TAB_HEAD;
 #pragma unroll
-                for (int yj = 0; yj < WS; ++yj) {       // t = s * (scale log2 e) + bias, two scores per FFMA2
-                    const uint32_t* r = yj < 4 ? ra + yj * 8 : rb + (yj - 4) * 8;
+                for (int yj = 0; yj < WS / 2; ++yj) {   // t = s * (scale log2 e) + bias, two scores per FFMA2
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
+#ifdef SODT_X_NOBIAS
+                        const float2 b = make_float2(0.f, 0.f);
+#else
                         const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
-                        t[yj * 4 + q] = ffma2(pack2(__uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1])), c2, pack2(b.x, b.y));
+#endif
+                        t[yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
                     }
                 }
             }
             if (any_mask) {                            // group-uniform: only windows of the last window row / column
 #pragma unroll
-                for (int j = 0; j < NTOK / 2; ++j) {
+                for (int j = 0; j < NTOK / 4; ++j) {
                     float lo, hi;
                     unpack2(t[j], lo, hi);
-                    if ((mbits >> (2 * j)) & 1ull) lo += mv2;
-                    if ((mbits >> (2 * j + 1)) & 1ull) hi += mv2;
+                    if ((mbits >> (2 * j)) & 1u) lo += mv2;
+                    if ((mbits >> (2 * j + 1)) & 1u) hi += mv2;
                     t[j] = pack2(lo, hi);
                 }
             }
@@ -397,55 +428,59 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
                 m4[q] = fmaxf(lo, hi);
             }
 #pragma unroll
-            for (int j = 4; j < NTOK / 2; ++j) {
+            for (int j = 4; j < NTOK / 4; ++j) {
                 float lo, hi;
                 unpack2(t[j], lo, hi);
                 m4[j & 3] = fmax3(m4[j & 3], lo, hi);
             }
-            const float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+            float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+            const int par = (int)(k & 1) * (NG * 2 * ROWS);
+            my_max[par] = mx;
+            asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the two halves of every row have published their maxima
+            mx = fmaxf(mx, pt_max[par]);
             const uint64_t nmx2 = pack2(-mx, -mx);
-            // The exponentials of the two groups take turns on the MUFU (16 results per clock and SM: two groups in lock step
-            // both crawl at half speed and nothing else of theirs overlaps); while one group is here, the other does its
-            // tensor-memory loads, bias FMAs, row maxima and epilogue.
-            asm volatile("bar.sync %0, 256;" ::"r"(EXP_BAR0 + g) : "memory");
-            if (row == 0) TRACE(g, tr_u, 10);
-            uint64_t sum2[2] = {0ull, 0ull};
-            uint32_t pk[32];
+            uint64_t sum2 = 0ull;
+            uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < NTOK / 2; ++j) {
+            for (int j = 0; j < NTOK / 4; ++j) {
                 float lo, hi;
                 unpack2(fadd2(t[j], nmx2), lo, hi);
+#ifdef SODT_X_NOEXP
+                const float p0 = lo * 0.001f + 1.f, p1 = hi * 0.001f + 1.f;
+#else
                 const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
-                sum2[j & 1] = fadd2(sum2[j & 1], pack2(p0, p1));
+#endif
+                sum2 = fadd2(sum2, pack2(p0, p1));
                 pk[j] = pack_bf16(p0, p1);
             }
-            asm volatile("bar.arrive %0, 256;" ::"r"(EXP_BAR0 + (g ^ 1)) : "memory");       // the other group's turn
-            float inv_cur;
+            float sum_cur;
             {
                 float a, b;
-                unpack2(fadd2(sum2[0], sum2[1]), a, b);
-                inv_cur = 1.f / (a + b);
+                unpack2(sum2, a, b);
+                sum_cur = a + b;
             }
-            if (row == 0) TRACE(g, tr_u, 3);
+            if (row == 0 && half == 0) TRACE(g, tr_u, 3);
             if (k > 0) {                               // previous unit of this group: its P / O columns are free again
                 mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
-                if (row == 0) TRACE(g, tr_u, 4);
+                if (row == 0 && half == 0) TRACE(g, tr_u, 4);
                 fence_after_sync();
                 epilogue();
-                if (row == 0) TRACE(g, tr_u, 5);
+                if (row == 0 && half == 0) TRACE(g, tr_u, 5);
             }
-            tmem_st32(tP, pk);
+            my_sum[par] = sum_cur;                     // the partner reads it in its epilogue, after the next exchange barrier
+            tmem_st16(tP, pk);
             tmem_wait_st();
             fence_before_sync();
             mbar_arrive(&p_full[g]);
-            if (row == 0) TRACE(g, tr_u, 6);
-            prev_inv = inv_cur; prev_pr = pr; prev_stage = stg;
+            if (row == 0 && half == 0) TRACE(g, tr_u, 6);
+            prev_sum = sum_cur; prev_pr = pr; prev_stage = stg; prev_k = k;
 #pragma unroll
             for (int i = 0; i < NG; ++i) advance();
         }
         if (k > 0) {
             mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
             fence_after_sync();
+            asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the partner's last row sum is visible
             epilogue();
         }
     }
@@ -456,7 +491,7 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
 
 size_t win8_table_bytes(int heads) { return (size_t)TAB_COPIES * tab_copy_stride(heads) * sizeof(float); }
 
-size_t win8_smem_bytes(int heads) { return (size_t)STAGES * STAGE_BYTES + OT_RING * OT_BYTES + win8_table_bytes(heads) + 1024; }
+size_t win8_smem_bytes(int heads) { return (size_t)STAGES * STAGE_BYTES + OT_RING * OT_BYTES + XCH_FLOATS * sizeof(float) + win8_table_bytes(heads) + 1024; }
 
 bool make_maps(Maps* m, const void* base, int B, int H, int W, int Cfull, int shift, bool is_output) {
     const long long dims[3] = {Cfull, W, (long long)B * H}, strides[2] = {Cfull, (long long)W * Cfull};
@@ -499,7 +534,13 @@ int window_attn_win8(const void* qkv, const float* table, void* out, void* works
     if (!make_maps(&in_maps, qkv, B, H, W, 3 * C, shift, false) || !make_maps(&out_maps, out, B, H, W, C, shift, true)) return SODT_ERR_CUDA;
     const size_t smem = win8_smem_bytes(heads);
     const int hd = C / heads;
-    const int grid = (int)(geo.total_windows < num_sms ? geo.total_windows : num_sms);
+    // CTA c takes windows c, c + grid, ...: with gcd(grid, windows per image) > 1 the (slower) wrapped windows of the last window
+    // column pile up on a few CTAs (148 and 32 x 32 share the factor 4: a quarter of the CTAs got all of them, +50 % run time
+    // at 16 x 16 windows).  A grid size coprime to the window count spreads them evenly; it costs at most a few idle SMs.
+    auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+    int grid = (int)(geo.total_windows < num_sms ? geo.total_windows : num_sms);
+    if (shift > 0 && geo.total_windows > num_sms)
+        while (grid > 1 && gcd(grid, geo.nW) != 1) --grid;
     cudaError_t e;
     if (hd == 16) {
         auto kern = window_attn_win8_kernel<16>;

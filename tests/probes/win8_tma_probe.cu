@@ -25,6 +25,7 @@ struct Params { int hd, vmode; };
 __global__ void __launch_bounds__(160) probe(const __grid_constant__ CUtensorMap m_full, const __grid_constant__ CUtensorMap m_ra,
                                              const __grid_constant__ CUtensorMap m_rb, const __grid_constant__ CUtensorMap o_full,
                                              const __grid_constant__ CUtensorMap o_ra, const __grid_constant__ CUtensorMap o_rb,
+                                             const __grid_constant__ CUtensorMap o_map4, int clip_stores,
                                              __nv_bfloat16* dump, float* S_out, float* O_out, Params p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t bar_ld, bar_mma;
@@ -123,6 +124,13 @@ __global__ void __launch_bounds__(160) probe(const __grid_constant__ CUtensorMap
     __syncthreads();
     if (tid == 128) {
         tma::store_3d(&o_full, stg, 0, SHIFT, SHIFT);
+        if (clip_stores) {        // the wrapped window as four full boxes, the out-of-image parts clipped by the TMA unit
+            const int x0 = WS + SHIFT, y0 = WS + SHIFT;
+            tma::store_4d(&o_map4, stg + 8192, 0, x0, y0, 0);
+            tma::store_4d(&o_map4, stg + 8192, 0, x0 - W, y0, 0);
+            tma::store_4d(&o_map4, stg + 8192, 0, x0, y0 - H, 0);
+            tma::store_4d(&o_map4, stg + 8192, 0, x0 - W, y0 - H, 0);
+        } else
         for (int ty = 0; ty < WS; ++ty) {
             const int ys = (WS + ty + SHIFT) % H;
             tma::store_3d(&o_ra, stg + 8192 + ty * 1024, 0, WS + SHIFT, ys);
@@ -142,6 +150,7 @@ static float bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 int main(int argc, char** argv) {
     Params p{argc > 1 ? atoi(argv[1]) : 16, argc > 2 ? atoi(argv[2]) : 0};
+    const int clip_stores = argc > 3 ? atoi(argv[3]) : 0;
     std::vector<__nv_bfloat16> qkv((size_t)H * W * C3);
     std::vector<float> qf(qkv.size());
     unsigned s = 12345u;
@@ -159,7 +168,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&d_O, 4 * 128 * 32 * 4));
     CK(cudaMemcpy(d_qkv, qkv.data(), qkv.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemset(d_out, 0, (size_t)H * W * C * 2));
-    CUtensorMap m_full, m_ra, m_rb, o_full, o_ra, o_rb;
+    CUtensorMap m_full, m_ra, m_rb, o_full, o_ra, o_rb, o_map4;
     {
         const long long dims[3] = {C3, W, H}, strides[2] = {C3, (long long)W * C3};
         const int bf_[3] = {64, 8, 8}, ba[3] = {64, WS - SHIFT, 1}, bb[3] = {64, SHIFT, 1};
@@ -170,9 +179,14 @@ int main(int argc, char** argv) {
             !tma::make_map_bf16(&o_ra, d_out, 3, odims, ostr, ba, CU_TENSOR_MAP_L2_PROMOTION_NONE) ||
             !tma::make_map_bf16(&o_rb, d_out, 3, odims, ostr, bb, CU_TENSOR_MAP_L2_PROMOTION_NONE)) { printf("tensor map encode failed\n"); return 2; }
     }
+    {
+        const long long d4[4] = {C, W, H, 1}, s4[3] = {C, (long long)W * C, (long long)H * W * C};
+        const int b4[4] = {64, 8, 8, 1};
+        if (!tma::make_map_bf16(&o_map4, d_out, 4, d4, s4, b4, CU_TENSOR_MAP_L2_PROMOTION_NONE)) { printf("map4 encode failed\n"); return 2; }
+    }
     const size_t smem = 4 * OP_BYTES + 1024;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    probe<<<1, 160, smem>>>(m_full, m_ra, m_rb, o_full, o_ra, o_rb, d_dump, d_S, d_O, p);
+    probe<<<1, 160, smem>>>(m_full, m_ra, m_rb, o_full, o_ra, o_rb, o_map4, clip_stores, d_dump, d_S, d_O, p);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     std::vector<__nv_bfloat16> dump(3 * OP_BYTES / 2), out((size_t)H * W * C);

@@ -31,6 +31,17 @@ int main(int argc, char** argv) {
         cudaError_t e = cudaDeviceSynchronize();
         if (st != 0 || e != cudaSuccess) { printf("error %d %s\n", st, cudaGetErrorString(e)); return 1; }
     }
+    {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a);
+        for (int rep = 0; rep < 5; ++rep) window_attn_win8(qkv, table, out, ws, B, H, W, C, heads, shift, 0.25f, -100.f, 148, true, 0);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        printf("kernel time (B=%d, %dx%d tokens, C=%d): %.3f ms\n", B, H, W, C, ms / 5);
+    }
     static long long t[4][128][12];
     cudaMemcpyFromSymbol(t, g_trace, sizeof(t));
     const long long t0 = t[2][0][0];
@@ -39,7 +50,7 @@ int main(int argc, char** argv) {
         const int g = n & 1;
         printf("%3d |", n);
         for (int e = 0; e < 7; ++e) printf(" %7lld", t[g][n][e] ? t[g][n][e] - t0 : -1);
-        printf(" [%lld %lld %lld] |", t[g][n][7] - t0, t[g][n][8] - t0, t[g][n][9] - t0);
+        printf(" [%lld %lld %lld] exp[%lld %lld] |", t[g][n][7] - t0, t[g][n][8] - t0, t[g][n][9] - t0, t[g][n][10] - t0, t[g][n][11] - t0);
         for (int e = 0; e < 7; ++e) printf(" %7lld", t[2][n][e] ? t[2][n][e] - t0 : -1);
         printf("\n");
     }

@@ -12,7 +12,7 @@ reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 which = sys.argv[2] if len(sys.argv) > 2 else "all"
 g = torch.Generator(device="cuda").manual_seed(0)
 B = 32
-cases = {"1": (256, 192, 12, 8, 2), "2": (128, 384, 12, 8, 2), "3": (64, 768, 12, 32, 0)}
+cases = {"1": (256, 192, 12, 8, 2), "1s0": (256, 192, 12, 8, 0), "2": (128, 384, 12, 8, 2), "2s0": (128, 384, 12, 8, 0), "3": (64, 768, 12, 32, 0)}
 for key, (h, C, heads, ws, shift) in cases.items():
     if which not in ("all", key):
         continue
