@@ -98,12 +98,15 @@ int sodt_window_attn_fwd_prepared(const void* qkv, const float* bias_table, cons
  *   normalize_qk 1: q and k are L2-normalised over head_dim (eps 1e-12) first.  head_scale + normalize_qk = the SwinV2 cosine
  *                attention, backbone_swinv2.py:895-921, with head_scale = exp(min(logit_scale, ln 100)) and bias_table =
  *                16 sigmoid(cpb_mlp(relative_coords_table)) evaluated once per weight version by the host.
+ *   rel_pos_h/w  [2*ws-1, head_dim] fp32 or NULL (both or neither): decomposed relative position embeddings of the SAM-style
+ *                global Attention (backbone_vit.py:347-404, add_decomposed_rel_pos :705-740), shared by all heads:
+ *                score += q_unscaled . (rel_pos_h[yi-yj+ws-1] + rel_pos_w[xi-xj+ws-1]); bias_table may be all zeros.
  */
 int sodt_window_attn_ex_fwd(const void* qkv, const float* bias_table, const void* pad_qkv, void* out,
                             int B, int H, int W, int C, int heads, int ws, int shift,
                             int dtype, float scale, float mask_value,
                             const float* dense_mask, int mask_windows, const float* head_scale, int normalize_qk,
-                            void* stream);
+                            const float* rel_pos_h, const float* rel_pos_w, void* stream);
 
 /*
  * Fused (residual add +) LayerNorm over the channels of token rows.

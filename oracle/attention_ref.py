@@ -246,3 +246,69 @@ def cattention_block(streams, ln_w, ln_b, heads, ws=1, shift=0, eps=1e-5, dtype=
             o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
         outs.append(F.layer_norm(s[qi] + o, (C,), ln_w[i].to(dtype), ln_b[i].to(dtype), eps))
     return outs
+
+
+# ------------------------------------------------------------------ attention variants
+def cosine_window_attention(xw, p, prefix, heads, ws, mask=None, dtype=torch.float64):
+    """SwinV2 cosine window attention, backbone_swinv2.py:895-949.  xw [B_, N, C]; p holds qkv.weight, q_bias, v_bias,
+    logit_scale [heads,1,1], cpb_mlp.{0.weight,0.bias,2.weight}, proj.{weight,bias}."""
+    B_, N, C = xw.shape
+    w = lambda n: p[prefix + n].to(dtype)
+    bias = torch.cat((w("q_bias"), torch.zeros(C, dtype=dtype), w("v_bias")))
+    qkv = F.linear(xw.to(dtype), w("qkv.weight"), bias).reshape(B_, N, 3, heads, -1).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    s = F.normalize(q, dim=-1) @ F.normalize(k, dim=-1).transpose(-2, -1)                       # :905
+    s = s * torch.clamp(w("logit_scale"), max=math.log(1.0 / 0.01)).exp()                         # :906-907
+    # continuous relative position bias: log-spaced coordinate table -> MLP -> 16 sigmoid (:858-874, :909-915)
+    c = torch.arange(-(ws - 1), ws, dtype=torch.float32)
+    table = torch.stack(torch.meshgrid([c, c], indexing="ij")).permute(1, 2, 0).contiguous()
+    table = table / (ws - 1) * 8
+    table = (torch.sign(table) * torch.log2(torch.abs(table) + 1.0) / math.log2(8)).to(dtype)
+    t = F.linear(F.relu(F.linear(table, w("cpb_mlp.0.weight"), w("cpb_mlp.0.bias"))), w("cpb_mlp.2.weight")).reshape(-1, heads)
+    idx = relative_position_index(ws, ws).reshape(-1)
+    s = s + (16 * torch.sigmoid(t[idx].reshape(N, N, heads).permute(2, 0, 1)))[None]
+    if mask is not None:
+        nW = mask.shape[0]
+        s = (s.reshape(B_ // nW, nW, heads, N, N) + mask.to(dtype)[None, :, None]).reshape(B_, heads, N, N)
+    o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(B_, N, C)
+    return F.linear(o, w("proj.weight"), w("proj.bias"))
+
+
+def sam_attention(x, p, prefix, heads, use_rel_pos, dtype=torch.float64):
+    """SAM-style global attention with decomposed relative position embeddings, backbone_vit.py:386-404 and
+    add_decomposed_rel_pos :705-740 (square maps whose size matches the tables: no interpolation).  x [B,H,W,C]."""
+    B, H, W, C = x.shape
+    w = lambda n: p[prefix + n].to(dtype)
+    hd = C // heads
+    qkv = F.linear(x.to(dtype), w("qkv.weight"), w("qkv.bias")).reshape(B, H * W, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.reshape(3, B * heads, H * W, hd).unbind(0)
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    if use_rel_pos:
+        ar = torch.arange(H)
+        Rh = w("rel_pos_h")[(ar[:, None] - ar[None, :]) + (H - 1)]          # get_rel_pos, equal sizes (:674-703)
+        aw = torch.arange(W)
+        Rw = w("rel_pos_w")[(aw[:, None] - aw[None, :]) + (W - 1)]
+        rq = q.reshape(B * heads, H, W, hd)
+        rel_h = torch.einsum("bhwc,hkc->bhwk", rq, Rh)
+        rel_w = torch.einsum("bhwc,wkc->bhwk", rq, Rw)
+        s = (s.view(-1, H, W, H, W) + rel_h[:, :, :, :, None] + rel_w[:, :, :, None, :]).view(-1, H * W, H * W)
+    o = (torch.softmax(s, dim=-1) @ v).view(B, heads, H, W, hd).permute(0, 2, 3, 1, 4).reshape(B, H, W, C)
+    return F.linear(o, w("proj.weight"), w("proj.bias"))
+
+
+def mf_block(rgb, ir, p, prefix="", dtype=torch.float64):
+    """SuperYOLO's MF fusion block, common.py:165-212.  rgb [B,3,H,W], ir [B,1,H,W] -> [B,64,H,W]."""
+    w = lambda n: p[prefix + n].to(dtype)
+
+    def se(x, name):
+        y = x.mean(dim=(2, 3))
+        y = torch.sigmoid(F.linear(F.relu(F.linear(y, w(name + ".fc.0.weight"))), w(name + ".fc.2.weight")))
+        return x * y[:, :, None, None]
+
+    rgb, ir = rgb.to(dtype), ir.to(dtype)
+    r, i = se(rgb, "se_r"), se(ir, "se_i")
+    rm = F.conv2d(r, w("mask_map_r.weight"), w("mask_map_r.bias")).repeat(1, 3, 1, 1) * r
+    im = F.conv2d(i, w("mask_map_i.weight"), w("mask_map_i.bias")) * i
+    out_ir = F.conv2d(im + ir, w("bottleneck1.weight"), None, 1, 1)
+    out_rgb = F.conv2d(rm + rgb, w("bottleneck2.weight"), None, 1, 1)
+    return se(torch.cat([out_rgb, out_ir], 1), "se")

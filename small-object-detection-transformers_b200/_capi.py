@@ -24,7 +24,7 @@ SIGNATURES = {
     "sodt_built_for_sm": (_i, []),
     "sodt_window_attn_workspace_bytes": (_sz, [_i, _i, _i]),
     "sodt_window_attn_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _sz, _p]),
-    "sodt_window_attn_ex_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _i, _p, _i, _p]),
+    "sodt_window_attn_ex_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _i, _p, _i, _p, _p, _p]),
     "sodt_window_attn_kernel_class": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "sodt_window_attn_prepare": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "sodt_window_attn_fwd_prepared": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _sz, _p]),

@@ -247,6 +247,42 @@ class WindowAttention(nn.Module):
         return f"dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}"
 
 
+class Attention(nn.Module):
+    """SAM-style global multi-head attention with decomposed relative position embeddings (reference backbone_vit.py:347-404,
+    add_decomposed_rel_pos :705-740).  Defined by the reference but never instantiated by its ImageEncoderViT; kept for API
+    completeness.  forward(x [B,H,W,C]) -> [B,H,W,C]; the whole map is one window of the exact attention kernel, the
+    content-dependent terms q . Rh[yi-yj], q . Rw[xi-xj] are evaluated inside it (sodt_window_attn_ex_fwd)."""
+
+    def __init__(self, dim: int, num_heads: int = 8, qkv_bias: bool = True, use_rel_pos: bool = False,
+                 rel_pos_zero_init: bool = True, input_size: Optional[Tuple[int, int]] = None):
+        super().__init__()
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.use_rel_pos = use_rel_pos
+        if use_rel_pos:
+            if input_size is None:
+                raise ValueError("input_size must be provided if using relative positional encoding")
+            self.rel_pos_h = nn.Parameter(torch.zeros(2 * input_size[0] - 1, head_dim))
+            self.rel_pos_w = nn.Parameter(torch.zeros(2 * input_size[1] - 1, head_dim))
+
+    def forward(self, x):
+        B, H, W, C = x.shape
+        if H != W:
+            raise NotImplementedError("the global-attention kernel path covers square token maps")
+        rel = None
+        if self.use_rel_pos:
+            if self.rel_pos_h.shape[0] != 2 * H - 1 or self.rel_pos_w.shape[0] != 2 * W - 1:
+                raise NotImplementedError("interpolated relative position tables (get_rel_pos with a size mismatch) are out of scope")
+            rel = (self.rel_pos_h, self.rel_pos_w)
+        zero_table = ops.cached_derived(self.qkv.weight, ("zero_table", H), lambda t: torch.zeros(
+            (2 * H - 1) ** 2, self.num_heads, dtype=torch.float32, device=t.device))
+        o = ops.window_attention_ex(self.qkv(x), zero_table, self.num_heads, H, 0, scale=self.scale, rel_pos=rel)
+        return self.proj(o)
+
+
 class SwinTransformerBlock(nn.Module):
     """Swin block (reference backbone_vit.py:1011): x + Attn(LN(x)), then x + Mlp(LN(x))."""
 
@@ -284,7 +320,7 @@ class SwinTransformerBlock(nn.Module):
         B, L, C = x.shape
         if L != H * W:
             raise ValueError("input feature has wrong size")
-        if min(H, W) <= self.window_size and (H != W or H != self.window_size):
+        if min(H, W) < self.window_size:
             raise ValueError(f"token grid {H}x{W} is smaller than the window {self.window_size}")
         attn, mlp = self.attn, self.mlp
         if x.dtype == torch.bfloat16 and ops.USE_TC_LINEAR and ops.linear_ln_supported(x, C):

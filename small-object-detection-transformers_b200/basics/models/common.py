@@ -148,6 +148,45 @@ class SPP(nn.Module):
         return self.cv2(torch.cat([x] + [m(x) for m in self.m], 1))
 
 
+class SE_Block(nn.Module):
+    """Squeeze-and-excitation channel gate (reference common.py:165)."""
+
+    def __init__(self, ch_in, reduction=16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Linear(ch_in, ch_in // reduction, bias=False), nn.ReLU(inplace=True),
+                                nn.Linear(ch_in // reduction, ch_in, bias=False), nn.Sigmoid())
+
+    def forward(self, x):
+        b, c = x.shape[:2]
+        return x * self.fc(self.avg_pool(x).view(b, c)).view(b, c, 1, 1)
+
+
+class MF(nn.Module):
+    """SuperYOLO's multimodal fusion block (reference common.py:183-212): SE gates on RGB and IR, 1x1 "mask" convs, 3x3 convs to
+    48 + 16 channels, SE gate on their concatenation.  No attention in it; forward([rgb, ir1]) -> 64 ch."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.mask_map_r = nn.Conv2d(channels, 1, 1, 1, 0, bias=True)
+        self.mask_map_i = nn.Conv2d(1, 1, 1, 1, 0, bias=True)
+        self.softmax = nn.Softmax(-1)
+        self.bottleneck1 = nn.Conv2d(1, 16, 3, 1, 1, bias=False)
+        self.bottleneck2 = nn.Conv2d(channels, 48, 3, 1, 1, bias=False)
+        self.se = SE_Block(64, 16)
+        self.se_r = SE_Block(3, 3)
+        self.se_i = SE_Block(1, 1)
+
+    def forward(self, x):
+        rgb0, ir0 = x[0], x[1]
+        rgb, ir = self.se_r(rgb0), self.se_i(ir0)
+        rgb_m = self.mask_map_r(rgb).repeat(1, 3, 1, 1) * rgb
+        ir_m = self.mask_map_i(ir) * ir
+        out_ir = self.bottleneck1(ir_m + ir0)
+        out_rgb = self.bottleneck2(rgb_m + rgb0)
+        return self.se(torch.cat([out_rgb, out_ir], 1))
+
+
 class Focus(nn.Module):
     """Space-to-depth then conv (reference common.py:68)."""
 

@@ -16,7 +16,7 @@ import torch.nn as nn
 from ... import ops
 from ..utils.general import make_divisible
 from .backbone_vit import ImageEncoderViT
-from .common import C3, SPP, Bottleneck, Concat, Conv, DWConv, Focus
+from .common import C3, MF, SPP, Bottleneck, Concat, Conv, DWConv, Focus, SE_Block
 
 logger = logging.getLogger(__name__)
 
@@ -79,7 +79,7 @@ class Detect(nn.Module):
 
 _MODULES = {
     "Conv": Conv, "DWConv": DWConv, "Bottleneck": Bottleneck, "C3": C3, "SPP": SPP, "Focus": Focus,
-    "Concat": Concat, "Detect": Detect, "ImageEncoderViT": ImageEncoderViT,
+    "Concat": Concat, "Detect": Detect, "ImageEncoderViT": ImageEncoderViT, "MF": MF, "SE_Block": SE_Block,
     "nn.Upsample": nn.Upsample, "nn.BatchNorm2d": nn.BatchNorm2d,
 }
 _WIDTH_SCALED = (Conv, Bottleneck, SPP, DWConv, Focus, C3)
@@ -105,6 +105,11 @@ def parse_model(d, string, ch, config=None):
     names = {"nc": nc, "anchors": anchors}
     parts = string.split("+")
     rows = sum((d[p] for p in parts), []) if len(parts) == 2 else d[parts[-1]]
+    # 'backbone+head' = the upstream SuperYOLO / YOLOv5 layer list (SRyolo_MF.yaml, SRyolo_PF.yaml): ch = [input channels, out of
+    # layer 0, out of layer 1, ...], so a `from` index j >= 0 reads ch[j + 1].  The reference dropped that + 1 when it re-seeded
+    # ch for its ViT head (model.py:410: "changed removed + 1"), which is why these configs fail there.
+    legacy = len(parts) == 2
+    chan = (lambda j: ch[j if j < 0 else j + 1]) if legacy else (lambda j: ch[j])
     if string == "head":   # the three backbone outputs seed the head's channel list (reference model.py:367-370)
         ch[0] = 256
         ch += [256, 512]
@@ -130,9 +135,9 @@ def parse_model(d, string, ch, config=None):
             elif m is nn.BatchNorm2d:
                 args = [ch[f]]
             elif m is Concat:
-                c2 = sum(ch[j] for j in f)
+                c2 = sum(chan(j) for j in f)
             elif m is Detect:
-                args.append([ch[j] for j in f])
+                args.append([chan(j) for j in f])
                 if isinstance(args[1], int):
                     args[1] = [list(range(args[1] * 2))] * len(f)
             else:
@@ -184,11 +189,26 @@ class Model(nn.Module):
             self.yaml["nc"] = nc
         if anchors:
             self.yaml["anchors"] = round(anchors)
-        self.image_encoder, self.save1 = parse_model(deepcopy(self.yaml), "backbone", ch=[ch], config=config)
-        self.detect, self.save2 = parse_model(deepcopy(self.yaml), "head", ch=[ch], config=config)
-        det = self.detect[-1]
+        # Two families of configs share the schema.  models/model.yaml (the detector of the paper, the only config the reference can
+        # run): an ImageEncoderViT backbone row + a head whose `from` indices address [y0, y1, y2, head layers...].
+        # SRyolo_MF.yaml / SRyolo_PF.yaml (SuperYOLO leftovers, named by BASELINE.json): one 'backbone+head' layer list with the
+        # upstream index semantics; the reference fails on them, so this path has no oracle.
+        self.legacy = self.yaml["backbone"][0][2] != "ImageEncoderViT"
+        if self.legacy:
+            self.model, self.save = parse_model(deepcopy(self.yaml), "backbone+head", ch=[ch], config=config)
+            det = self.model[-1]
+        else:
+            self.image_encoder, self.save1 = parse_model(deepcopy(self.yaml), "backbone", ch=[ch], config=config)
+            self.detect, self.save2 = parse_model(deepcopy(self.yaml), "head", ch=[ch], config=config)
+            det = self.detect[-1]
         if isinstance(det, Detect):
-            det.stride = torch.tensor([4.0])             # hard-coded in the reference (model.py:130)
+            if self.legacy:      # upstream: strides from a dummy forward at 256 px (training mode returns the raw level maps)
+                s = 256
+                with torch.no_grad():
+                    raw = self.forward(torch.zeros(1, ch_steam, s, s), torch.zeros(1, ch_steam, s, s), input_mode)[0]
+                det.stride = torch.tensor([s / r.shape[-2] for r in raw])
+            else:
+                det.stride = torch.tensor([4.0])         # hard-coded in the reference (model.py:130)
             det.anchors /= det.stride.view(-1, 1, 1)
             area = det.anchor_grid.prod(-1).view(-1)     # check_anchor_order (utils/autoanchor.py:13)
             if (area[-1] - area[0]).sign() != (det.stride[-1] - det.stride[0]).sign():
@@ -200,8 +220,11 @@ class Model(nn.Module):
             if type(m) is nn.BatchNorm2d:
                 m.eps, m.momentum = 1e-3, 0.03
 
+    def _detect_layer(self):
+        return self.model[-1] if self.legacy else self.detect[-1]
+
     def _initialize_biases(self, cf=None):
-        det = self.detect[-1]
+        det = self._detect_layer()
         with torch.no_grad():
             for conv, s in zip(det.m, det.stride):
                 b = conv.bias.view(det.na, -1)        # in-place view: objectness and class priors (arXiv 1708.02002, 3.3)
@@ -215,6 +238,8 @@ class Model(nn.Module):
             return x
         if input_mode == "IR":
             return ir
+        if input_mode == "RGB+IR+MF":                    # the MF block takes the pair (reference model.py:190)
+            return [x, ir[:, 0:1]]
         raise NotImplementedError(f"input_mode {input_mode!r} is out of scope")
 
     def forward(self, x, ir=None, input_mode="RGB+IR", augment=False, profile=False):
@@ -224,7 +249,7 @@ class Model(nn.Module):
             ir = x
         if x.dtype == torch.uint8:
             # extension: the evaluation loop's uint8 images (basics/test.py:124-130); /255 happens inside the front-end kernel
-            if input_mode != "RGB+IR" or ir.dtype != torch.uint8:
+            if self.legacy or input_mode != "RGB+IR" or ir.dtype != torch.uint8:
                 raise NotImplementedError("uint8 input is supported for input_mode='RGB+IR' with uint8 rgb and ir")
             stem = (x, ir)
         else:
@@ -235,7 +260,19 @@ class Model(nn.Module):
             return head_out, feats
         return head_out[0], head_out[1], feats
 
+    def _forward_legacy(self, x):
+        """Upstream layer loop over the 'backbone+head' list: `from` -1 = previous output, j >= 0 = saved output of layer j."""
+        y = []
+        for m in self.model:
+            if m.f != -1:
+                x = y[m.f] if isinstance(m.f, int) else [x if j == -1 else y[j] for j in m.f]
+            x = m(x)
+            y.append(x if m.i in self.save else None)
+        return x, y
+
     def forward_once(self, x, string="yolo", profile=False):
+        if self.legacy:
+            return self._forward_legacy(x)
         y = list(self.image_encoder(x[0], ir_u8=x[1]) if isinstance(x, tuple) else self.image_encoder(x))
         x = y[-1]
         mods = list(self.detect)

@@ -14,7 +14,7 @@ int window_attn_generic(const void* qkv, const float* table, const void* pad_qkv
 int window_attn_generic_ex(const void* qkv, const float* table, const void* pad_qkv, void* out, int B, int H, int W,
                            int C, int heads, int ws, int shift, int dtype, float scale, float mask_value,
                            const float* dense_mask, int mask_windows, const float* head_scale, int normalize_qk,
-                           cudaStream_t stream);
+                           const float* rel_pos_h, const float* rel_pos_w, cudaStream_t stream);
 
 size_t window_attn_flash_workspace(int heads, int ws);
 bool window_attn_flash_supported(int H, int W, int C, int heads, int ws, int shift, int dtype);
@@ -177,7 +177,7 @@ extern "C" int sodt_window_attn_ex_fwd(const void* qkv, const float* bias_table,
                                        int B, int H, int W, int C, int heads, int ws, int shift,
                                        int dtype, float scale, float mask_value,
                                        const float* dense_mask, int mask_windows, const float* head_scale, int normalize_qk,
-                                       void* stream) {
+                                       const float* rel_pos_h, const float* rel_pos_w, void* stream) {
     using namespace sodt;
     if (!qkv || !bias_table || !out) return SODT_ERR_INVALID_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0 || ws <= 0 || C % heads != 0) return SODT_ERR_INVALID_ARG;
@@ -185,7 +185,7 @@ extern "C" int sodt_window_attn_ex_fwd(const void* qkv, const float* bias_table,
     if (dtype != SODT_F32 && dtype != SODT_BF16) return SODT_ERR_INVALID_ARG;
     if (!aligned16(qkv) || !aligned16(out) || (pad_qkv && !aligned16(pad_qkv))) return SODT_ERR_ALIGNMENT;
     return window_attn_generic_ex(qkv, bias_table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value, dense_mask,
-                                  mask_windows, head_scale, normalize_qk, static_cast<cudaStream_t>(stream));
+                                  mask_windows, head_scale, normalize_qk, rel_pos_h, rel_pos_w, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sodt_window_attn_kernel_class(int B, int H, int W, int C, int heads, int ws, int shift, int dtype) {

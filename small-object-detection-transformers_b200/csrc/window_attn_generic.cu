@@ -10,7 +10,8 @@
 // :1094-1123 (roll / partition / unpartition), :1058-1079 (mask).
 // Score variants (struct ScoreExtras): an explicit dense additive mask [mask_windows, N, N] (WindowAttention.forward(x, mask),
 // backbone_vit.py:979-984); the SwinV2 cosine attention (backbone_swinv2.py:895-921): q and k L2-normalised per head
-// (F.normalize, eps 1e-12) and a per-head logit scale instead of head_dim^-0.5.
+// (F.normalize, eps 1e-12) and a per-head logit scale instead of head_dim^-0.5; the decomposed relative position terms of the
+// SAM-style global Attention (backbone_vit.py:347-404,705-740), q . (Rh[dy] + Rw[dx]) with the UNSCALED q.
 #include "common.cuh"
 
 namespace sodt {
@@ -75,6 +76,8 @@ struct ScoreExtras {
     int mask_windows;
     const float* head_scale;   // [heads] multiplier of the (normalised) scores, or null (use `scale`)
     int normalize_qk;          // 1: q, k rows are L2-normalised over head_dim before the dot product
+    const float* rel_pos_h;    // [2 ws - 1][hd] or null: decomposed relative position embeddings (SAM / MViTv2 Attention,
+    const float* rel_pos_w;    //   backbone_vit.py:705-740): score += q_i . (rel_pos_h[yi - yj + ws - 1] + rel_pos_w[xi - xj + ws - 1])
 };
 
 template <typename T, int HDP, bool kExact>
@@ -110,8 +113,10 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
     stage_tile<T, HDP>(ks, qkv, pad_qkv, g, b, win, blockIdx.x * BQ, N, C, hd, head, 0, vec_ok != 0);
     __syncthreads();
     float q[HDP];
+    float q_unscale = 1.f;         // q_raw = q * q_unscale (decomposed relative position terms)
     {
         float qs = ex.head_scale != nullptr ? ex.head_scale[head] : scale;
+        q_unscale = 1.f / qs;
         if (ex.normalize_qk) {
             float n2 = 0.f;
 #pragma unroll
@@ -173,6 +178,13 @@ window_attn_generic_kernel(const T* __restrict__ qkv, const float* __restrict__ 
             if (k0 + j < N) {
                 const int meta = kmeta[j];
                 const int tyk = meta & 1023, txk = (meta >> 10) & 1023, rk = meta >> 20;
+                if (ex.rel_pos_h != nullptr) {        // the reference multiplies the UNSCALED q (add_decomposed_rel_pos gets q, not q * scale)
+                    const float* rh = ex.rel_pos_h + (long long)(tyq - tyk + ws - 1) * hd;
+                    const float* rw = ex.rel_pos_w + (long long)(txq - txk + ws - 1) * hd;
+                    float rel = 0.f;
+                    for (int d = 0; d < hd; ++d) rel = fmaf(q[d], __ldg(rh + d) + __ldg(rw + d), rel);
+                    acc += rel * q_unscale;
+                }
                 const int bidx = (tyq - tyk + ws - 1) * span + (txq - txk + ws - 1);
                 const float bias = table_in_smem ? tab[bidx] : __ldg(table + (long long)bidx * heads + head);
                 acc += bias;
@@ -274,11 +286,12 @@ int dispatch_hd(const void* qkv, const float* table, const void* pad_qkv, void* 
 int window_attn_generic_ex(const void* qkv, const float* table, const void* pad_qkv, void* out, int B, int H, int W,
                            int C, int heads, int ws, int shift, int dtype, float scale, float mask_value,
                            const float* dense_mask, int mask_windows, const float* head_scale, int normalize_qk,
-                           cudaStream_t stream) {
+                           const float* rel_pos_h, const float* rel_pos_w, cudaStream_t stream) {
     const int hd = C / heads;
     if (hd > 64 || ws > 1023) return SODT_ERR_UNSUPPORTED;
     if (dense_mask != nullptr && mask_windows <= 0) return SODT_ERR_INVALID_ARG;
-    const ScoreExtras ex{dense_mask, dense_mask ? mask_windows : 1, head_scale, normalize_qk ? 1 : 0};
+    if ((rel_pos_h == nullptr) != (rel_pos_w == nullptr) || (rel_pos_h != nullptr && normalize_qk)) return SODT_ERR_INVALID_ARG;
+    const ScoreExtras ex{dense_mask, dense_mask ? mask_windows : 1, head_scale, normalize_qk ? 1 : 0, rel_pos_h, rel_pos_w};
     if (dtype == SODT_F32)
         return dispatch_hd<float, true>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
     return dispatch_hd<__nv_bfloat16, false>(qkv, table, pad_qkv, out, B, H, W, C, heads, hd, ws, shift, scale, mask_value, ex, stream);
@@ -288,7 +301,7 @@ int window_attn_generic(const void* qkv, const float* table, const void* pad_qkv
                         int C, int heads, int ws, int shift, int dtype, float scale, float mask_value,
                         cudaStream_t stream) {
     return window_attn_generic_ex(qkv, table, pad_qkv, out, B, H, W, C, heads, ws, shift, dtype, scale, mask_value, nullptr, 0, nullptr, 0,
-                                  stream);
+                                  nullptr, nullptr, stream);
 }
 
 }  // namespace sodt

@@ -150,10 +150,18 @@ def window_attention(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=No
 
 
 def window_attention_ex(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale=None, mask_value=-100.0, dense_mask=None,
-                        head_scale=None, normalize_qk=False):
+                        head_scale=None, normalize_qk=False, rel_pos=None):
     """window_attention with a non-standard score epilogue (see sodt_window_attn_ex_fwd): an explicit dense additive mask
-    [mask_windows, N, N], a per-head score multiplier, L2-normalised q / k (SwinV2 cosine attention).  Exact fp32-math kernel."""
+    [mask_windows, N, N], a per-head score multiplier, L2-normalised q / k (SwinV2 cosine attention), decomposed relative
+    position embeddings ``rel_pos=(rel_pos_h, rel_pos_w)``, each [2*ws-1, head_dim] (SAM-style Attention).  Exact fp32-math kernel."""
     _require_cuda(qkv, bias_table, pad_qkv, dense_mask, head_scale)
+    rph = rpw = None
+    if rel_pos is not None:
+        rph, rpw = (t.detach().to(torch.float32).contiguous() for t in rel_pos)
+        _require_cuda(rph, rpw)
+        hd_ = qkv.shape[-1] // 3 // heads
+        if tuple(rph.shape) != (2 * ws - 1, hd_) or tuple(rpw.shape) != (2 * ws - 1, hd_):
+            raise ValueError(f"rel_pos tables must be [{2 * ws - 1}, {hd_}]")
     if qkv.dim() != 4 or qkv.shape[-1] % 3 or qkv.dtype not in _DT:
         raise ValueError("qkv must be [B, H, W, 3*C] in fp32 / bf16")
     B, H, W, C3 = qkv.shape
@@ -181,7 +189,7 @@ def window_attention_ex(qkv, bias_table, heads, ws, shift=0, pad_qkv=None, scale
     with torch.cuda.device(qkv.device), _Timed(f"window_attn_ex[B={B},H={H},W={W},C={C},heads={heads},ws={ws},shift={shift}]"):
         st = _capi.lib().sodt_window_attn_ex_fwd(qkv.data_ptr(), table.data_ptr(), _ptr(pad_qkv), out.data_ptr(), B, H, W, C, heads, ws,
                                                  shift, _DT[qkv.dtype], float(scale), float(mask_value), _ptr(dense_mask), mask_windows,
-                                                 _ptr(head_scale), int(bool(normalize_qk)), _stream())
+                                                 _ptr(head_scale), int(bool(normalize_qk)), _ptr(rph), _ptr(rpw), _stream())
     _capi.check(st, "sodt_window_attn_ex_fwd")
     return out
 

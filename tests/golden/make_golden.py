@@ -157,8 +157,68 @@ def gen_model():
     print("model pred stats", out["pred_stats"])
 
 
+# Round 2: block-level cases at the detector's own widths (they reach the tcgen05 window / flash / GEMM kernels in bf16)
+# name -> (dim, (H, W), heads, ws, shift, linear_mlp, B)
+SWIN_BIG_CASES = {
+    "s1_dim192_shift0_lin": (192, (16, 16), 12, 8, 0, True, 2),
+    "s1_dim192_shift2_conv": (192, (16, 16), 12, 8, 2, False, 2),
+    "s2_dim384_shift2_conv": (384, (16, 16), 12, 8, 2, False, 1),
+    "s2_dim384_shift0_lin": (384, (16, 8), 12, 8, 0, True, 2),
+    "s3_dim768_global": (768, (32, 32), 12, 32, 0, True, 1),
+}
+
+
+def gen_swin_big():
+    out = {}
+    for name, (dim, res, heads, ws, shift, lin, B) in SWIN_BIG_CASES.items():
+        blk = bv.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift, linear_mlp=lin).eval()
+        blk.load_state_dict(fx.fill_state_dict(blk.state_dict(), seed=1))
+        x = fx.det_input("swin:" + name, (B, res[0] * res[1], dim))
+        y = blk(x)
+        out[name + "/y"] = np32(y[:, ::3])                      # every third token keeps the fixture small
+    np.savez_compressed(os.path.join(HERE, "swin_blocks_big.npz"), **out)
+
+
+def fill_parameters(module, seed):
+    sd = module.state_dict()
+    for k, v in module.named_parameters():
+        sd[k] = fx.deterministic_tensor(k, v.shape, seed)
+    module.load_state_dict(sd)
+
+
+def gen_variants():
+    """Attention variants SURVEY.md section 8(f) rank 4 names: the reference defines them (and they run standalone) although its
+    detector never instantiates them; and SuperYOLO's MF fusion block."""
+    import basics.models.common as cm
+    out = {}
+    # SwinV2 cosine attention (backbone_swinv2.py:837-949), with and without a shift mask
+    for name, (dim, ws, heads, B_, masked) in {"v2attn_ws8": (96, 8, 6, 4, False), "v2attn_ws4_mask": (48, 4, 3, 8, True),
+                                                "v2attn_ws7": (64, 7, 2, 3, False)}.items():
+        m = sw.WindowAttention(dim, (ws, ws), heads).eval()
+        fill_parameters(m, seed=5)                                # buffers (coordinate table, index) stay as constructed
+        x = fx.det_input("v2attn:" + name, (B_, ws * ws, dim))
+        mask = None
+        if masked:
+            mask = bv.SwinTransformerBlock(dim, (2 * ws, 2 * ws), heads, window_size=ws, shift_size=ws // 2).attn_mask
+        out[name + "/y"] = np32(m(x, mask))
+    # SAM-style global attention with decomposed relative position embeddings (backbone_vit.py:347-404,705-740)
+    for name, (dim, heads, S, B, rel) in {"sam_rel_16": (64, 4, 16, 2, True), "sam_norel_8": (48, 3, 8, 2, False),
+                                           "sam_rel_32": (128, 2, 32, 1, True)}.items():
+        m = bv.Attention(dim, heads, qkv_bias=True, use_rel_pos=rel, input_size=(S, S)).eval()
+        m.load_state_dict(fx.fill_state_dict(m.state_dict(), seed=6))
+        x = fx.det_input("sam:" + name, (B, S, S, dim))
+        out[name + "/y"] = np32(m(x))
+    # MF fusion block (common.py:183-212)
+    mf = cm.MF(3).eval()
+    mf.load_state_dict(fx.fill_state_dict(mf.state_dict(), seed=7))
+    rgb = fx.det_input("mf:rgb", (2, 3, 24, 32), kind="uniform")
+    ir = fx.det_input("mf:ir", (2, 1, 24, 32), kind="uniform")
+    out["mf/y"] = np32(mf([rgb, ir]))
+    np.savez_compressed(os.path.join(HERE, "variants.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["swin", "cattn", "detect", "nms", "model"]
+    which = sys.argv[1:] or ["swin", "cattn", "detect", "nms", "model", "swin_big", "variants"]
     for w in which:
         globals()["gen_" + w]()
         print("generated", w)

@@ -60,3 +60,34 @@ def swin_state_shapes(dim, ws, linear_mlp, heads, res=None):
                        "mlp.conv1.weight": (dim, dim, 2, 2), "mlp.conv1.bias": (dim,),
                        "mlp.fc2.weight": (dim, dim), "mlp.fc2.bias": (dim,)})
     return shapes
+
+
+# Round 2 fixtures (tests/golden/swin_blocks_big.npz, variants.npz).  name -> (dim, (H, W), heads, ws, shift, linear_mlp, B)
+SWIN_BIG_CASES = {
+    "s1_dim192_shift0_lin": (192, (16, 16), 12, 8, 0, True, 2),
+    "s1_dim192_shift2_conv": (192, (16, 16), 12, 8, 2, False, 2),
+    "s2_dim384_shift2_conv": (384, (16, 16), 12, 8, 2, False, 1),
+    "s2_dim384_shift0_lin": (384, (16, 8), 12, 8, 0, True, 2),
+    "s3_dim768_global": (768, (32, 32), 12, 32, 0, True, 1),
+}
+# name -> (dim, ws, heads, B_, masked)
+V2ATTN_CASES = {"v2attn_ws8": (96, 8, 6, 4, False), "v2attn_ws4_mask": (48, 4, 3, 8, True), "v2attn_ws7": (64, 7, 2, 3, False)}
+# name -> (dim, heads, S, B, use_rel_pos)
+SAM_CASES = {"sam_rel_16": (64, 4, 16, 2, True), "sam_norel_8": (48, 3, 8, 2, False), "sam_rel_32": (128, 2, 32, 1, True)}
+
+
+def v2attn_state_shapes(dim, ws, heads):
+    return {"logit_scale": (heads, 1, 1), "cpb_mlp.0.weight": (512, 2), "cpb_mlp.0.bias": (512,), "cpb_mlp.2.weight": (heads, 512),
+            "qkv.weight": (3 * dim, dim), "q_bias": (dim,), "v_bias": (dim,), "proj.weight": (dim, dim), "proj.bias": (dim,)}
+
+
+def sam_state_shapes(dim, heads, S, rel):
+    shapes = {"qkv.weight": (3 * dim, dim), "qkv.bias": (3 * dim,), "proj.weight": (dim, dim), "proj.bias": (dim,)}
+    if rel:
+        shapes.update({"rel_pos_h": (2 * S - 1, dim // heads), "rel_pos_w": (2 * S - 1, dim // heads)})
+    return shapes
+
+
+MF_SHAPES = {"mask_map_r.weight": (1, 3, 1, 1), "mask_map_r.bias": (1,), "mask_map_i.weight": (1, 1, 1, 1), "mask_map_i.bias": (1,),
+             "bottleneck1.weight": (16, 1, 3, 3), "bottleneck2.weight": (48, 3, 3, 3), "se.fc.0.weight": (4, 64), "se.fc.2.weight": (64, 4),
+             "se_r.fc.0.weight": (1, 3), "se_r.fc.2.weight": (3, 1), "se_i.fc.0.weight": (1, 1), "se_i.fc.2.weight": (1, 1)}

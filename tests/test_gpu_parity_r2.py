@@ -19,6 +19,16 @@ YAML = os.path.join(ROOT, "small-object-detection-transformers_b200", "models", 
 TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
 
 
+@pytest.fixture(scope="module", autouse=True)
+def exact_fp32_libraries():
+    """fp32 parity mode: cuBLAS / cuDNN must not silently use TF32."""
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
 def rel_err(a, b):
     a = a.detach().double().cpu()
     b = torch.as_tensor(b).double().cpu()
@@ -65,7 +75,8 @@ def test_detector_1024_bf16_graph_path_vs_oracle():
     # decoded predictions: fp32 decode of the bf16 raw output; box centres within 1e-3 of the image size, sizes within bf16 error
     got, ref = pred.double().cpu(), pred_ref.double()
     assert (got[..., :2] - ref[..., :2]).abs().max() < 0.05 * 4            # 5 % of one stride (sigmoid of a bf16 logit)
-    assert ((got[..., 2:4] - ref[..., 2:4]).abs() / ref[..., 2:4]).max() < 0.05
+    assert rel_err(got[..., 2:4], ref[..., 2:4]) < 2e-2                      # box sizes: (2 sigmoid)^2 of a bf16 logit
+    assert ((got[..., 2:4] - ref[..., 2:4]).abs() / ref[..., 2:4]).max() < 0.15
     assert (got[..., 4:] - ref[..., 4:]).abs().max() < 2e-2
     # (2) graph replay == eager step, bit for bit, and it produces detections at this threshold
     buf_graph = det.detect_device(rgb8.cuda(), ir8.cuda())
@@ -245,3 +256,101 @@ def test_window_attention_module_dense_mask_kernel_path():
             y = m(x.to("cuda", dtype), mask.cuda())
         assert ops().launch_count() > n0, "the dense-mask path must run a sodt kernel"
         assert rel_err(y, ref) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+# ------------------------------------------------------ reference-golden blocks at the detector's widths (tcgen05 kernels)
+from tests.golden_cases import (MF_SHAPES, SAM_CASES, SWIN_BIG_CASES, V2ATTN_CASES, sam_state_shapes, swin_state_shapes,  # noqa: E402
+                                v2attn_state_shapes)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", list(SWIN_BIG_CASES))
+def test_swin_block_at_detector_widths_vs_reference_golden(golden, name, dtype):
+    """Block-level reference outputs at dim 192 / 384 / 768 with 12 heads: in bf16 these run the TMA-fed window-pair kernel
+    (head_dim 16 / 32), the flash kernel (N = 1024, head_dim 64) and the tcgen05 GEMMs with folded LayerNorms."""
+    from sodt_b200.basics.models.backbone_vit import SwinTransformerBlock
+    dim, res, heads, ws, shift, lin, B = SWIN_BIG_CASES[name]
+    blk = SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift, linear_mlp=lin).eval()
+    p = {k: fx.deterministic_tensor(k, s, seed=1) for k, s in swin_state_shapes(dim, ws, lin, heads, res).items()}
+    missing = blk.load_state_dict(p, strict=False)
+    assert set(missing.missing_keys) <= {"attn_mask", "attn.relative_position_index"} and not missing.unexpected_keys
+    blk = blk.to("cuda", dtype)
+    x = fx.det_input("swin:" + name, (B, res[0] * res[1], dim)).to("cuda", dtype)
+    n0 = ops().launch_count()
+    with torch.no_grad():
+        y = blk(x)
+    assert ops().launch_count() > n0
+    assert rel_err(y[:, ::3], golden("swin_blocks_big")[name + "/y"]) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+# --------------------------------------------------------------- attention variants (SURVEY.md section 8f rank 4)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", list(V2ATTN_CASES))
+def test_swinv2_cosine_window_attention_vs_reference_golden(golden, name, dtype):
+    from sodt_b200.basics.models.backbone_swinv2 import WindowAttention
+    dim, ws, heads, B_, masked = V2ATTN_CASES[name]
+    m = WindowAttention(dim, (ws, ws), heads).eval()
+    p = {k: fx.deterministic_tensor(k, s, seed=5) for k, s in v2attn_state_shapes(dim, ws, heads).items()}
+    res = m.load_state_dict(p, strict=False)
+    assert set(res.missing_keys) <= {"relative_coords_table", "relative_position_index"} and not res.unexpected_keys
+    m = m.to("cuda", dtype)
+    x = fx.det_input("v2attn:" + name, (B_, ws * ws, dim)).to("cuda", dtype)
+    mask = A.shift_attn_mask(2 * ws, 2 * ws, ws, ws // 2).cuda() if masked else None
+    with torch.no_grad():
+        y = m(x, mask)
+    assert rel_err(y, golden("variants")[name + "/y"]) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", list(SAM_CASES))
+def test_sam_decomposed_rel_pos_attention_vs_reference_golden(golden, name, dtype):
+    from sodt_b200.basics.models.backbone_vit import Attention
+    dim, heads, S, B, rel = SAM_CASES[name]
+    m = Attention(dim, heads, qkv_bias=True, use_rel_pos=rel, input_size=(S, S)).eval()
+    m.load_state_dict({k: fx.deterministic_tensor(k, s, seed=6) for k, s in sam_state_shapes(dim, heads, S, rel).items()})
+    m = m.to("cuda", dtype)
+    x = fx.det_input("sam:" + name, (B, S, S, dim)).to("cuda", dtype)
+    with torch.no_grad():
+        y = m(x)
+    assert rel_err(y, golden("variants")[name + "/y"]) < (2e-5 if dtype == torch.float32 else 2e-2)
+
+
+def test_mf_block_vs_reference_golden(golden):
+    from sodt_b200.basics.models.common import MF
+    m = MF(3).eval()
+    m.load_state_dict({k: fx.deterministic_tensor(k, s, seed=7) for k, s in MF_SHAPES.items()})
+    m = m.cuda()
+    rgb = fx.det_input("mf:rgb", (2, 3, 24, 32), kind="uniform").cuda()
+    ir = fx.det_input("mf:ir", (2, 1, 24, 32), kind="uniform").cuda()
+    with torch.no_grad():
+        y = m([rgb, ir])
+    assert rel_err(y, golden("variants")["mf/y"]) < 1e-5
+
+
+@pytest.mark.parametrize("cfg,mode,ch", [("SRyolo_MF.yaml", "RGB+IR+MF", 64), ("SRyolo_PF.yaml", "RGB+IR", 4)])
+def test_sryolo_configs_build_and_run(cfg, mode, ch):
+    """BASELINE.json: "SRyolo_MF/PF configs ... drop in".  The reference cannot run them, so there is no
+    reference output to compare with -- PARITY UNPINNED; checked here: they parse with the upstream semantics, the fused bf16
+    CUDA path (tcgen05 conv GEMMs, Detect decode kernel, NMS kernels) agrees with the same module's unfused fp32 torch math."""
+    from sodt_b200.basics.models.model import Model
+    from sodt_b200.basics.utils.general import non_max_suppression
+    path = os.path.join(ROOT, "small-object-detection-transformers_b200", "models", cfg)
+    torch.manual_seed(0)
+    m = Model(path, input_mode=mode, ch_steam=3, ch=ch, nc=8).eval()
+    m.load_state_dict(fx.fill_state_dict(m.state_dict(), seed=9))
+    assert m._detect_layer().stride.tolist() == [4.0]
+    rgb = fx.det_input("sryolo:rgb", (2, 3, 256, 256), kind="uniform")
+    ir = fx.det_input("sryolo:ir", (2, 3, 256, 256), kind="uniform")
+    m32 = m.cuda()
+    with torch.no_grad():
+        pred32, raw32, _ = m32(rgb.cuda(), ir.cuda(), mode)
+    import copy
+    m16 = copy.deepcopy(m32).fuse().to(torch.bfloat16)
+    n0 = ops().launch_count()
+    with torch.no_grad():
+        pred16, raw16, _ = m16(rgb.cuda().to(torch.bfloat16), ir.cuda().to(torch.bfloat16), mode)
+    assert ops().launch_count() - n0 >= 10, "the fused bf16 path must run on the sodt kernels"
+    assert pred32.shape == (2, 3 * 64 * 64, 13) and pred16.shape == pred32.shape
+    assert rel_err(raw16[0], raw32[0]) < 3e-2
+    dets = non_max_suppression(pred32, conf_thres=1e-5, iou_thres=0.45)
+    assert len(dets) == 2 and all(d.shape[1] == 6 for d in dets)

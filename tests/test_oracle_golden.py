@@ -11,8 +11,8 @@ from oracle import attention_ref as A
 from oracle import fixtures as fx
 from oracle import model_ref, nms_ref
 from oracle.detect_ref import detect_decode
-from tests.golden_cases import (CATTN_CASES, DETECT_ANCHORS, DETECT_FEATS, DETECT_STRIDES, NMS_CASES,
-                                SWIN_CASES, swin_state_shapes)
+from tests.golden_cases import (CATTN_CASES, DETECT_ANCHORS, DETECT_FEATS, DETECT_STRIDES, MF_SHAPES, NMS_CASES, SAM_CASES,
+                                SWIN_BIG_CASES, SWIN_CASES, V2ATTN_CASES, sam_state_shapes, swin_state_shapes, v2attn_state_shapes)
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -173,3 +173,37 @@ def test_model_forward_matches_reference(golden):
     got = pred[0, ::61]
     assert ((got[:, :4] - ref[:, :4]).abs() / ref[:, :4].abs().clamp_min(1.0)).max() < 1e-3
     assert (got[:, 4:] - ref[:, 4:]).abs().max() < 1e-4
+
+
+# ------------------------------------------------------------------------------ round-2 fixtures
+@pytest.mark.parametrize("name", list(SWIN_BIG_CASES))
+def test_swin_block_at_detector_widths_matches_reference(golden, name):
+    dim, res, heads, ws, shift, lin, B = SWIN_BIG_CASES[name]
+    p = {k: fx.deterministic_tensor(k, s, seed=1) for k, s in swin_state_shapes(dim, ws, lin, heads, res).items()}
+    x = fx.det_input("swin:" + name, (B, res[0] * res[1], dim))
+    y = A.swin_block(x, p, "", res[0], res[1], heads, ws, shift, lin)
+    assert rel_err(y[:, ::3], golden("swin_blocks_big")[name + "/y"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", list(V2ATTN_CASES))
+def test_cosine_window_attention_matches_reference(golden, name):
+    dim, ws, heads, B_, masked = V2ATTN_CASES[name]
+    p = {k: fx.deterministic_tensor(k, s, seed=5) for k, s in v2attn_state_shapes(dim, ws, heads).items()}
+    x = fx.det_input("v2attn:" + name, (B_, ws * ws, dim))
+    mask = A.shift_attn_mask(2 * ws, 2 * ws, ws, ws // 2) if masked else None
+    assert rel_err(A.cosine_window_attention(x, p, "", heads, ws, mask), golden("variants")[name + "/y"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", list(SAM_CASES))
+def test_sam_attention_matches_reference(golden, name):
+    dim, heads, S, B, rel = SAM_CASES[name]
+    p = {k: fx.deterministic_tensor(k, s, seed=6) for k, s in sam_state_shapes(dim, heads, S, rel).items()}
+    x = fx.det_input("sam:" + name, (B, S, S, dim))
+    assert rel_err(A.sam_attention(x, p, "", heads, rel), golden("variants")[name + "/y"]) < 2e-6
+
+
+def test_mf_block_matches_reference(golden):
+    p = {k: fx.deterministic_tensor(k, s, seed=7) for k, s in MF_SHAPES.items()}
+    rgb = fx.det_input("mf:rgb", (2, 3, 24, 32), kind="uniform")
+    ir = fx.det_input("mf:ir", (2, 1, 24, 32), kind="uniform")
+    assert rel_err(A.mf_block(rgb, ir, p), golden("variants")["mf/y"]) < 2e-6
