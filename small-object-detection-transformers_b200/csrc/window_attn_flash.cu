@@ -5,21 +5,25 @@
 // basics/models/backbone_vit.py:151-160), no shift.  Flash-style: one CTA owns 128 query rows of
 // one (window, head) and streams the keys / values in tiles of 128 through shared memory.
 //
-//   S = Q K^T          tcgen05.mma SS, M=128 N=128 K=64, both operands K-major (SWIZZLE_NONE canonical
-//                      layout [8-element chunk][row][16 B]), accumulator in TMEM columns [0,128)
+// Operand tiles arrive by TMA: 128 tokens of a window = 4 window rows = the (64 channels, 32, 4) box of the [B*H, W, 3C] qkv
+// image (window partition as box coordinates), landing as SWIZZLE_128B tiles of 128 rows x 128 B; the output tile leaves
+// through a TMA store of the same box shape.
+//
+//   S = Q K^T          tcgen05.mma SS, M=128 N=128 K=64, both operands K-major SWIZZLE_128B (the descriptor start address
+//                      advances 32 B per 16 channels), accumulator in TMEM columns [0,128)
 //   softmax            one thread per query row reads its S row from TMEM (tcgen05.ld 32x32b), adds the
 //                      relative-position bias (closed-form index into the shared-memory table,
 //                      conflict free: the 32 lanes of a warp are 32 consecutive tokens of one window row),
 //                      exp2 with a lazily updated running maximum, writes P as packed bf16 pairs back to
 //                      TMEM columns [128,192)
-//   O += P V           tcgen05.mma TS (A = P from TMEM, B = V MN-major from shared memory), accumulator in
+//   O += P V           tcgen05.mma TS (A = P from TMEM, B = V MN-major SWIZZLE_128B, 16 keys = 2048 B per step), accumulator in
 //                      TMEM columns [192,256); rescaled in TMEM only when a row maximum grew by > 2^8
 //
-// Warp roles: warps 0-3 softmax + epilogue (128 threads = 128 rows), warp 4 cp.async producer,
+// Warp roles: warps 0-3 softmax + epilogue (128 threads = 128 rows), warp 4 TMA producer (one lane),
 // warp 5 MMA issuer (one elected lane).  Two CTAs per SM (256 TMEM columns, ~97 KB smem each) so that one
 // CTA's softmax overlaps the other's MMAs.  No score, probability, bias or window tensor reaches HBM.
 #include "common.cuh"
-#include "tc05.cuh"
+#include "tma.cuh"
 
 namespace sodt {
 namespace {
@@ -31,7 +35,6 @@ constexpr int TN = 128;            // keys per tile
 constexpr int HD = 64;             // head dim
 constexpr int NTHREADS = 192;
 constexpr int TILE_BYTES = TM * HD * 2;   // 16 KB
-constexpr int CHUNK_STRIDE = TM * 16;     // bytes between 8-element chunks of the canonical layout
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -51,26 +54,10 @@ __global__ void prep_table_kernel(const float* __restrict__ table, float* __rest
     }
 }
 
-// 128 tokens x 64 dims of q / k / v of one head -> canonical tile.  One warp; lane = (chunk quad, token octet).
-template <int WS>
-__device__ __forceinline__ void load_tile(uint32_t dst, const __nv_bfloat16* __restrict__ qkv, long long win_base,
-                                          int W, int C3, int t0, int col0, int lane) {
-    const int tsub = lane & 7, csub = lane >> 3;
-#pragma unroll 4
-    for (int oct = 0; oct < TM / 8; ++oct) {
-        const int t = t0 + oct * 8 + tsub;
-        const int ty = t / WS, tx = t - ty * WS;
-        const __nv_bfloat16* src = qkv + (win_base + (long long)ty * W + tx) * C3 + col0;
-        const uint32_t d = dst + (oct * 8 + tsub) * 16;
-        cp_async16(d + csub * CHUNK_STRIDE, src + csub * 8);
-        cp_async16(d + (csub + 4) * CHUNK_STRIDE, src + (csub + 4) * 8);
-    }
-}
-
 template <int WS>
 __global__ void __launch_bounds__(NTHREADS, 2)
-window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __restrict__ table_t,
-                         __nv_bfloat16* __restrict__ out, int H, int W, int C, int heads, float scale) {
+window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                         const float* __restrict__ table_t, int H, int W, int C, int heads, float scale) {
     constexpr int N = WS * WS;
     constexpr int T = N / TN;
     constexpr int SPAN = 2 * WS - 1;
@@ -83,14 +70,13 @@ window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
     const int nww = W / WS, nW = (H / WS) * nww;
     const int b = blockIdx.z / nW, win = blockIdx.z - b * nW;
     const int wy = win / nww, wx = win - wy * nww;
-    const long long win_base = ((long long)b * H + wy * WS) * W + wx * WS;   // token index of the window's corner
-    const int C3 = 3 * C;
-    const uint32_t sbase = smem_u32(smem);
-    float* tab = reinterpret_cast<float*>(smem + SmemLayout::TAB);
+    const int x0 = wx * WS, y0 = b * H + wy * WS;                            // the window's corner in the [B*H, W] token image
+    const uint32_t sbase = (smem_u32(smem) + 1023u) & ~1023u;               // SWIZZLE_128B tiles: 1024-byte aligned
+    float* tab = reinterpret_cast<float*>(smem + (sbase - smem_u32(smem)) + SmemLayout::TAB);
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&bar_k_full[s], 32); mbar_init(&bar_v_full[s], 32); mbar_init(&bar_kv_empty[s], 1); }
-        mbar_init(&bar_q_full, 32);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bar_k_full[s], 1); mbar_init(&bar_v_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
+        mbar_init(&bar_q_full, 1);
         mbar_init(&bar_s_full, 1);
         mbar_init(&bar_s_free, TM);
         mbar_init(&bar_p_full, TM);
@@ -104,29 +90,20 @@ window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
     const uint32_t tm_S = tmem_slot, tm_P = tmem_slot + 128, tm_O = tmem_slot + 192;
 
     if (warp == 4) {
-        // ===================================================================== producer
-        load_tile<WS>(sbase + SmemLayout::Q, qkv, win_base, W, C3, qtile * TM, head * HD, lane);
-        cp_async_commit();
-        uint64_t* pending = &bar_q_full;          // barrier of the most recently committed group
-        for (int t = 0; t < T; ++t) {
-            const int s = t & 1;
-            if (t >= 2) mbar_wait(&bar_kv_empty[s], ((t >> 1) - 1) & 1);
-            load_tile<WS>(sbase + SmemLayout::K + s * TILE_BYTES, qkv, win_base, W, C3, t * TN, C + head * HD, lane);
-            cp_async_commit();
-            cp_async_wait<1>();                  // everything but the group just committed has landed
-            fence_proxy_async();
-            mbar_arrive(pending);
-            pending = &bar_k_full[s];
-            load_tile<WS>(sbase + SmemLayout::V + s * TILE_BYTES, qkv, win_base, W, C3, t * TN, 2 * C + head * HD, lane);
-            cp_async_commit();
-            cp_async_wait<1>();
-            fence_proxy_async();
-            mbar_arrive(pending);
-            pending = &bar_v_full[s];
+        // ===================================================================== producer (one lane, TMA)
+        if (lane == 0) {
+            constexpr int RPT = TN / WS;                        // window rows per 128-token tile
+            tma::expect_tx(&bar_q_full, TILE_BYTES);
+            tma::load_3d(sbase + SmemLayout::Q, &in_map, &bar_q_full, head * HD, x0, y0 + qtile * (TM / WS));
+            for (int t = 0; t < T; ++t) {
+                const int s = t & 1;
+                if (t >= 2) mbar_wait(&bar_kv_empty[s], ((t >> 1) - 1) & 1);
+                tma::expect_tx(&bar_k_full[s], TILE_BYTES);
+                tma::load_3d(sbase + SmemLayout::K + s * TILE_BYTES, &in_map, &bar_k_full[s], C + head * HD, x0, y0 + t * RPT);
+                tma::expect_tx(&bar_v_full[s], TILE_BYTES);
+                tma::load_3d(sbase + SmemLayout::V + s * TILE_BYTES, &in_map, &bar_v_full[s], 2 * C + head * HD, x0, y0 + t * RPT);
+            }
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        mbar_arrive(pending);
     } else if (warp == 5) {
         // =================================================================== MMA issuer
         if (lane == 0) {
@@ -136,14 +113,10 @@ window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
                 const int s = t & 1;
                 mbar_wait(&bar_k_full[s], (t >> 1) & 1);
                 if (t > 0) mbar_wait(&bar_s_free, (t - 1) & 1);
-                fence_proxy_async();
                 fence_after_sync();
+                const uint64_t a = tma::desc_sw128(sbase + SmemLayout::Q), bd = tma::desc_sw128(sbase + SmemLayout::K + s * TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k) {
-                    const uint64_t a = smem_desc(sbase + SmemLayout::Q + k * 2 * CHUNK_STRIDE, CHUNK_STRIDE, 128);
-                    const uint64_t bd = smem_desc(sbase + SmemLayout::K + s * TILE_BYTES + k * 2 * CHUNK_STRIDE, CHUNK_STRIDE, 128);
-                    mma_ss(tm_S, a, bd, idesc_s, k > 0);
-                }
+                for (int k = 0; k < HD / 16; ++k) mma_ss(tm_S, a + 2 * k, bd + 2 * k, idesc_s, k > 0);     // 16 channels = 32 B per step
                 mma_commit(&bar_s_full);
             };
             mbar_wait(&bar_q_full, 0);
@@ -153,14 +126,11 @@ window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
                 if (t + 1 < T) issue_s(t + 1);
                 mbar_wait(&bar_v_full[s], (t >> 1) & 1);
                 mbar_wait(&bar_p_full, t & 1);
-                fence_proxy_async();
                 fence_after_sync();
+                const uint64_t vd = tma::desc_sw128(sbase + SmemLayout::V + s * TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < TN / 16; ++k) {
-                    // V tile [dim chunk][key][16 B]: 8-key groups 128 B apart, dim chunks CHUNK_STRIDE apart
-                    const uint64_t bd = smem_desc(sbase + SmemLayout::V + s * TILE_BYTES + k * 256, 128, CHUNK_STRIDE);
-                    mma_ts(tm_O, tm_P + k * 8, bd, idesc_o, (t > 0) || (k > 0));
-                }
+                for (int k = 0; k < TN / 16; ++k)          // V tile rows = keys: 16 keys (2048 B) per step, MN-major
+                    mma_ts(tm_O, tm_P + k * 8, vd + k * (2048 >> 4), idesc_o, (t > 0) || (k > 0));
                 mma_commit(&bar_pv_done);
                 mma_commit(&bar_kv_empty[s]);
             }
@@ -243,8 +213,8 @@ window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
         mbar_wait(&bar_pv_done, (T - 1) & 1);
         fence_after_sync();
         const float inv = 1.f / l_run;
-        const int ty = tq / WS, tx = tq - ty * WS;
-        __nv_bfloat16* dst = out + (win_base + (long long)ty * W + tx) * C + head * HD;
+        // O / rowsum -> bf16 -> the (now idle) Q tile as a SWIZZLE_128B staging tile -> one TMA store of the window rows
+        const uint32_t stg = sbase + SmemLayout::Q + (uint32_t)row * 128;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
             uint32_t o[32];
@@ -252,13 +222,20 @@ window_attn_flash_kernel(const __nv_bfloat16* __restrict__ qkv, const float* __r
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                uint4 v;
-                v.x = pack_bf16(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv);
-                v.y = pack_bf16(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv);
-                v.z = pack_bf16(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv);
-                v.w = pack_bf16(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv);
-                *reinterpret_cast<uint4*>(dst + h2 * 32 + j) = v;
+                const uint32_t chunk = (uint32_t)((h2 * 32 + j) >> 3) ^ (uint32_t)(row & 7);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (chunk << 4)),
+                             "r"(pack_bf16(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv)),
+                             "r"(pack_bf16(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv)),
+                             "r"(pack_bf16(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv)),
+                             "r"(pack_bf16(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv)) : "memory");
             }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+            tma::store_3d(&out_map, sbase + SmemLayout::Q, head * HD, x0, y0 + qtile * (TM / WS));
+            tma::store_commit();
+            tma::store_wait_all();
         }
     }
     fence_before_sync();
@@ -289,15 +266,22 @@ int window_attn_flash(const void* qkv, const float* table, void* out, void* work
         const int st = window_attn_flash_prepare(table, workspace, heads, ws, stream);
         if (st != SODT_OK) return st;
     }
-    const size_t smem = SmemLayout::TAB + (size_t)entries * sizeof(float);
+    const size_t smem = SmemLayout::TAB + (size_t)entries * sizeof(float) + 1024;
     auto kern = window_attn_flash_kernel<WS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const long long nwin = (long long)B * (H / ws) * (W / ws);
     if (nwin > 65535) return SODT_ERR_UNSUPPORTED;      // grid.z limit; the dispatcher routes larger batches to another kernel
+    CUtensorMap in_map, out_map;
+    {
+        const int box[3] = {HD, WS, TN / WS};
+        const long long din[3] = {3LL * C, W, (long long)B * H}, sin[2] = {3LL * C, 3LL * C * W};
+        const long long dout[3] = {C, W, (long long)B * H}, sout[2] = {C, (long long)C * W};
+        if (!tma::make_map_bf16(&in_map, qkv, 3, din, sin, box) ||
+            !tma::make_map_bf16(&out_map, out, 3, dout, sout, box, CU_TENSOR_MAP_L2_PROMOTION_NONE)) return SODT_ERR_CUDA;
+    }
     dim3 grid(ws * ws / TM, heads, (unsigned)nwin);
-    kern<<<grid, NTHREADS, smem, stream>>>(static_cast<const __nv_bfloat16*>(qkv), table_t,
-                                           static_cast<__nv_bfloat16*>(out), H, W, C, heads, scale);
+    kern<<<grid, NTHREADS, smem, stream>>>(in_map, out_map, table_t, H, W, C, heads, scale);
     return check_launch();
 }
 
