@@ -201,6 +201,51 @@ __device__ __forceinline__ float fast_exp2(float x) {   // single MUFU.EX2
     return y;
 }
 
+// ------------------------------------------------------------------ packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMNMX3)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {     // FFMA2: two fp32 FMAs per issue slot
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {                  // FMNMX3
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// 2^x on the FMA / ALU pipes instead of the MUFU (16 results per clock and SM): round-to-nearest split x = n + f, |f| <= 0.5,
+// degree-4 polynomial of 2^f (relative error 4e-5, far below bf16's 2^-9), n added to the exponent field.  x <= ~100.
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+    float lo, hi;
+    unpack2(x2, lo, hi);
+    x2 = pack2(fmaxf(lo, -125.f), fmaxf(hi, -125.f));
+    const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+    const uint64_t t = fadd2(x2, magic);                    // n in the low mantissa bits
+    const uint64_t n = fadd2(t, nmagic);
+    float nl, nh;
+    unpack2(n, nl, nh);
+    const uint64_t f = fadd2(x2, pack2(-nl, -nh));
+    uint64_t p = ffma2(f, pack2(0.0096181291f, 0.0096181291f), pack2(0.0555041087f, 0.0555041087f));
+    p = ffma2(p, f, pack2(0.2402265070f, 0.2402265070f));
+    p = ffma2(p, f, pack2(0.6931471806f, 0.6931471806f));
+    p = ffma2(p, f, pack2(1.f, 1.f));
+    float pl, ph, tl, th;
+    unpack2(p, pl, ph);
+    unpack2(t, tl, th);
+    return pack2(__int_as_float(__float_as_int(pl) + (__float_as_int(tl) << 23)), __int_as_float(__float_as_int(ph) + (__float_as_int(th) << 23)));
+}
+
 __device__ __forceinline__ float fast_tanh(float x) {   // single MUFU.TANH, relative error <= 2^-11
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

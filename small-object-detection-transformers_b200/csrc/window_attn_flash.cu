@@ -37,6 +37,10 @@ constexpr int NTHREADS = 192;
 constexpr int TILE_BYTES = TM * HD * 2;   // 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
+#ifndef SODT_FLASH_POLY_EXP
+#define SODT_FLASH_POLY_EXP 0
+#endif
+constexpr bool POLY_EXP = SODT_FLASH_POLY_EXP != 0;
 
 struct SmemLayout {
     static constexpr int Q = 0;
@@ -149,37 +153,63 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
         for (int t = 0; t < T; ++t) {
             mbar_wait(&bar_s_full, t & 1);
             fence_after_sync();
-            float s2[TN];
+            // packed fp32x2 arithmetic: t = s * (scale log2 e) + bias, two scores per FFMA2; key j of this tile sits at window row
+            // t*(TN/WS) + j/WS, column j%WS
+            const float* tb = tab_q - (t * (TN / WS)) * SPAN;
+            const uint64_t c2 = pack2(c, c);
+            uint64_t t2[TN / 2];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
                 uint32_t r[32];
                 tmem_ld32(tm_S + lane_addr + q4 * 32, r);
                 tmem_wait_ld();
+                if (q4 == 3) { fence_before_sync(); mbar_arrive(&bar_s_free); }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) s2[q4 * 32 + j] = __uint_as_float(r[j]);
+                for (int j = 0; j < 32; j += 2) {
+                    const int k0 = q4 * 32 + j;
+                    const float b0 = tb[-((k0 / WS) * SPAN + (k0 % WS))], b1 = tb[-(((k0 + 1) / WS) * SPAN + ((k0 + 1) % WS))];
+                    t2[k0 >> 1] = ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(b0, b1));
+                }
             }
-            fence_before_sync();
-            mbar_arrive(&bar_s_free);
-            // key j of this tile sits at window row t*(TN/WS) + j/WS, column j%WS
-            const float* tb = tab_q - (t * (TN / WS)) * SPAN;
-            float m_tile = -INFINITY;
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                s2[j] = fmaf(s2[j], c, tb[-((j / WS) * SPAN + (j % WS))]);
-                m_tile = fmaxf(m_tile, s2[j]);
+            for (int j = 0; j < TN / 2; ++j) {
+                float lo, hi;
+                unpack2(t2[j], lo, hi);
+                m4[j & 3] = fmax3(m4[j & 3], lo, hi);
             }
+            const float m_tile = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
             float alpha = 1.f;
             if (m_tile > m_used + RESCALE_THRESHOLD) {
                 alpha = fast_exp2(m_used - m_tile);   // 0 on the first tile (m_used = -inf)
                 m_used = m_tile;
             }
-            float sum = 0.f;
+            // exponentials: the MUFU delivers 16 per clock and SM, the tensor pipe wants 128 x 128 of them per 512 clocks of MMAs,
+            // so 3 of every 8 score pairs take the FMA-pipe polynomial (exp2_poly2) instead
+            const uint64_t nm2 = pack2(-m_used, -m_used);
+            uint64_t sum2[2] = {0ull, 0ull};
             uint32_t pk[TN / 2];
 #pragma unroll
-            for (int j = 0; j < TN; j += 2) {
-                const float p0 = fast_exp2(s2[j] - m_used), p1 = fast_exp2(s2[j + 1] - m_used);
-                sum += p0 + p1;
-                pk[j / 2] = pack_bf16(p0, p1);
+            for (int j = 0; j < TN / 2; ++j) {
+                const uint64_t x2 = fadd2(t2[j], nm2);
+                uint64_t p2;
+                if (POLY_EXP && ((j & 7) == 1 || (j & 7) == 4 || (j & 7) == 6)) {
+                    p2 = exp2_poly2(x2);
+                } else {
+                    float lo, hi;
+                    unpack2(x2, lo, hi);
+                    p2 = pack2(fast_exp2(lo), fast_exp2(hi));
+                }
+                sum2[j & 1] = fadd2(sum2[j & 1], p2);
+                float p0, p1;
+                unpack2(p2, p0, p1);
+                pk[j] = pack_bf16(p0, p1);
+            }
+            float sum;
+            {
+                float a, b;
+                unpack2(fadd2(sum2[0], sum2[1]), a, b);
+                sum = a + b;
             }
             l_run = l_run * alpha + sum;
             if (t > 0) {

@@ -82,13 +82,18 @@ for r in data:
                    "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}, first stage-1 launch (B=32, 256x256 tokens, C=192)"}
 open(os.path.join(out_dir, f"{rnd}_kernels_ncu.md"), "w").write("\n".join(lines) + "\n")
 if traffic:
+    import hashlib
     traffic["attention_tensor_pipe_pct"] = tensor_pct       # BASELINE.json's "attn tensor-pipe %" (sm__pipe_tensor_cycles_active)
+    # stamp: bench.py reports these numbers only while the kernel sources are the ones that were profiled
+    csrc = os.path.join(ROOT, "small-object-detection-transformers_b200", "csrc")
+    traffic["source_sha256"] = {f: hashlib.sha256(open(os.path.join(csrc, f), "rb").read()).hexdigest()
+                                for f in ("window_attn_win8.cu", "window_attn_flash.cu", "cattn.cu", "tc05.cuh", "tma.cuh")}
     json.dump(traffic, open(os.path.join(out_dir, f"{rnd}_roofline_traffic.json"), "w"), indent=1)
 # trim the launch list to whole steps: from the first front-end launch to the last one (exclusive)
 lrows = open(launches).read().splitlines()
 hi = next(i for i, l in enumerate(lrows) if l.startswith('"ID"'))
 body = lrows[hi + 1:]
-fe = [i for i, l in enumerate(body) if "frontend_kernel" in l]
+fe = [i for i, l in enumerate(body) if "frontend" in l and "kernel" in l]
 if len(fe) >= 2:
     body = body[fe[0]:fe[-1]]
 launches_trimmed = os.path.join(out_dir, f"{rnd}_bench_launches.csv")
