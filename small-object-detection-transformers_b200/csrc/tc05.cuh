@@ -246,6 +246,11 @@ __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
     return pack2(__int_as_float(__float_as_int(pl) + (__float_as_int(tl) << 23)), __int_as_float(__float_as_int(ph) + (__float_as_int(th) << 23)));
 }
 
+__device__ __forceinline__ float fast_rcp(float x) {    // single MUFU.RCP (relative error 2^-23 class; no slow path)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float fast_tanh(float x) {   // single MUFU.TANH, relative error <= 2^-11
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

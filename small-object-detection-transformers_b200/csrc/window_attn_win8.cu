@@ -53,8 +53,8 @@ constexpr int NTHREADS = (NG * SM_WARPS + NG + 2) * 32;
 constexpr int MMA_WARP0 = NG * SM_WARPS, TMA_WARP = MMA_WARP0 + NG, STORE_WARP = TMA_WARP + 1;   // one MMA-issuing warp per softmax group
 constexpr int STAGES = 4;
 constexpr int WIN_BYTES = NTOK * 128;         // one box: 64 token rows x 128 B
-constexpr int STAGE_BYTES = 5 * WIN_BYTES;    // QA QB KA KB V
-constexpr int OFF_Q = 0, OFF_K = 2 * WIN_BYTES, OFF_V = 4 * WIN_BYTES;
+constexpr int STAGE_BYTES = 4 * WIN_BYTES;    // QA QB K V
+constexpr int OFF_Q = 0, OFF_K = 2 * WIN_BYTES, OFF_V = 3 * WIN_BYTES;
 constexpr int OT_BYTES = WIN_BYTES;           // output staging tile of a stage
 constexpr int OT_RING = 4;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -66,10 +66,11 @@ __host__ __device__ constexpr int tab_copy_stride(int heads) {         // floats
     return ((heads * TAB_HEAD * 4 + 95) / 128 * 128 + 32) / 4;          // warp (2 rows x 2 copies x 4 offsets) hit 16 distinct bank pairs
 }
 constexpr int TAB_COPIES = 2;
-// TMEM columns per group g: S = g*128 (128 columns), P = 256 + g*32, O = 320 + g*64 (2*hd <= 64 columns)
-constexpr uint32_t TM_S = 0, TM_P = 256, TM_O = 320;
+// TMEM columns per group g and head pair pr: S = g*128 + pr*64, P = 256 + g*64 + pr*32, O = 384 + g*64 + pr*2hd
+constexpr uint32_t TM_S = 0, TM_P = 256, TM_O = 384;
+constexpr uint32_t ALL = 0xFFFFFFFFu;
 constexpr int XCH_BAR0 = 2;                   // named barriers 2, 3: row-maximum exchange inside a softmax group
-constexpr int XCH_FLOATS = 2 * 2 * NG * 2 * ROWS;    // {max, sum} x unit parity x group x half x row
+constexpr int XCH_FLOATS = 2 * 2 * 2 * NG * 2 * ROWS;    // {max, sum} x unit parity x head pair x group x half x row
 
 __global__ void prep_table_win8_kernel(const float* __restrict__ table, float* __restrict__ out, int heads) {
     const int cs = tab_copy_stride(heads);
@@ -114,16 +115,16 @@ struct Maps {
     CUtensorMap full, row8, row_a, row_b;     // boxes (64, 8, 8), (64, 8, 1), (64, 8 - shift, 1), (64, shift, 1)
 };
 
-// The five boxes of a stage (QA, QB, KA, KB, V), issued by the whole producer warp: a window inside the image is one box per
-// operand tile (lanes 0-4); a window that wraps around the image is 8 row boxes per tile, or 16 row parts when the rows
-// themselves wrap (40 / 80 small copies spread over the 32 lanes: one lane needs ~130 cycles per TMA instruction).
+// The four boxes of a stage (QA, QB, K, V), issued by the whole producer warp: a window inside the image is one box per
+// operand tile (lanes 0-3); a window that wraps around the image is 8 row boxes per tile, or 16 row parts when the rows
+// themselves wrap (32 / 64 small copies spread over the 32 lanes: one lane needs ~130 cycles per TMA instruction).
 template <int HD>
 __device__ __forceinline__ void load_stage(const Maps& m, const Geo& geo, const WinBox& b, uint32_t st, int c0, int C, uint64_t* bar, int lane) {
     const int per_box = !b.wrap_x && !b.wrap_y ? 1 : (b.wrap_x ? 2 * WS : WS);
-    for (int item = lane; item < 5 * per_box; item += 32) {
+    for (int item = lane; item < 4 * per_box; item += 32) {
         const int bi = item / per_box, sub = item - bi * per_box;
-        const uint32_t sm = st + bi * WIN_BYTES;                                 // tiles in the order QA QB KA KB V
-        const int ch = (bi >> 1) * C + c0 + ((bi & 1) && bi < 4 ? HD : 0);        // q, q + hd, k, k + hd, v
+        const uint32_t sm = st + bi * WIN_BYTES;                                 // tiles in the order QA QB K V
+        const int ch = (bi < 2 ? 0 : bi - 1) * C + c0 + (bi == 1 ? HD : 0);       // q, q + hd, k, v
         if (per_box == 1) {
             tma::load_3d(sm, &m.full, bar, ch, b.x0, b.yg_base + b.y0);
         } else {
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ Maps out_maps,
                         const float* __restrict__ table_p, Geo geo, int C, int heads, float scale, float mask_value) {
     constexpr int G = 64 / HD;                // heads per stage
-    constexpr int UPS = G / 2;                // units (head pairs) per stage: 2 (head_dim 16) or 1 (head_dim 32)
+    constexpr int HPB = G / 2;                // head pairs per stage = per unit: 2 (head_dim 16) or 1 (head_dim 32)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t stage_full[STAGES], stage_empty[STAGES], s_full[NG], s_free[NG], p_full[NG], pv_done[NG], ot_full[OT_RING], ot_free[OT_RING];
     __shared__ uint32_t tmem_slot;
@@ -172,14 +173,13 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
     float* xch = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + STAGES * STAGE_BYTES + OT_RING * OT_BYTES);
     float* tab = xch + XCH_FLOATS;
     const int groups = C / 64;                                                         // stages per window
-    long long my_windows = 0;
-    if ((long long)blockIdx.x < geo.total_windows) my_windows = (geo.total_windows - blockIdx.x + gridDim.x - 1) / gridDim.x;
-    const long long n_stages = my_windows * groups;
-    const long long n_units = n_stages * UPS;
+    int my_windows = 0;
+    if ((long long)blockIdx.x < geo.total_windows) my_windows = (int)((geo.total_windows - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const int n_stages = my_windows * groups;         // unit = stage; group g takes this CTA's stages g, g + NG, ...
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], UPS); }     // one commit per head pair of the stage
-        for (int s = 0; s < OT_RING; ++s) { mbar_init(&ot_full[s], UPS * 2 * ROWS); mbar_init(&ot_free[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
+        for (int s = 0; s < OT_RING; ++s) { mbar_init(&ot_full[s], 2 * ROWS); mbar_init(&ot_free[s], 1); }
         for (int g = 0; g < NG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 2 * ROWS); mbar_init(&p_full[g], 2 * ROWS); mbar_init(&pv_done[g], 1); }
         fence_barrier_init();
     }
@@ -219,19 +219,19 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
     } else if (warp == STORE_WARP) {
         // ============================================================ output stores: the warp stores every finished staging tile
         if (lane == 0) tma::prefetch_map(&out_maps.full);
-        long long st = 0;
+        int st = 0;
         for (long long wdx = blockIdx.x; wdx < geo.total_windows; wdx += gridDim.x) {
             const WinBox b = win_box(geo, wdx);
             for (int gi = 0; gi < groups; ++gi, ++st) {
-                const int slot = (int)(st & (OT_RING - 1));
-                if (lane == 0) mbar_wait(&ot_full[slot], (uint32_t)((st / OT_RING) & 1));        // every head pair's columns are in the tile
+                const int slot = st & (OT_RING - 1);
+                if (lane == 0) mbar_wait(&ot_full[slot], (uint32_t)((st / OT_RING) & 1));        // every head's columns are in the tile
                 __syncwarp();
                 store_tile(out_maps, geo, b, ot_base + slot * OT_BYTES, gi * 64, lane);
                 tma::store_commit();                                                     // per lane: each lane tracks its own copies
                 if (st > 0) {                                                            // the previous tile has been read: its slot is free
                     tma::store_wait_read<1>();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ot_free[(int)((st - 1) & (OT_RING - 1))]);
+                    if (lane == 0) mbar_arrive(&ot_free[(st - 1) & (OT_RING - 1)]);
                 }
             }
         }
@@ -240,48 +240,56 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         // =============================================================== MMA issuers: one thread per softmax group
         // (a single issuer serialised the groups: the scores of one group waited behind the other group's P)
         if (lane == 0) {
-            constexpr uint32_t idesc_s = idesc_bf16(ROWS, 2 * NTOK, false, false);
+            constexpr uint32_t idesc_s = idesc_bf16(ROWS, NTOK, false, false);
             constexpr uint32_t idesc_o = idesc_bf16(ROWS, 2 * HD, false, true);
             const int g = warp - MMA_WARP0;
             const uint64_t d0 = tma::desc_sw128(sbase);
-            const uint32_t tS = tm + TM_S + g * 128, tP = tm + TM_P + g * 32, tO = tm + TM_O + g * 64;
-            // unit k of this group = global unit u = NG k + g = (stage u / UPS, head pair u % UPS)
-            const long long nk = n_units > g ? (n_units - g + NG - 1) / NG : 0;
-            auto issue_qk = [&](long long k) {
-                const long long u = NG * k + g, stg = u / UPS;
-                const int pr = (int)(u - stg * UPS), slot = (int)(stg % STAGES);
-                TRACE(2, (int)u, 0);
+            const uint32_t tS = tm + TM_S + g * 128, tP = tm + TM_P + g * 64, tO = tm + TM_O + g * 64;
+            const int nk = n_stages > g ? (n_stages - g + NG - 1) / NG : 0;          // unit k of this group = stage NG k + g
+            auto issue_qk = [&](int k) {
+                const int stg = NG * k + g, slot = stg % STAGES;
+                TRACE(2, stg, 0);
                 mbar_wait_spin(&stage_full[slot], (uint32_t)((stg / STAGES) & 1));
-                TRACE(2, (int)u, 1);
+                TRACE(2, stg, 1);
                 if (k > 0) mbar_wait_spin(&s_free[g], (uint32_t)((k - 1) & 1));
-                TRACE(2, (int)u, 2);
+                TRACE(2, stg, 2);
                 fence_after_sync();
-                const uint32_t off = (uint32_t)(slot * STAGE_BYTES + pr * (2 * HD * 2)) >> 4;
-                const uint64_t qd = d0 + off + (OFF_Q >> 4), kd = d0 + off + (OFF_K >> 4);
 #pragma unroll
-                for (int ks = 0; ks < HD / 16; ++ks)            // [Q_even ; Q_odd] x [K_even ; K_odd]^T, 16 channels per step
-                    mma_ss(tS, qd + 2 * ks, kd + 2 * ks, idesc_s, ks > 0);
+                for (int pr = 0; pr < HPB; ++pr) {
+                    // lanes 0-63: even head = Q rows of QA x K at the even head's columns; lanes 64-127: odd head = Q rows of QB (the same
+                    // tokens, channels shifted by one head) x K at the odd head's columns
+                    const uint32_t off = (uint32_t)(slot * STAGE_BYTES + pr * (2 * HD * 2)) >> 4;
+                    const uint64_t qd = d0 + off + (OFF_Q >> 4), kd = d0 + off + (OFF_K >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd + 2 * ks, kd + 2 * ks, idesc_s, ks > 0, 0u, 0u, ALL, ALL);
+#pragma unroll
+                    for (int ks = 0; ks < HD / 16; ++ks)
+                        mma_ss_masked(tS + pr * 64, qd + 2 * ks, kd + ((HD * 2) >> 4) + 2 * ks, idesc_s, ks > 0, ALL, ALL, 0u, 0u);
+                }
                 mma_commit(&s_full[g]);
-                TRACE(2, (int)u, 3);
+                TRACE(2, stg, 3);
             };
             if (nk > 0) issue_qk(0);
-            for (long long k = 0; k < nk; ++k) {
+            for (int k = 0; k < nk; ++k) {
                 // S is free as soon as softmax(k) has copied it to registers, so the group's next scores are computed while
                 // softmax(k) is still running
                 if (k + 1 < nk) issue_qk(k + 1);
-                const long long u = NG * k + g, stg = u / UPS;
-                const int pr = (int)(u - stg * UPS), slot = (int)(stg % STAGES);
-                TRACE(2, (int)u, 4);
+                const int stg = NG * k + g, slot = stg % STAGES;
+                TRACE(2, stg, 4);
                 mbar_wait_spin(&p_full[g], (uint32_t)(k & 1));
-                TRACE(2, (int)u, 5);
+                TRACE(2, stg, 5);
                 fence_after_sync();
-                const uint64_t vd = d0 + ((uint32_t)(slot * STAGE_BYTES + OFF_V + pr * (2 * HD * 2)) >> 4);
 #pragma unroll
-                for (int ks = 0; ks < NTOK / 16; ++ks)          // O[128 x 2hd] = P [V_even | V_odd], 16 keys (2048 B of the V tile) per step
-                    mma_ts(tO, tP + ks * 8, vd + ks * (2048 >> 4), idesc_o, ks > 0);
+                for (int ks = 0; ks < NTOK / 16; ++ks) {        // O[128 x 2hd] = P [V_even | V_odd], 16 keys (2048 B of the V tile) per step;
+#pragma unroll
+                    for (int pr = 0; pr < HPB; ++pr) {          // the pairs' chains interleaved (independent accumulators)
+                        const uint64_t vd = d0 + ((uint32_t)(slot * STAGE_BYTES + OFF_V + pr * (2 * HD * 2)) >> 4);
+                        mma_ts(tO + pr * (2 * HD), tP + pr * 32 + ks * 8, vd + ks * (2048 >> 4), idesc_o, ks > 0);
+                    }
+                }
                 mma_commit(&pv_done[g]);
-                mma_commit(&stage_empty[slot]);                  // this pair's reads of the stage are done
-                TRACE(2, (int)u, 6);
+                mma_commit(&stage_empty[slot]);                  // the stage's tiles are no longer read
+                TRACE(2, stg, 6);
             }
         }
     } else {
@@ -289,13 +297,13 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         // Two threads per score row: warps w and w + 4 of a group own the same 32 TMEM lanes (a warp reaches lane quarter
         // warp % 4 only) and split the 64 keys, so 16 softmax warps (4 per SM sub-partition) cover one another's tensor-memory,
         // shared-memory and MUFU latencies; row maximum and row sum are exchanged through shared memory.
-        const int g = warp >> 3;                       // group g takes units g, g + NG, ...
+        const int g = warp >> 3;                       // group g takes stages g, g + NG, ...
         const int half = (warp >> 2) & 1;              // keys [32 half, 32 half + 32) = key rows yj in [4 half, 4 half + 4)
         const int row = (warp & 3) * 32 + lane;        // TMEM lane = 64 * (head parity) + query token
         const int hp = row >> 6, ti = row & 63, ty = ti >> 3, tx = ti & 7;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tS = tm + TM_S + g * 128 + hp * 64 + half * 32 + lane_addr;
-        const uint32_t tP = tm + TM_P + g * 32 + half * 16 + lane_addr;
+        const uint32_t tS = tm + TM_S + g * 128 + half * 32 + lane_addr;
+        const uint32_t tP = tm + TM_P + g * 64 + half * 16 + lane_addr;
         const uint32_t tO = tm + TM_O + g * 64 + hp * HD + half * (HD / 2) + lane_addr;
         const float c = scale * LOG2E, mv2 = mask_value * LOG2E;
         const uint64_t c2 = pack2(c, c);
@@ -306,159 +314,159 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         const uint64_t yhi = s_ > 0 ? (~0ull << (8 * (WS - s_))) : 0ull;                       // keys with ty >= ws - shift
         const uint64_t xhi = s_ > 0 ? 0x0101010101010101ull * (uint64_t)((0xFFu << (WS - s_)) & 0xFFu) : 0ull;  // tx >= ws - shift
         const uint32_t srow = (uint32_t)ti * 128, sw = (uint32_t)(ti & 7);
-        float* my_max = xch + (g * 2 + half) * ROWS + row;            // [parity k & 1][group][half][row]; partner: half ^ 1
+        // exchange slots [parity][pair][group][half][row]: this thread's and its partner's (the other half of the same row)
+        float* my_max = xch + (g * 2 + half) * ROWS + row;
         float* pt_max = xch + (g * 2 + (half ^ 1)) * ROWS + row;
-        float* my_sum = my_max + 2 * NG * 2 * ROWS;
-        float* pt_sum = pt_max + 2 * NG * 2 * ROWS;
-        long long cur_win_it = -1;
+        float* my_sum = my_max + XCH_FLOATS / 2;
+        float* pt_sum = pt_max + XCH_FLOATS / 2;
+        constexpr int XPAIR = NG * 2 * ROWS, XPAR = 2 * XPAIR;      // strides of the pair / parity dimensions
         uint32_t mbits = 0;
-        WinBox wb = {};                                // geometry of the window of the current unit
-        float prev_sum = 0.f;
-        int prev_pr = 0;
-        long long prev_stage = 0, prev_k = 0;
-        [[maybe_unused]] int tr_u = 0;
+        bool any_mask = false;
+        float prev_sum[HPB] = {};
+        int prev_stg = 0, prev_par = 0;
 
-        // Epilogue of the group's previous unit: this thread's half of its head's O columns / rowsum -> staging tile of the stage;
-        // the store warp sends the tile off when every head pair of the stage has delivered.
+        // Epilogue of the group's previous unit: this thread's half of its heads' O columns / rowsum -> staging tile of the stage;
+        // the store warp sends the tile off when all 256 threads of the group have delivered.
         auto epilogue = [&]() {
-            const int slot = (int)(prev_stage & (OT_RING - 1));
+            const int slot = prev_stg & (OT_RING - 1);
             const uint32_t tile_s = ot_base + (uint32_t)slot * OT_BYTES;
-            uint32_t o[HD / 2];
-            if constexpr (HD == 16) tmem_ld8(tO, o); else tmem_ld16(tO, o);
-            const float inv = 1.f / (prev_sum + pt_sum[(prev_k & 1) * (NG * 2 * ROWS)]);     // written before the partner's p_full arrival
-            tmem_wait_ld();
-            if (row == 0 && half == 0) TRACE(g, tr_u, 7);
-            if (prev_stage >= OT_RING) mbar_wait(&ot_free[slot], (uint32_t)(((prev_stage / OT_RING) - 1) & 1));   // the slot's previous tile has left
-            if (row == 0 && half == 0) TRACE(g, tr_u, 8);
+            uint32_t o[HPB][HD / 2];
+            float inv[HPB];
 #pragma unroll
-            for (int j = 0; j < HD / 2; j += 8) {
-                const uint32_t chunk = (uint32_t)(((2 * prev_pr + hp) * HD + half * (HD / 2) + j) >> 3) ^ sw;
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
-                             "r"(pack_bf16(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv)),
-                             "r"(pack_bf16(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv)),
-                             "r"(pack_bf16(__uint_as_float(o[j + 4]) * inv, __uint_as_float(o[j + 5]) * inv)),
-                             "r"(pack_bf16(__uint_as_float(o[j + 6]) * inv, __uint_as_float(o[j + 7]) * inv)) : "memory");
+            for (int pr = 0; pr < HPB; ++pr) {
+                if constexpr (HD == 16) tmem_ld8(tO + pr * (2 * HD), o[pr]); else tmem_ld16(tO + pr * (2 * HD), o[pr]);
+                inv[pr] = fast_rcp(prev_sum[pr] + pt_sum[prev_par * XPAR + pr * XPAIR]);      // written before the partner's p_full arrival
+            }
+            tmem_wait_ld();
+            if (prev_stg >= OT_RING) mbar_wait(&ot_free[slot], (uint32_t)(((prev_stg / OT_RING) - 1) & 1));   // the slot's previous tile has left
+#pragma unroll
+            for (int pr = 0; pr < HPB; ++pr) {
+#pragma unroll
+                for (int j = 0; j < HD / 2; j += 8) {
+                    const uint32_t chunk = (uint32_t)(((2 * pr + hp) * HD + half * (HD / 2) + j) >> 3) ^ sw;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
+                                 "r"(pack_bf16(__uint_as_float(o[pr][j]) * inv[pr], __uint_as_float(o[pr][j + 1]) * inv[pr])),
+                                 "r"(pack_bf16(__uint_as_float(o[pr][j + 2]) * inv[pr], __uint_as_float(o[pr][j + 3]) * inv[pr])),
+                                 "r"(pack_bf16(__uint_as_float(o[pr][j + 4]) * inv[pr], __uint_as_float(o[pr][j + 5]) * inv[pr])),
+                                 "r"(pack_bf16(__uint_as_float(o[pr][j + 6]) * inv[pr], __uint_as_float(o[pr][j + 7]) * inv[pr])) : "memory");
+                }
             }
             fence_proxy_async();                                          // staging writes -> visible to the TMA store
             mbar_arrive(&ot_full[slot]);
-            if (row == 0 && half == 0) TRACE(g, tr_u, 9);
         };
 
-        long long k = 0, stg = 0, win_it = 0;          // this CTA's stage / window counters of the current unit
-        int pr = 0, gi = 0;
-        auto advance = [&]() { if (++pr == UPS) { pr = 0; ++stg; if (++gi == groups) { gi = 0; ++win_it; } } };
-        for (int i = 0; i < g; ++i) advance();
-        for (long long u = g; u < n_units; u += NG, ++k) {
-            if (win_it != cur_win_it) {                // new window: geometry, shifted-window mask bits of this thread's 32 keys
+        int k = 0, gi = g % groups, win_it = g / groups, cur_win_it = -1;     // stage stg = NG k + g = (window iteration, channel group)
+        for (int stg = g; stg < n_stages; stg += NG, ++k) {
+            if (win_it != cur_win_it) {                // new window: shifted-window mask bits of this thread's 32 keys
                 cur_win_it = win_it;
-                wb = win_box(geo, (long long)blockIdx.x + win_it * gridDim.x);
+                const WinBox wb = win_box(geo, (long long)blockIdx.x + (long long)win_it * gridDim.x);
                 uint64_t mb = 0;
                 if (s_ > 0) {
                     if (wb.last_row) mb |= (ty >= WS - s_) ? ~yhi : yhi;
                     if (wb.last_col) mb |= (tx >= WS - s_) ? ~xhi : xhi;
                 }
                 mbits = (uint32_t)(mb >> (32 * half));
+                any_mask = s_ > 0 && (wb.last_row || wb.last_col);          // uniform over the group
             }
-            const bool any_mask = s_ > 0 && (wb.last_row || wb.last_col);
-            tr_u = (int)u;
-            if (row == 0 && half == 0) TRACE(g, tr_u, 0);
-            mbar_wait(&s_full[g], (uint32_t)(k & 1));
-            if (row == 0 && half == 0) TRACE(g, tr_u, 1);
+            const int par = k & 1;
+            if (row == 0 && half == 0) TRACE(g, stg, 0);
+            mbar_wait(&s_full[g], (uint32_t)par);
+            if (row == 0 && half == 0) TRACE(g, stg, 1);
             fence_after_sync();
-            const int h = gi * G + 2 * pr + hp;
-            uint64_t t[NTOK / 4];
-            {
-                uint32_t ra[32];
-                tmem_ld32(tS, ra);
-                tmem_wait_ld();
-                fence_before_sync();
-                mbar_arrive(&s_free[g]);                // the unit's scores are in registers
-                if (row == 0 && half == 0) TRACE(g, tr_u, 2);
-                const float* tb = tab_row + h * TAB_HEAD;
+            float sum_cur[HPB];
+            uint32_t pk[HPB][16];
 #pragma unroll
-                for (int yj = 0; yj < WS / 2; ++yj) {   // t = s * (scale log2 e) + bias, two scores per FFMA2
+            for (int pr = 0; pr < HPB; ++pr) {
+                const int h = gi * G + 2 * pr + hp;
+                uint64_t t[NTOK / 4];
+                {
+                    uint32_t ra[32];
+                    tmem_ld32(tS + pr * 64, ra);
+                    tmem_wait_ld();
+                    if (pr == HPB - 1) { fence_before_sync(); mbar_arrive(&s_free[g]); }       // the unit's scores are in registers
+                    const float* tb = tab_row + h * TAB_HEAD;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int yj = 0; yj < WS / 2; ++yj) {   // t = s * (scale log2 e) + bias, two scores per FFMA2
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
 #ifdef SODT_X_NOBIAS
-                        const float2 b = make_float2(0.f, 0.f);
+                            const float2 b = make_float2(0.f, 0.f);
 #else
-                        const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
+                            const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
 #endif
-                        t[yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
+                            t[yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
+                        }
                     }
                 }
-            }
-            if (any_mask) {                            // group-uniform: only windows of the last window row / column
+                if (any_mask) {                            // group-uniform: only windows of the last window row / column
+#pragma unroll
+                    for (int j = 0; j < NTOK / 4; ++j) {
+                        float lo, hi;
+                        unpack2(t[j], lo, hi);
+                        if ((mbits >> (2 * j)) & 1u) lo += mv2;
+                        if ((mbits >> (2 * j + 1)) & 1u) hi += mv2;
+                        t[j] = pack2(lo, hi);
+                    }
+                }
+                float m4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float lo, hi;
+                    unpack2(t[q], lo, hi);
+                    m4[q] = fmaxf(lo, hi);
+                }
+#pragma unroll
+                for (int j = 4; j < NTOK / 4; ++j) {
+                    float lo, hi;
+                    unpack2(t[j], lo, hi);
+                    m4[j & 3] = fmax3(m4[j & 3], lo, hi);
+                }
+                float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+                my_max[par * XPAR + pr * XPAIR] = mx;
+                asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the two halves of every row have published their maxima
+                mx = fmaxf(mx, pt_max[par * XPAR + pr * XPAIR]);
+                const uint64_t nmx2 = pack2(-mx, -mx);
+                uint64_t sum2 = 0ull;
 #pragma unroll
                 for (int j = 0; j < NTOK / 4; ++j) {
                     float lo, hi;
-                    unpack2(t[j], lo, hi);
-                    if ((mbits >> (2 * j)) & 1u) lo += mv2;
-                    if ((mbits >> (2 * j + 1)) & 1u) hi += mv2;
-                    t[j] = pack2(lo, hi);
-                }
-            }
-            float m4[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float lo, hi;
-                unpack2(t[q], lo, hi);
-                m4[q] = fmaxf(lo, hi);
-            }
-#pragma unroll
-            for (int j = 4; j < NTOK / 4; ++j) {
-                float lo, hi;
-                unpack2(t[j], lo, hi);
-                m4[j & 3] = fmax3(m4[j & 3], lo, hi);
-            }
-            float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
-            const int par = (int)(k & 1) * (NG * 2 * ROWS);
-            my_max[par] = mx;
-            asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the two halves of every row have published their maxima
-            mx = fmaxf(mx, pt_max[par]);
-            const uint64_t nmx2 = pack2(-mx, -mx);
-            uint64_t sum2 = 0ull;
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < NTOK / 4; ++j) {
-                float lo, hi;
-                unpack2(fadd2(t[j], nmx2), lo, hi);
+                    unpack2(fadd2(t[j], nmx2), lo, hi);
 #ifdef SODT_X_NOEXP
-                const float p0 = lo * 0.001f + 1.f, p1 = hi * 0.001f + 1.f;
+                    const float p0 = lo * 0.001f + 1.f, p1 = hi * 0.001f + 1.f;
 #else
-                const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
+                    const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
 #endif
-                sum2 = fadd2(sum2, pack2(p0, p1));
-                pk[j] = pack_bf16(p0, p1);
-            }
-            float sum_cur;
-            {
+                    sum2 = fadd2(sum2, pack2(p0, p1));
+                    pk[pr][j] = pack_bf16(p0, p1);
+                }
                 float a, b;
                 unpack2(sum2, a, b);
-                sum_cur = a + b;
+                sum_cur[pr] = a + b;
             }
-            if (row == 0 && half == 0) TRACE(g, tr_u, 3);
+            if (row == 0 && half == 0) TRACE(g, stg, 3);
             if (k > 0) {                               // previous unit of this group: its P / O columns are free again
                 mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
-                if (row == 0 && half == 0) TRACE(g, tr_u, 4);
                 fence_after_sync();
                 epilogue();
-                if (row == 0 && half == 0) TRACE(g, tr_u, 5);
             }
-            my_sum[par] = sum_cur;                     // the partner reads it in its epilogue, after the next exchange barrier
-            tmem_st16(tP, pk);
+#pragma unroll
+            for (int pr = 0; pr < HPB; ++pr) {
+                my_sum[par * XPAR + pr * XPAIR] = sum_cur[pr];   // the partner reads it in its epilogue, after the next exchange barrier
+                tmem_st16(tP + pr * 32, pk[pr]);
+                prev_sum[pr] = sum_cur[pr];
+            }
             tmem_wait_st();
             fence_before_sync();
             mbar_arrive(&p_full[g]);
-            if (row == 0 && half == 0) TRACE(g, tr_u, 6);
-            prev_sum = sum_cur; prev_pr = pr; prev_stage = stg; prev_k = k;
-#pragma unroll
-            for (int i = 0; i < NG; ++i) advance();
+            if (row == 0 && half == 0) TRACE(g, stg, 6);
+            prev_stg = stg; prev_par = par;
+            gi += NG;
+            while (gi >= groups) { gi -= groups; ++win_it; }
         }
         if (k > 0) {
             mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
             fence_after_sync();
-            asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the partner's last row sum is visible
+            asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the partner's last row sums are visible
             epilogue();
         }
     }

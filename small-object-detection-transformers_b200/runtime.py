@@ -44,18 +44,43 @@ class DetectionBuffer:
         return flat[:n].view(batch, max_det, 6), flat[n:n + batch].view(torch.int32)
 
 
+class GatheredDetections:
+    """The all-gathered flat buffers of every rank, split lazily: ``det`` [world, B, max_det, 6] and ``counts`` [world, B] are
+    strided VIEWS of the receive buffer (no re-assembly kernels); ``tensors()`` makes the contiguous [world*B, ...] copies."""
+
+    def __init__(self, flat, world, batch, max_det=MAX_DET, event=None):
+        self.flat, self.world, self.batch, self.max_det, self.event = flat, world, batch, max_det, event
+        rows = flat.view(world, -1)
+        n = batch * max_det * 6
+        self.det = rows[:, :n].unflatten(1, (batch, max_det, 6))
+        self.counts = rows[:, n:n + batch].view(torch.int32)
+
+    def wait(self, stream=None):
+        """Makes ``stream`` (default: the current one) wait for the gather; call before reading the views on the device."""
+        if self.event is not None:
+            (stream or torch.cuda.current_stream(self.flat.device)).wait_event(self.event)
+        return self
+
+    def tensors(self):
+        self.wait()
+        return self.det.reshape(-1, self.max_det, 6), self.counts.reshape(-1)
+
+
 def allgather_detections(buf, group=None):
-    """All-gathers every rank's DetectionBuffer (equal local batch).  Returns (det [world*B,300,6],
-    counts [world*B]) in rank order == global image order for contiguous sharding."""
+    """All-gathers every rank's DetectionBuffer.  Returns (det [world*B,300,6], counts [world*B]) in rank order == global
+    image order for contiguous sharding.  The ranks must hold EQUAL local batches (all_gather_into_tensor has one block size):
+    an uneven split from shard_range must be padded by the caller; checked here."""
     world = dist.get_world_size(group)
+    sizes = torch.tensor([buf.batch], dtype=torch.int64, device=buf.flat.device)
+    if world > 1:
+        lo, hi = sizes.clone(), sizes.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        if int(lo) != int(hi):
+            raise ValueError(f"allgather_detections needs equal local batches on every rank (got {int(lo)}..{int(hi)}): pad the shards")
     recv = torch.empty(world * buf.flat.numel(), dtype=buf.flat.dtype, device=buf.flat.device)
     dist.all_gather_into_tensor(recv, buf.flat, group=group)
-    dets, counts = [], []
-    for r in range(world):
-        d, c = DetectionBuffer.split(recv[r * buf.flat.numel():(r + 1) * buf.flat.numel()], buf.batch, buf.max_det)
-        dets.append(d)
-        counts.append(c)
-    return torch.cat(dets), torch.cat(counts)
+    return GatheredDetections(recv, world, buf.batch, buf.max_det).tensors()
 
 
 class Detector:
@@ -234,9 +259,12 @@ class Detector:
             nxt = next(it, None)
             staged = upload(nxt) if nxt is not None else None      # overlaps with the compute below
             dev_ring, host_ring, gather_ring = self._rings(rgb.shape[0], world=world)
-            buf, host = dev_ring[i % len(dev_ring)], host_ring[i % len(host_ring)]
+            host = host_ring[i % len(host_ring)]
             compute.wait_event(ev)
-            self.detect_device(rgb, ir, buf)
+            if pending is not None:
+                compute.wait_event(pending[1])         # the previous read-back / gather has finished with the step's output buffer
+            # graph path: the replayed NMS writes into the graph's own buffer, which is read back / gathered in place (no pack copy)
+            buf = self.detect_device(rgb, ir)
             rgb.record_stream(compute)
             ir.record_stream(compute)
             src = buf.flat
@@ -276,11 +304,36 @@ class ShardedDetector:
     def local_slice(self, n_images):
         return shard_range(n_images, self.rank, self.world)
 
+        self.comm_stream = torch.cuda.Stream(detector.device) if detector.device.type == "cuda" else None
+        self._recv = {}                 # ring of receive buffers per batch size
+        self._step = 0
+        self._pending = None            # gather of the previous step (its send buffer is the next step's NMS output)
+
     @torch.no_grad()
     def detect_device(self, rgb_u8_local, ir_u8_local):
-        """Each rank passes ITS shard (equal sizes); returns the gathered detections of all ranks."""
-        buf = self.detector.detect_device(rgb_u8_local, ir_u8_local)
-        return allgather_detections(buf, self.group)
+        """Each rank passes ITS shard (equal sizes); returns the gathered detections of all ranks as a GatheredDetections
+        (views of the receive buffer; ``.tensors()`` for contiguous copies).  The NMS kernel of the (graph-replayed) step writes
+        straight into the buffer NCCL sends; the all-gather runs on a side stream and overlaps the next step, which only waits
+        for it before its own NMS output could overwrite the send buffer."""
+        det = self.detector
+        compute = torch.cuda.current_stream(det.device)
+        if self._pending is not None:                     # the previous gather still reads the send buffer this step rewrites
+            compute.wait_event(self._pending)
+        buf = det.detect_device(rgb_u8_local, ir_u8_local)
+        n = buf.flat.numel()
+        ring = self._recv.setdefault(buf.batch, [torch.empty(self.world * n, dtype=torch.float32, device=det.device) for _ in range(3)])
+        recv = ring[self._step % len(ring)]
+        self._step += 1
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            dist.all_gather_into_tensor(recv, buf.flat, group=self.group)
+            done = torch.cuda.Event()
+            done.record(self.comm_stream)
+        recv.record_stream(self.comm_stream)
+        self._pending = done
+        return GatheredDetections(recv, self.world, buf.batch, buf.max_det, event=done)
 
     def detect_stream(self, local_batches):
         """Pipelined host API (see Detector.detect_stream): each rank feeds its own shard of every batch and receives the
