@@ -130,6 +130,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[16]) { tmem_st16(taddr, r); }
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st32(taddr, r); }
+
 // --------------------------------------------------------------------------------- tcgen05.mma
 // Shared-memory matrix descriptor, SWIZZLE_NONE ("interleaved" canonical layout of 8x16-byte
 // core matrices).  lbo / sbo in bytes:

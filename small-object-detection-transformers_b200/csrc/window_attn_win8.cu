@@ -12,13 +12,12 @@
 // An MMA instruction of these shapes costs ~100 cycles of the tensor pipe whatever N is (64 with independent accumulators;
 // tests/probes/umma_probe.cu), so the kernel is organised around the FEWEST instructions: the 128 TMEM lanes hold TWO HEADS of
 // one window (lane = 64 * head parity + query token) and every MMA is unmasked.
-// Stage = one window x 64 channels (4 heads of 16 or 2 heads of 32 channels): five boxes, 40 KB
-//   QA, KA   q / k channels [c0, c0 + 64) of the window's tokens           QB, KB   the same tokens, channels [c0 + hd, c0 + hd + 64)
-//   V        v channels [c0, c0 + 64)
-// so that an operand of 128 rows starting in QA (KA) at the even head's column offset continues in QB (KB) with the ODD head's
-// channels at the same column offset (the second fetch of the same lines is served by L2).  Per head pair
-//   S[128x128]  ONE tcgen05.mma per 16 channels (SS, M=128, N=128): lane (p, i), column (p', j) = q_{head p}(i) . k_{head p'}(j);
-//               lane half p reads its own 64 columns [64 p, 64 p + 64); the cross-head half is discarded
+// Stage = one window x 64 channels (4 heads of 16 or 2 heads of 32 channels): three boxes K, Q, V = 24 KB, seven stages in
+// flight (a TMA load takes ~2700 cycles from issue to data under load: the depth of this ring, not the softmax, bounded the
+// kernel until it reached 5+ stages).  Per head pair
+//   S[128x64]   two lane-masked tcgen05.mma per 16 channels (SS, M=128, N=64): lanes 0-63 = even head, lanes 64-127 = odd head.
+//               Both read the SAME Q tile: the odd head's A operand starts one tile below Q at the odd head's column offset, so its
+//               rows 64-127 are Q's tokens (its rows 0-63, the K tile, feed disabled lanes)
 //   softmax     one thread per (head, query row): tcgen05.ld of its 64 scores, relative position bias (closed-form index
 //               into a shared-memory table laid out for 8-byte loads), shifted-window mask from two 64-bit region masks
 //               (border windows only), packed fp32x2 arithmetic, exp2 on the MUFU; P goes back to TMEM as packed bf16
@@ -48,13 +47,18 @@ constexpr int WS = 8;
 constexpr int NTOK = 64;                 // tokens per window
 constexpr int ROWS = 128;                // TMEM lanes = 2 heads x 64 tokens
 constexpr int NG = 2;                    // softmax groups
-constexpr int SM_WARPS = 8;              // softmax warps per group: two threads per score row
+#ifndef SODT_WIN8_TPR
+#define SODT_WIN8_TPR 1
+#endif
+constexpr int TPR = SODT_WIN8_TPR;       // threads per score row (1 or 2): 2 = warps w and w + 4 of a group split the 64 keys
+constexpr int KPT = NTOK / TPR;          // keys per thread
+constexpr int SM_WARPS = 4 * TPR;        // softmax warps per group
 constexpr int NTHREADS = (NG * SM_WARPS + NG + 2) * 32;
 constexpr int MMA_WARP0 = NG * SM_WARPS, TMA_WARP = MMA_WARP0 + NG, STORE_WARP = TMA_WARP + 1;   // one MMA-issuing warp per softmax group
-constexpr int STAGES = 4;
+constexpr int STAGES = TPR == 1 ? 7 : 6;       // 24 KB each; two threads per row spend 16 KB on the exchange buffer instead
 constexpr int WIN_BYTES = NTOK * 128;         // one box: 64 token rows x 128 B
-constexpr int STAGE_BYTES = 4 * WIN_BYTES;    // QA QB K V
-constexpr int OFF_Q = 0, OFF_K = 2 * WIN_BYTES, OFF_V = 3 * WIN_BYTES;
+constexpr int STAGE_BYTES = 3 * WIN_BYTES;    // K Q V (Q is NOT first: the odd heads' A operand starts one tile below it, see the MMA issuer)
+constexpr int OFF_K = 0, OFF_Q = WIN_BYTES, OFF_V = 2 * WIN_BYTES;
 constexpr int OT_BYTES = WIN_BYTES;           // output staging tile of a stage
 constexpr int OT_RING = 4;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -70,7 +74,7 @@ constexpr int TAB_COPIES = 2;
 constexpr uint32_t TM_S = 0, TM_P = 256, TM_O = 384;
 constexpr uint32_t ALL = 0xFFFFFFFFu;
 constexpr int XCH_BAR0 = 2;                   // named barriers 2, 3: row-maximum exchange inside a softmax group
-constexpr int XCH_FLOATS = 2 * 2 * 2 * NG * 2 * ROWS;    // {max, sum} x unit parity x head pair x group x half x row
+constexpr int XCH_FLOATS = TPR == 2 ? 2 * 2 * 2 * NG * 2 * ROWS : 0;    // {max, sum} x unit parity x head pair x group x half x row
 
 __global__ void prep_table_win8_kernel(const float* __restrict__ table, float* __restrict__ out, int heads) {
     const int cs = tab_copy_stride(heads);
@@ -115,16 +119,16 @@ struct Maps {
     CUtensorMap full, row8, row_a, row_b;     // boxes (64, 8, 8), (64, 8, 1), (64, 8 - shift, 1), (64, shift, 1)
 };
 
-// The four boxes of a stage (QA, QB, K, V), issued by the whole producer warp: a window inside the image is one box per
-// operand tile (lanes 0-3); a window that wraps around the image is 8 row boxes per tile, or 16 row parts when the rows
-// themselves wrap (32 / 64 small copies spread over the 32 lanes: one lane needs ~130 cycles per TMA instruction).
+// The three boxes of a stage (K, Q, V), issued by the whole producer warp: a window inside the image is one box per
+// operand tile (lanes 0-2); a window that wraps around the image is 8 row boxes per tile, or 16 row parts when the rows
+// themselves wrap (24 / 48 small copies spread over the 32 lanes: one lane needs ~130 cycles per TMA instruction).
 template <int HD>
 __device__ __forceinline__ void load_stage(const Maps& m, const Geo& geo, const WinBox& b, uint32_t st, int c0, int C, uint64_t* bar, int lane) {
     const int per_box = !b.wrap_x && !b.wrap_y ? 1 : (b.wrap_x ? 2 * WS : WS);
-    for (int item = lane; item < 4 * per_box; item += 32) {
+    for (int item = lane; item < 3 * per_box; item += 32) {
         const int bi = item / per_box, sub = item - bi * per_box;
-        const uint32_t sm = st + bi * WIN_BYTES;                                 // tiles in the order QA QB K V
-        const int ch = (bi < 2 ? 0 : bi - 1) * C + c0 + (bi == 1 ? HD : 0);       // q, q + hd, k, v
+        const uint32_t sm = st + bi * WIN_BYTES;                                 // tiles in the order K Q V
+        const int ch = (bi == 0 ? C : bi == 1 ? 0 : 2 * C) + c0;
         if (per_box == 1) {
             tma::load_3d(sm, &m.full, bar, ch, b.x0, b.yg_base + b.y0);
         } else {
@@ -179,8 +183,8 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
-        for (int s = 0; s < OT_RING; ++s) { mbar_init(&ot_full[s], 2 * ROWS); mbar_init(&ot_free[s], 1); }
-        for (int g = 0; g < NG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], 2 * ROWS); mbar_init(&p_full[g], 2 * ROWS); mbar_init(&pv_done[g], 1); }
+        for (int s = 0; s < OT_RING; ++s) { mbar_init(&ot_full[s], TPR * ROWS); mbar_init(&ot_free[s], 1); }
+        for (int g = 0; g < NG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], TPR * ROWS); mbar_init(&p_full[g], TPR * ROWS); mbar_init(&pv_done[g], 1); }
         fence_barrier_init();
     }
     if (warp == MMA_WARP0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
@@ -256,15 +260,18 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
                 fence_after_sync();
 #pragma unroll
                 for (int pr = 0; pr < HPB; ++pr) {
-                    // lanes 0-63: even head = Q rows of QA x K at the even head's columns; lanes 64-127: odd head = Q rows of QB (the same
-                    // tokens, channels shifted by one head) x K at the odd head's columns
+                    // lanes 0-63 (even head): A = the 128 rows from the Q tile on, at the even head's columns (rows 64-127 = the V
+                    // tile: their output lanes are disabled, so their content does not matter), B = K at the even head's columns;
+                    // lanes 64-127 (odd head): A starts one tile BELOW Q, at the odd head's columns, so that its rows 64-127 are the
+                    // Q tile's 64 tokens (rows 0-63 = the K tile, disabled lanes), B = K at the odd head's columns.
+                    // No second, channel-shifted copy of Q is needed.
                     const uint32_t off = (uint32_t)(slot * STAGE_BYTES + pr * (2 * HD * 2)) >> 4;
                     const uint64_t qd = d0 + off + (OFF_Q >> 4), kd = d0 + off + (OFF_K >> 4);
+                    const uint64_t qd_odd = qd - (WIN_BYTES >> 4) + ((HD * 2) >> 4), kd_odd = kd + ((HD * 2) >> 4);
 #pragma unroll
                     for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd + 2 * ks, kd + 2 * ks, idesc_s, ks > 0, 0u, 0u, ALL, ALL);
 #pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks)
-                        mma_ss_masked(tS + pr * 64, qd + 2 * ks, kd + ((HD * 2) >> 4) + 2 * ks, idesc_s, ks > 0, ALL, ALL, 0u, 0u);
+                    for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd_odd + 2 * ks, kd_odd + 2 * ks, idesc_s, ks > 0, ALL, ALL, 0u, 0u);
                 }
                 mma_commit(&s_full[g]);
                 TRACE(2, stg, 3);
@@ -297,19 +304,19 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         // Two threads per score row: warps w and w + 4 of a group own the same 32 TMEM lanes (a warp reaches lane quarter
         // warp % 4 only) and split the 64 keys, so 16 softmax warps (4 per SM sub-partition) cover one another's tensor-memory,
         // shared-memory and MUFU latencies; row maximum and row sum are exchanged through shared memory.
-        const int g = warp >> 3;                       // group g takes stages g, g + NG, ...
-        const int half = (warp >> 2) & 1;              // keys [32 half, 32 half + 32) = key rows yj in [4 half, 4 half + 4)
+        const int g = warp / SM_WARPS;                 // group g takes stages g, g + NG, ...
+        const int half = TPR == 2 ? (warp >> 2) & 1 : 0;    // keys [KPT half, KPT half + KPT) = key rows yj from (KPT / 8) half
         const int row = (warp & 3) * 32 + lane;        // TMEM lane = 64 * (head parity) + query token
         const int hp = row >> 6, ti = row & 63, ty = ti >> 3, tx = ti & 7;
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tS = tm + TM_S + g * 128 + half * 32 + lane_addr;
-        const uint32_t tP = tm + TM_P + g * 64 + half * 16 + lane_addr;
-        const uint32_t tO = tm + TM_O + g * 64 + hp * HD + half * (HD / 2) + lane_addr;
+        const uint32_t tS = tm + TM_S + g * 128 + half * KPT + lane_addr;
+        const uint32_t tP = tm + TM_P + g * 64 + half * (KPT / 2) + lane_addr;
+        const uint32_t tO = tm + TM_O + g * 64 + hp * HD + half * (HD / TPR) + lane_addr;
         const float c = scale * LOG2E, mv2 = mask_value * LOG2E;
         const uint64_t c2 = pack2(c, c);
         // bias row of this thread's first key row: copy (7 - tx) % 2 at entry (7 - tx) - copy (even), table row dy = ty + 7 - yj
         const int r0 = WS - 1 - tx, cp = r0 & 1;
-        const float* tab_row = tab + cp * tab_copy_stride(heads) + (ty + WS - 1 - 4 * half) * TAB_ROW + (r0 - cp);
+        const float* tab_row = tab + cp * tab_copy_stride(heads) + (ty + WS - 1 - (KPT / 8) * half) * TAB_ROW + (r0 - cp);
         const int s_ = geo.shift;
         const uint64_t yhi = s_ > 0 ? (~0ull << (8 * (WS - s_))) : 0ull;                       // keys with ty >= ws - shift
         const uint64_t xhi = s_ > 0 ? 0x0101010101010101ull * (uint64_t)((0xFFu << (WS - s_)) & 0xFFu) : 0ull;  // tx >= ws - shift
@@ -320,7 +327,7 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         float* my_sum = my_max + XCH_FLOATS / 2;
         float* pt_sum = pt_max + XCH_FLOATS / 2;
         constexpr int XPAIR = NG * 2 * ROWS, XPAR = 2 * XPAIR;      // strides of the pair / parity dimensions
-        uint32_t mbits = 0;
+        uint64_t mbits = 0;
         bool any_mask = false;
         float prev_sum[HPB] = {};
         int prev_stg = 0, prev_par = 0;
@@ -330,20 +337,25 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         auto epilogue = [&]() {
             const int slot = prev_stg & (OT_RING - 1);
             const uint32_t tile_s = ot_base + (uint32_t)slot * OT_BYTES;
-            uint32_t o[HPB][HD / 2];
+            constexpr int OC = HD / TPR;                  // O columns per thread
+            uint32_t o[HPB][OC];
             float inv[HPB];
 #pragma unroll
             for (int pr = 0; pr < HPB; ++pr) {
-                if constexpr (HD == 16) tmem_ld8(tO + pr * (2 * HD), o[pr]); else tmem_ld16(tO + pr * (2 * HD), o[pr]);
-                inv[pr] = fast_rcp(prev_sum[pr] + pt_sum[prev_par * XPAR + pr * XPAIR]);      // written before the partner's p_full arrival
+                if constexpr (OC == 8) tmem_ld8(tO + pr * (2 * HD), o[pr]);
+                else if constexpr (OC == 16) tmem_ld16(tO + pr * (2 * HD), o[pr]);
+                else tmem_ld32(tO + pr * (2 * HD), o[pr]);
+                float total = prev_sum[pr];
+                if constexpr (TPR == 2) total += pt_sum[prev_par * XPAR + pr * XPAIR];      // written before the partner's p_full arrival
+                inv[pr] = fast_rcp(total);
             }
             tmem_wait_ld();
             if (prev_stg >= OT_RING) mbar_wait(&ot_free[slot], (uint32_t)(((prev_stg / OT_RING) - 1) & 1));   // the slot's previous tile has left
 #pragma unroll
             for (int pr = 0; pr < HPB; ++pr) {
 #pragma unroll
-                for (int j = 0; j < HD / 2; j += 8) {
-                    const uint32_t chunk = (uint32_t)(((2 * pr + hp) * HD + half * (HD / 2) + j) >> 3) ^ sw;
+                for (int j = 0; j < OC; j += 8) {
+                    const uint32_t chunk = (uint32_t)(((2 * pr + hp) * HD + half * OC + j) >> 3) ^ sw;
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
                                  "r"(pack_bf16(__uint_as_float(o[pr][j]) * inv[pr], __uint_as_float(o[pr][j + 1]) * inv[pr])),
                                  "r"(pack_bf16(__uint_as_float(o[pr][j + 2]) * inv[pr], __uint_as_float(o[pr][j + 3]) * inv[pr])),
@@ -365,7 +377,7 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
                     if (wb.last_row) mb |= (ty >= WS - s_) ? ~yhi : yhi;
                     if (wb.last_col) mb |= (tx >= WS - s_) ? ~xhi : xhi;
                 }
-                mbits = (uint32_t)(mb >> (32 * half));
+                mbits = TPR == 2 ? (mb >> (32 * half)) & 0xFFFFFFFFull : mb;
                 any_mask = s_ > 0 && (wb.last_row || wb.last_col);          // uniform over the group
             }
             const int par = k & 1;
@@ -374,19 +386,21 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
             if (row == 0 && half == 0) TRACE(g, stg, 1);
             fence_after_sync();
             float sum_cur[HPB];
-            uint32_t pk[HPB][16];
+            bool epi_done = k == 0;
 #pragma unroll
             for (int pr = 0; pr < HPB; ++pr) {
                 const int h = gi * G + 2 * pr + hp;
-                uint64_t t[NTOK / 4];
-                {
-                    uint32_t ra[32];
-                    tmem_ld32(tS + pr * 64, ra);
-                    tmem_wait_ld();
-                    if (pr == HPB - 1) { fence_before_sync(); mbar_arrive(&s_free[g]); }       // the unit's scores are in registers
-                    const float* tb = tab_row + h * TAB_HEAD;
+                uint64_t t[KPT / 2];
+                uint32_t pk[KPT / 2];
 #pragma unroll
-                    for (int yj = 0; yj < WS / 2; ++yj) {   // t = s * (scale log2 e) + bias, two scores per FFMA2
+                for (int part = 0; part < KPT / 32; ++part) {
+                    uint32_t ra[32];
+                    tmem_ld32(tS + pr * 64 + part * 32, ra);
+                    tmem_wait_ld();
+                    if (pr == HPB - 1 && part == KPT / 32 - 1) { fence_before_sync(); mbar_arrive(&s_free[g]); }   // the unit's scores are in registers
+                    const float* tb = tab_row + h * TAB_HEAD - part * 4 * TAB_ROW;
+#pragma unroll
+                    for (int yj = 0; yj < 4; ++yj) {        // t = s * (scale log2 e) + bias, two scores per FFMA2
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
 #ifdef SODT_X_NOBIAS
@@ -394,17 +408,17 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
 #else
                             const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
 #endif
-                            t[yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
+                            t[part * 16 + yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
                         }
                     }
                 }
                 if (any_mask) {                            // group-uniform: only windows of the last window row / column
 #pragma unroll
-                    for (int j = 0; j < NTOK / 4; ++j) {
+                    for (int j = 0; j < KPT / 2; ++j) {
                         float lo, hi;
                         unpack2(t[j], lo, hi);
-                        if ((mbits >> (2 * j)) & 1u) lo += mv2;
-                        if ((mbits >> (2 * j + 1)) & 1u) hi += mv2;
+                        if ((mbits >> (2 * j)) & 1ull) lo += mv2;
+                        if ((mbits >> (2 * j + 1)) & 1ull) hi += mv2;
                         t[j] = pack2(lo, hi);
                     }
                 }
@@ -416,19 +430,21 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
                     m4[q] = fmaxf(lo, hi);
                 }
 #pragma unroll
-                for (int j = 4; j < NTOK / 4; ++j) {
+                for (int j = 4; j < KPT / 2; ++j) {
                     float lo, hi;
                     unpack2(t[j], lo, hi);
                     m4[j & 3] = fmax3(m4[j & 3], lo, hi);
                 }
                 float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
-                my_max[par * XPAR + pr * XPAIR] = mx;
-                asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the two halves of every row have published their maxima
-                mx = fmaxf(mx, pt_max[par * XPAR + pr * XPAIR]);
+                if constexpr (TPR == 2) {
+                    my_max[par * XPAR + pr * XPAIR] = mx;
+                    asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the two halves of every row have published their maxima
+                    mx = fmaxf(mx, pt_max[par * XPAR + pr * XPAIR]);
+                }
                 const uint64_t nmx2 = pack2(-mx, -mx);
                 uint64_t sum2 = 0ull;
 #pragma unroll
-                for (int j = 0; j < NTOK / 4; ++j) {
+                for (int j = 0; j < KPT / 2; ++j) {
                     float lo, hi;
                     unpack2(fadd2(t[j], nmx2), lo, hi);
 #ifdef SODT_X_NOEXP
@@ -437,22 +453,23 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
                     const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
 #endif
                     sum2 = fadd2(sum2, pack2(p0, p1));
-                    pk[pr][j] = pack_bf16(p0, p1);
+                    pk[j] = pack_bf16(p0, p1);
                 }
                 float a, b;
                 unpack2(sum2, a, b);
                 sum_cur[pr] = a + b;
+                if (!epi_done) {                       // previous unit of this group: its P / O columns are free again
+                    epi_done = true;
+                    mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
+                    fence_after_sync();
+                    epilogue();
+                }
+                tmem_st(tP + pr * 32, pk);
             }
             if (row == 0 && half == 0) TRACE(g, stg, 3);
-            if (k > 0) {                               // previous unit of this group: its P / O columns are free again
-                mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
-                fence_after_sync();
-                epilogue();
-            }
 #pragma unroll
             for (int pr = 0; pr < HPB; ++pr) {
-                my_sum[par * XPAR + pr * XPAIR] = sum_cur[pr];   // the partner reads it in its epilogue, after the next exchange barrier
-                tmem_st16(tP + pr * 32, pk[pr]);
+                if constexpr (TPR == 2) my_sum[par * XPAR + pr * XPAIR] = sum_cur[pr];   // the partner reads it in its epilogue, after the next exchange barrier
                 prev_sum[pr] = sum_cur[pr];
             }
             tmem_wait_st();
@@ -466,7 +483,7 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         if (k > 0) {
             mbar_wait(&pv_done[g], (uint32_t)((k - 1) & 1));
             fence_after_sync();
-            asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the partner's last row sums are visible
+            if constexpr (TPR == 2) asm volatile("bar.sync %0, 256;" ::"r"(XCH_BAR0 + g) : "memory");      // the partner's last row sums are visible
             epilogue();
         }
     }
