@@ -334,6 +334,12 @@ class SwinTransformerBlock(nn.Module):
                                      self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
                                      mask_value=MASK_VALUE)
             x, st = ops.linear(o.view(B, L, C), attn.proj.weight, attn.proj.bias, residual=x, want_stats=True)
+            if (mlp.linear and isinstance(mlp.act, nn.GELU) and mlp.act.approximate == "none"
+                    and ops.mlp_ln_supported(x, mlp.fc1.weight.shape[0]) and mlp.fc2.weight.shape[0] == C):
+                # the whole MLP half as one kernel: the [B*L, 4C] hidden activation stays in tensor memory
+                r = ops.mlp_ln(x, (prep(st, self.norm2.eps), self.norm2.weight, self.norm2.bias, self.norm2.eps),
+                               mlp.fc1.weight, mlp.fc1.bias, mlp.fc2.weight, mlp.fc2.bias, want_stats=want_stats)
+                return r
             h = mlp.hidden(x, H, W, ln=(self.norm2, prep(st, self.norm2.eps)))
             if want_stats:
                 return ops.linear(h, mlp.fc2.weight, mlp.fc2.bias, residual=x, want_stats=True)

@@ -533,6 +533,49 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
     return y
 
 
+USE_FUSED_MLP = True    # fc1 + GELU + fc2 + residual of the linear-MLP Swin blocks as one kernel (hidden stays in TMEM)
+
+
+def mlp_ln_supported(x, hidden):
+    """True if ``mlp_ln`` can run: bf16 CUDA rows of width 64 / 128 / 192, hidden a multiple of 128 (>= 256)."""
+    C = x.shape[-1]
+    return bool(USE_TC_LINEAR and USE_LN_FOLD and USE_FUSED_MLP and x.is_cuda and x.dtype == torch.bfloat16
+                and _capi.lib().sodt_mlp_supported(x.numel() // C, C, hidden, 1))
+
+
+def mlp_ln(x, ln, fc1_weight, fc1_bias, fc2_weight, fc2_bias, want_stats=False):
+    """``x + fc2(GELU(fc1(LayerNorm(x))))`` over the last dim in one kernel (sodt_mlp_ln_fwd): the second half of a Swin block
+    with a linear MLP (reference backbone_vit.py:885-890,1128).  ``ln = (stats, ln_weight, ln_bias[, eps])`` as in ``linear``;
+    ``want_stats``: also return the [C/64, M, 2] partial row statistics of the result -> (out, partials)."""
+    _require_cuda(x, fc1_weight, fc1_bias, fc2_weight, fc2_bias)
+    C = x.shape[-1]
+    M = x.numel() // C
+    hidden = fc1_weight.shape[0]
+    if tuple(fc1_weight.shape) != (hidden, C) or tuple(fc2_weight.shape) != (C, hidden):
+        raise ValueError("fc1_weight must be [hidden, C] and fc2_weight [C, hidden]")
+    if not mlp_ln_supported(x, hidden) or fc2_weight.dtype != torch.bfloat16:
+        raise _capi.SodtError("mlp_ln needs a shape covered by the fused MLP kernel (mlp_ln_supported)")
+    mr, ln_w, ln_b, ln_eps = (tuple(ln) + (1e-5,))[:4]
+    if mr.dtype != torch.float32 or not mr.is_contiguous() or tuple(mr.shape[-2:]) != (M, 2) or mr.dim() > 3:
+        raise ValueError("ln statistics must be contiguous fp32 [M, 2] or [boxes, M, 2]")
+    ln_boxes = mr.shape[0] if mr.dim() == 3 else 0
+    if ln_boxes > 3:
+        raise ValueError("more than 3 partial pairs per row: reduce them with finalize_stats first")
+    xa, ldx = _rows(x)
+    w1, colsum, b1 = fold_layernorm(fc1_weight, fc1_bias, ln_w, ln_b)
+    w2 = fc2_weight.detach().contiguous()
+    b2 = _as_f32(fc2_bias) if fc2_bias is not None else cached_derived(fc2_weight, "zero_bias", lambda w: torch.zeros(
+        w.shape[0], dtype=torch.float32, device=w.device))
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    stats_out = torch.empty((C // 64, M, 2), dtype=torch.float32, device=x.device) if want_stats else None
+    with torch.cuda.device(x.device), _Timed(f"mlp_ln[M={M},C={C},hidden={hidden},stats={want_stats}]"):
+        st = _capi.lib().sodt_mlp_ln_fwd(xa.data_ptr(), ldx, mr.data_ptr(), ln_boxes, float(ln_eps), colsum.data_ptr(), w1.data_ptr(),
+                                         b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out.data_ptr(), C, _ptr(stats_out), M, C, hidden,
+                                         1, _stream())
+    _capi.check(st, "sodt_mlp_ln_fwd")
+    return (out, stats_out) if want_stats else out
+
+
 def conv2d_nhwc_supported(x, cout, kh, kw):
     """True if ops.conv2d_nhwc runs ``x`` [B,H,W,Cin] on the tcgen05 tap-GEMM kernel."""
     if not (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and USE_TC_LINEAR):

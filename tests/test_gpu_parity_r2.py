@@ -354,3 +354,51 @@ def test_sryolo_configs_build_and_run(cfg, mode, ch):
     assert rel_err(raw16[0], raw32[0]) < 3e-2
     dets = non_max_suppression(pred32, conf_thres=1e-5, iou_thres=0.45)
     assert len(dets) == 2 and all(d.shape[1] == 6 for d in dets)
+
+
+# ------------------------------------------------------------------ fused MLP half of the Swin block (sodt_mlp_ln_fwd)
+@pytest.mark.parametrize("M,C,hidden", [(128, 192, 768), (200, 192, 768), (4096 + 72, 192, 768), (148 * 128 * 2 + 9, 192, 768),
+                                        (1000, 128, 512), (777, 64, 256), (640, 192, 384)])
+def test_mlp_fused_vs_fp64(M, C, hidden):
+    """x + fc2(GELU(fc1(LayerNorm(x)))) in one kernel (reference backbone_vit.py:885-890,1128) against a float64 evaluation of
+    the same bf16 operands: <= 4e-3 like the GEMM-shaped kernels; the emitted row statistics reproduce the row sums."""
+    o = ops()
+    g = torch.Generator().manual_seed(M + C)
+    x = torch.randn(M, C, generator=g).cuda().to(torch.bfloat16)
+    gam, bet = (1.0 + 0.1 * torch.randn(C, generator=g)).cuda(), (0.1 * torch.randn(C, generator=g)).cuda()
+    w1 = (torch.randn(hidden, C, generator=g) / C ** 0.5).cuda().to(torch.bfloat16)
+    b1 = (0.1 * torch.randn(hidden, generator=g)).cuda()
+    w2 = (torch.randn(C, hidden, generator=g) / hidden ** 0.5).cuda().to(torch.bfloat16)
+    b2 = (0.1 * torch.randn(C, generator=g)).cuda()
+    xd = x.double()
+    ref = xd + torch.nn.functional.gelu(torch.nn.functional.layer_norm(xd, (C,), gam.double(), bet.double(), 1e-5)
+                                        @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double()
+    for stats in (o.row_stats(x, 1e-5), None):
+        if stats is None:       # partial (sum, sum of squares) pairs per 64-column box, as a producing GEMM emits them
+            xs = x.float().view(M, C // 64, 64)
+            stats = torch.stack((xs.sum(-1), (xs * xs).sum(-1)), dim=-1).permute(1, 0, 2).contiguous()
+        out, part = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2, want_stats=True)
+        assert rel_err(out, ref) <= 4e-3
+        s = part.sum(0).double()
+        assert torch.allclose(s[:, 0], ref.sum(1), atol=2e-2, rtol=2e-3)
+        assert torch.allclose(s[:, 1], (ref * ref).sum(1), atol=2e-2, rtol=2e-3)
+    out2 = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2)
+    assert torch.equal(out2, out)
+
+
+def test_swin_block_fused_mlp_matches_gemm_pair():
+    """The block with the fused MLP kernel against the same block on the fc1 / fc2 GEMM pair (ops.USE_FUSED_MLP off)."""
+    from sodt_b200.basics.models.backbone_vit import SwinTransformerBlock
+    o = ops()
+    torch.manual_seed(3)
+    blk = SwinTransformerBlock(192, (32, 32), 12, window_size=8, shift_size=2).cuda().to(torch.bfloat16).eval()
+    x = torch.randn(2, 32 * 32, 192, device="cuda").to(torch.bfloat16)
+    with torch.no_grad():
+        y1, s1 = blk(x, want_stats=True)
+        o.USE_FUSED_MLP = False
+        try:
+            y0, s0 = blk(x, want_stats=True)
+        finally:
+            o.USE_FUSED_MLP = True
+    assert rel_err(y1, y0) <= 4e-3
+    assert torch.allclose(s1.sum(0), s0.sum(0), atol=5e-2, rtol=5e-3)
