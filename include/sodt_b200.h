@@ -259,12 +259,16 @@ int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, int ln
  * sodt_linear_ln_fwd (w1 = fc1.weight * diag(ln_weight) in bf16, ln_colsum its fp32 row sums, b1 = fc1.bias + fc1.weight .
  * ln_bias; ln_mean_rstd / ln_boxes as there).  The [M, hidden] activation never reaches HBM: it lives in tensor memory
  * between the two GEMMs.  stats_out (optional) receives the [C/64][M][2] partial row statistics of out for the next
- * block's norm1.  C in {64, 128, 192}, hidden a multiple of 128 and >= 256, bf16 only; out may alias neither x nor weights.
+ * block's norm1.  w2_fp16 = 0: w2 is fc2.weight in bf16 and the hidden activation is rounded to bf16 (bit-identical to
+ * sodt_linear_ln_fwd(GELU) followed by sodt_linear_ln_fwd(residual)).  w2_fp16 = 1: w2 is 0.5 * fc2.weight in IEEE fp16 and the
+ * hidden operand is the fp16 value of 2 GELU(.) (11-bit significand instead of 8; the GELU is evaluated in packed fp16
+ * either way, so the fp16 form skips two conversions per pair).  C in {64, 128, 192}, hidden a multiple of 128 and >= 256,
+ * bf16 activations only; out may alias neither x nor weights.
  */
 int sodt_mlp_supported(int M, int C, int hidden, int dtype);
 int sodt_mlp_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, int ln_boxes, float ln_eps, const float* ln_colsum,
                     const void* w1, const float* b1, const void* w2, const float* b2, void* out, int ldo,
-                    float* stats_out, int M, int C, int hidden, int dtype, void* stream);
+                    float* stats_out, int M, int C, int hidden, int w2_fp16, int dtype, void* stream);
 int sodt_row_stats(const void* x, long long ld, float* mean_rstd, long long rows, int C, float eps, int dtype, void* stream);
 int sodt_stats_finalize(const float* partials, int boxes, float* mean_rstd, long long rows, int C, float eps, void* stream);
 int sodt_conv2d_nhwc_supported(int B, int H, int W, int Cin, int Cout, int kh, int kw, int dtype);

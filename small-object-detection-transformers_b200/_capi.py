@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsodt_b200.so")
+LIB_PATH = os.environ.get("SODT_B200_LIB") or os.path.join(_PKG, "libsodt_b200.so")     # override: kernel experiments only
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -41,7 +41,7 @@ SIGNATURES = {
     "sodt_linear_strided_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_linear_ln_fwd": (_i, [_p, _i, _p, _i, _f, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "sodt_mlp_supported": (_i, [_i, _i, _i, _i]),
-    "sodt_mlp_ln_fwd": (_i, [_p, _i, _p, _i, _f, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p]),
+    "sodt_mlp_ln_fwd": (_i, [_p, _i, _p, _i, _f, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "sodt_row_stats": (_i, [_p, _ll, _p, _ll, _i, _f, _i, _p]),
     "sodt_stats_finalize": (_i, [_p, _i, _p, _ll, _i, _f, _p]),
     "sodt_conv2d_nhwc_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),

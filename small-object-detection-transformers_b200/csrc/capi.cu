@@ -87,15 +87,16 @@ extern "C" int sodt_mlp_supported(int M, int C, int hidden, int dtype) {
 
 extern "C" int sodt_mlp_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, int ln_boxes, float ln_eps, const float* ln_colsum,
                                const void* w1, const float* b1, const void* w2, const float* b2, void* out, int ldo,
-                               float* stats_out, int M, int C, int hidden, int dtype, void* stream) {
+                               float* stats_out, int M, int C, int hidden, int w2_fp16, int dtype, void* stream) {
     using namespace sodt;
+    if (w2_fp16 < 0 || w2_fp16 > 1) return SODT_ERR_INVALID_ARG;
     if (!x || !ln_mean_rstd || !ln_colsum || !w1 || !b1 || !w2 || !b2 || !out || M <= 0 || C <= 0 || hidden <= 0) return SODT_ERR_INVALID_ARG;
     if (ln_boxes < 0 || ln_boxes > 3 || ln_eps < 0.f) return SODT_ERR_INVALID_ARG;
     if (dtype != SODT_BF16 || !mlp_tc_supported(M, C, hidden)) return SODT_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w1) || !aligned16(w2) || !aligned16(out) || !aligned16(b1) || !aligned16(b2) || !aligned16(ln_colsum) ||
         (reinterpret_cast<uintptr_t>(ln_mean_rstd) & 7) || (reinterpret_cast<uintptr_t>(stats_out) & 7))
         return SODT_ERR_ALIGNMENT;
-    MlpTcArgs g{x, ldx, ln_mean_rstd, ln_boxes, ln_eps, ln_colsum, w1, b1, w2, b2, out, ldo, stats_out, M, C, hidden};
+    MlpTcArgs g{x, ldx, ln_mean_rstd, ln_boxes, ln_eps, ln_colsum, w1, b1, w2, b2, out, ldo, stats_out, M, C, hidden, w2_fp16};
     return mlp_tc(g, sm_count(), static_cast<cudaStream_t>(stream));
 }
 

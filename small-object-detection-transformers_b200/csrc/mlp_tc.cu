@@ -8,8 +8,10 @@
 //
 // One CTA per SM walks 128-row tiles.  Per tile, for every 128-column chunk c of the hidden layer:
 //   G1(c)   H[128 x 128]  = X[128 x C] . W1'[c]^T           SS MMAs, X tile resident in shared memory, W1' chunk streamed
-//   E(c)    H <- bf16(GELU(rstd H - mean rstd colsum + b1'))  LayerNorm folded as in linear_tc.cu; fp32 TMEM columns are
-//                                                           overwritten in place by the packed bf16 values
+//   E(c)    H <- GELU(rstd H - mean rstd colsum + b1')       LayerNorm folded as in linear_tc.cu; fp32 TMEM columns are
+//                                                           overwritten in place by the packed 16-bit values: bf16, or
+//                                                           (w2_fp16) fp16 values of 2 GELU against 0.5 W2 in fp16, which
+//                                                           saves the conversions of the packed-half GELU arithmetic
 //   G2(c)   O[128 x C]   += H[128 x 128] . W2[:, c]^T       TS MMAs (A = H from TMEM), W2 chunk streamed
 // and once per tile  out = O + b2 + x  (the residual is the X tile itself: it is updated in place in shared memory and
 // leaves through TMA stores), plus the partial row statistics the next block's norm1 needs.
@@ -46,6 +48,7 @@ template <int C> struct Layout {
     static constexpr int W1_SLOT = HC * 128;        // [128 hidden rows x 64 k]
     static constexpr int W2_SLOT = C * 128;         // [C rows x 64 hidden k]
     static constexpr int A_OFF = 0, W1_OFF = 2 * A_BYTES, W2_OFF = W1_OFF + R1 * W1_SLOT, TOTAL = W2_OFF + R2 * W2_SLOT;
+    static constexpr int VEC_OFF = TOTAL;                 // colsum[hidden] then b1[hidden] (fp32), staged once per CTA
     static constexpr int O_COL = 0, H_COL = 256;
 };
 
@@ -67,7 +70,14 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int C>
+// MLP_TRACE (experiments only): CTA 0 records clock64 at the hand-offs of its first 64 chunks into stats_out
+#ifdef MLP_TRACE
+#define TRACE(role, q, k) do { if (blockIdx.x == 0 && (q) < 64) reinterpret_cast<long long*>(p.stats_out)[((role) * 64 + (q)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TRACE(role, q, k) do { } while (0)
+#endif
+
+template <int C, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
               const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_o, const MlpParams p) {
@@ -109,16 +119,22 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             auto load_w1 = [&](int c) {
                 for (int kb = 0; kb < KB; ++kb) {
                     if (r1 > 0) mbar_wait(&w1_empty[s1], (uint32_t)((r1 - 1) & 1));
-                    tma::expect_tx(&w1_full[s1], L::W1_SLOT);
-                    tma_load_2d(sbase + L::W1_OFF + s1 * L::W1_SLOT, &tmap_w1, &w1_full[s1], kb * 64, c * HC);
+#ifdef MLP_DBG_NOLOAD
+                    if (r1 > 0) { mbar_arrive(&w1_full[s1]); } else
+#endif
+                    { tma::expect_tx(&w1_full[s1], L::W1_SLOT);
+                    tma_load_2d(sbase + L::W1_OFF + s1 * L::W1_SLOT, &tmap_w1, &w1_full[s1], kb * 64, c * HC); }
                     if (++s1 == R1) { s1 = 0; ++r1; }
                 }
             };
             auto load_w2 = [&](int c) {
                 for (int bx = 0; bx < 2; ++bx) {
                     if (r2 > 0) mbar_wait(&w2_empty[s2], (uint32_t)((r2 - 1) & 1));
-                    tma::expect_tx(&w2_full[s2], L::W2_SLOT);
-                    tma_load_2d(sbase + L::W2_OFF + s2 * L::W2_SLOT, &tmap_w2, &w2_full[s2], c * HC + bx * 64, 0);
+#ifdef MLP_DBG_NOLOAD
+                    if (r2 > 0) { mbar_arrive(&w2_full[s2]); } else
+#endif
+                    { tma::expect_tx(&w2_full[s2], L::W2_SLOT);
+                    tma_load_2d(sbase + L::W2_OFF + s2 * L::W2_SLOT, &tmap_w2, &w2_full[s2], c * HC + bx * 64, 0); }
                     if (++s2 == R2) { s2 = 0; ++r2; }
                 }
             };
@@ -136,7 +152,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0 && n_iter > 0) {
-            constexpr uint32_t id1 = idesc_bf16(BM, HC, false, false), id2 = idesc_bf16(BM, C, false, false);
+            constexpr uint32_t id1 = idesc_bf16(BM, HC, false, false);
+            constexpr uint32_t id2 = F16 ? idesc_f16(BM, C, false, false) : idesc_bf16(BM, C, false, false);
             int s1 = 0, r1 = 0, s2 = 0, r2 = 0;
             auto g1 = [&](int q) {
                 const int t = q / NCH, c = q - t * NCH, ab = t & 1, hb = q & 1;
@@ -155,8 +172,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             };
             auto g2 = [&](int q) {
                 const int t = q / NCH, c = q - t * NCH, hb = q & 1;
+                TRACE(0, q, 0);
                 mbar_wait(&h_ready[hb], (uint32_t)((q >> 1) & 1));
+                TRACE(0, q, 1);
                 if (c == 0 && t > 0) mbar_wait(&o_empty, (uint32_t)((t - 1) & 1));
+                TRACE(0, q, 2);
                 for (int bx = 0; bx < 2; ++bx) {
                     mbar_wait(&w2_full[s2], (uint32_t)(r2 & 1));
                     fence_after_sync();
@@ -169,12 +189,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
                     if (++s2 == R2) { s2 = 0; ++r2; }
                 }
                 if (c == NCH - 1) mma_commit(&o_full);
+                TRACE(0, q, 3);
             };
             g1(0);
             if (total > 1) g1(1);
             for (int q = 0; q < total; ++q) {           // G2(q) frees H buffer q % 2 for G1(q + 2): the tensor pipe executes in issue order
                 g2(q);
                 if (q + 2 < total) g1(q + 2);
+                TRACE(0, q, 4);
             }
         }
     } else {
@@ -184,6 +206,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
         const int sw = row & 7;
         const bool issuer = quarter == 0 && lane == 0;
         int pending_ab = -1;                                     // X buffer whose TMA store this thread still has to see read
+        // per-column LayerNorm / bias terms of fc1 from shared memory: global (L1) loads in the chunk loop queue behind the
+        // tensor core's operand reads
+        float* vec = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + L::VEC_OFF);
+        for (int i = tid; i < p.hidden; i += EPI_WARPS * 32) { vec[i] = p.colsum[i]; vec[p.hidden + i] = p.b1[i]; }
+        asm volatile("bar.sync 5, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        const uint32_t vec_s = sbase + L::VEC_OFF;
         auto load_mr = [&](int t) {                              // (mean, rstd) of this thread's row of tile t
             float2 r = make_float2(0.f, 1.f);
             if (t < n_iter) {
@@ -204,7 +232,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             return r;
         };
         // 32 fp32 columns [32 g, 32 g + 32) of H buffer hb -> LayerNorm terms, bias, GELU -> 16 packed bf16 columns in place
-        auto h_box = [&](int hb, int c, float2 mr) {
+        auto h_box = [&](int hb, int c, float2 mr, int q) {
             const int col0 = c * HC + g * 32;
             const uint32_t tsrc = tm + lane_addr + L::H_COL + hb * HC + g * 32;
             const float rstd = mr.y, nmr = -mr.x * mr.y;
@@ -213,25 +241,34 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             tmem_ld16(tsrc, ra);
             tmem_ld16(tsrc + 16, rb);
             tmem_wait_ld();
+            if (lane == 0 && (warp == 0 || warp == 15)) TRACE(1 + (warp == 15), q, 6);
 #pragma unroll
             for (int j = 0; j < 32; j += 16) {
                 uint32_t pk[8];
 #pragma unroll
                 for (int e = 0; e < 16; e += 4) {
-                    const float4 cs = __ldg(reinterpret_cast<const float4*>(p.colsum + col0 + j + e));
-                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b1 + col0 + j + e));
+                    float4 cs, bb;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w) : "r"(vec_s + 4 * (col0 + j + e)));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(vec_s + 4 * (p.hidden + col0 + j + e)));
                     const uint32_t* a = j ? rb : ra;
                     float v0, v1, v2, v3;
                     unpack2(ffma2(rstd2, pack2(__uint_as_float(a[e]), __uint_as_float(a[e + 1])), ffma2(nmr2, pack2(cs.x, cs.y), pack2(bb.x, bb.y))), v0, v1);
                     unpack2(ffma2(rstd2, pack2(__uint_as_float(a[e + 2]), __uint_as_float(a[e + 3])), ffma2(nmr2, pack2(cs.z, cs.w), pack2(bb.z, bb.w))), v2, v3);
-                    gelu_fast2(v0, v1);
-                    gelu_fast2(v2, v3);
-                    pk[e >> 1] = pack_bf16(v0, v1);
-                    pk[(e >> 1) + 1] = pack_bf16(v2, v3);
+                    if (F16) {                                    // fp16 hidden operand holding 2 GELU (w2 carries the 0.5)
+                        pk[e >> 1] = gelu2x_f16x2(v0, v1);
+                        pk[(e >> 1) + 1] = gelu2x_f16x2(v2, v3);
+                    } else {
+                        gelu_fast2(v0, v1);
+                        gelu_fast2(v2, v3);
+                        pk[e >> 1] = pack_bf16(v0, v1);
+                        pk[(e >> 1) + 1] = pack_bf16(v2, v3);
+                    }
                 }
                 tmem_st8(tsrc + (j >> 1), pk);
             }
+            if (lane == 0 && (warp == 0 || warp == 15)) TRACE(1 + (warp == 15), q, 7);
             tmem_wait_st();
+            if (lane == 0 && (warp == 0 || warp == 15)) TRACE(1 + (warp == 15), q, 3);
             fence_before_sync();
             mbar_arrive(&h_ready[hb]);
         };
@@ -273,8 +310,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             }
             fence_before_sync();
             mbar_arrive(&o_empty);                               // this thread's accumulator columns are in registers / stored
+#ifndef MLP_TRACE
             if (p.stats_out != nullptr && grow < p.M)
                 reinterpret_cast<float2*>(p.stats_out)[(size_t)j * p.M + grow] = make_float2(so, sso);
+#endif
             fence_proxy_async();
             asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
             if (issuer) {
@@ -300,10 +339,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
             const int hb = q & 1;
             if (c == 0) { mr = mr_next; mr_next = load_mr(t + 1); }
             if (issuer && pending_ab >= 0) { tma::store_wait_read<0>(); mbar_arrive(&a_empty[pending_ab]); pending_ab = -1; }
+            if (lane == 0 && (warp == 0 || warp == 15)) TRACE(1 + (warp == 15), q, 0);
             mbar_wait(&h_full[hb], (uint32_t)((q >> 1) & 1));
             fence_after_sync();
-            h_box(hb, c, mr);
+            if (lane == 0 && (warp == 0 || warp == 15)) TRACE(1 + (warp == 15), q, 1);
+            h_box(hb, c, mr, q);
+            if (lane == 0 && (warp == 0 || warp == 15)) TRACE(1 + (warp == 15), q, 4);
             if (c == 0 && t > 0) o_tile(t - 1);
+            if (lane == 0 && (warp == 0 || warp == 15)) TRACE(1 + (warp == 15), q, 5);
             if (++c == NCH) { c = 0; ++t; }
         }
         if (n_iter > 0) o_tile(n_iter - 1);
@@ -320,7 +363,7 @@ bool map_2d(CUtensorMap* m, const void* base, long long rows, long long cols, lo
     return tma::make_map_bf16(m, base, 2, dims, strides, box, is_output ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-template <int C>
+template <int C, bool F16>
 int launch(const MlpTcArgs& g, int num_sms, cudaStream_t stream) {
     using L = Layout<C>;
     CUtensorMap mx, mw1, mw2, mo;
@@ -331,8 +374,9 @@ int launch(const MlpTcArgs& g, int num_sms, cudaStream_t stream) {
     p.b1 = g.b1; p.colsum = g.ln_colsum; p.b2 = g.b2; p.ln_stats = g.ln_stats; p.stats_out = g.stats_out;
     p.M = g.M; p.hidden = g.hidden; p.num_m_tiles = (g.M + BM - 1) / BM; p.ln_boxes = g.ln_boxes;
     p.ln_inv_k = 1.f / (float)C; p.ln_eps = g.ln_eps;
-    const size_t smem = (size_t)L::TOTAL + 1024;
-    auto kern = mlp_tc_kernel<C>;
+    const size_t smem = (size_t)L::TOTAL + 1024 + (size_t)g.hidden * 8;
+    if (smem > 227 * 1024) return SODT_ERR_UNSUPPORTED;
+    auto kern = mlp_tc_kernel<C, F16>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = p.num_m_tiles < num_sms ? p.num_m_tiles : num_sms;
@@ -343,7 +387,9 @@ int launch(const MlpTcArgs& g, int num_sms, cudaStream_t stream) {
 }  // namespace
 
 bool mlp_tc_supported(int M, int C, int hidden) {
-    return M > 0 && (C == 64 || C == 128 || C == 192) && hidden >= 2 * HC && hidden % HC == 0 && (long long)M + BM < 2147483647LL;
+    if (!(M > 0 && (C == 64 || C == 128 || C == 192) && hidden >= 2 * HC && hidden % HC == 0 && (long long)M + BM < 2147483647LL)) return false;
+    const long long smem = 2LL * (C / 64) * BOX_BYTES + R1 * HC * 128 + R2 * C * 128 + 1024 + 8LL * hidden;      // Layout<C>::TOTAL + staged vectors
+    return smem <= 227 * 1024;
 }
 
 int mlp_tc(const MlpTcArgs& g, int num_sms, cudaStream_t stream) {
@@ -352,9 +398,9 @@ int mlp_tc(const MlpTcArgs& g, int num_sms, cudaStream_t stream) {
         g.ldx % 8 || g.ldo % 8 || g.ldx < g.C || g.ldo < g.C)
         return SODT_ERR_INVALID_ARG;
     switch (g.C) {
-        case 64: return launch<64>(g, num_sms, stream);
-        case 128: return launch<128>(g, num_sms, stream);
-        default: return launch<192>(g, num_sms, stream);
+        case 64: return g.w2_fp16 ? launch<64, true>(g, num_sms, stream) : launch<64, false>(g, num_sms, stream);
+        case 128: return g.w2_fp16 ? launch<128, true>(g, num_sms, stream) : launch<128, false>(g, num_sms, stream);
+        default: return g.w2_fp16 ? launch<192, true>(g, num_sms, stream) : launch<192, false>(g, num_sms, stream);
     }
 }
 

@@ -167,6 +167,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major,
            | ((uint32_t)(M >> 4) << 24);
 }
 
+// kind::f16 with IEEE fp16 A/B (format code 0) and fp32 accumulation
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool a_mn_major, bool b_mn_major) {
+    return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
     asm volatile(
@@ -293,6 +298,20 @@ __device__ __forceinline__ void gelu_fast2(float& a, float& b) {
     const __half2 h = *reinterpret_cast<const __half2*>(&y);
     a = __low2float(h);
     b = __high2float(h);
+}
+// TWICE the same GELU of a pair, as packed fp16 (low = a): 2 gelu(x) = x + x tanh(x q(x^2)) saves the halving; the consumer
+// folds the factor 0.5 into its (fp16) weights.  5 packed-half FMA-pipe instructions and two MUFU.TANH per pair.
+__device__ __forceinline__ uint32_t gelu2x_f16x2(float a, float b) {
+    uint32_t x, s, q, t, y;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(b), "f"(a));
+    asm("mul.f16x2 %0, %1, %1;" : "=r"(s) : "r"(x));
+    asm("min.f16x2 %0, %1, %2;" : "=r"(s) : "r"(s), "r"(0x54005400u));                   // 64.0
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(s), "r"(0x8DC28DC2u), "r"(0x28BD28BDu));   // -0.0003515, 0.037006
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(q) : "r"(q), "r"(s), "r"(0x3A613A61u));             // 0.797508
+    asm("mul.f16x2 %0, %1, %2;" : "=r"(q) : "r"(x), "r"(q));
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(q));
+    asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(x), "r"(t));
+    return y;
 }
 // SiLU for bf16 outputs: x sigmoid(x) = 0.5 x (1 + tanh(x / 2)) exactly; one MUFU
 __device__ __forceinline__ float silu_fast(float x) {

@@ -543,10 +543,14 @@ def mlp_ln_supported(x, hidden):
                 and _capi.lib().sodt_mlp_supported(x.numel() // C, C, hidden, 1))
 
 
-def mlp_ln(x, ln, fc1_weight, fc1_bias, fc2_weight, fc2_bias, want_stats=False):
+MLP_HIDDEN_FP16 = True  # fused MLP: hidden operand as fp16 2*GELU against 0.5*fc2.weight in fp16 (False: bf16, as the GEMM pair)
+
+
+def mlp_ln(x, ln, fc1_weight, fc1_bias, fc2_weight, fc2_bias, want_stats=False, hidden_fp16=None):
     """``x + fc2(GELU(fc1(LayerNorm(x))))`` over the last dim in one kernel (sodt_mlp_ln_fwd): the second half of a Swin block
     with a linear MLP (reference backbone_vit.py:885-890,1128).  ``ln = (stats, ln_weight, ln_bias[, eps])`` as in ``linear``;
-    ``want_stats``: also return the [C/64, M, 2] partial row statistics of the result -> (out, partials)."""
+    ``want_stats``: also return the [C/64, M, 2] partial row statistics of the result -> (out, partials).
+    ``hidden_fp16`` (default MLP_HIDDEN_FP16): see sodt_mlp_ln_fwd's ``w2_fp16``."""
     _require_cuda(x, fc1_weight, fc1_bias, fc2_weight, fc2_bias)
     C = x.shape[-1]
     M = x.numel() // C
@@ -563,7 +567,9 @@ def mlp_ln(x, ln, fc1_weight, fc1_bias, fc2_weight, fc2_bias, want_stats=False):
         raise ValueError("more than 3 partial pairs per row: reduce them with finalize_stats first")
     xa, ldx = _rows(x)
     w1, colsum, b1 = fold_layernorm(fc1_weight, fc1_bias, ln_w, ln_b)
-    w2 = fc2_weight.detach().contiguous()
+    hidden_fp16 = MLP_HIDDEN_FP16 if hidden_fp16 is None else bool(hidden_fp16)
+    w2 = (cached_derived(fc2_weight, "half_fp16", lambda w: (0.5 * w.detach().float()).to(torch.float16).contiguous())
+          if hidden_fp16 else fc2_weight.detach().contiguous())
     b2 = _as_f32(fc2_bias) if fc2_bias is not None else cached_derived(fc2_weight, "zero_bias", lambda w: torch.zeros(
         w.shape[0], dtype=torch.float32, device=w.device))
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
@@ -571,7 +577,7 @@ def mlp_ln(x, ln, fc1_weight, fc1_bias, fc2_weight, fc2_bias, want_stats=False):
     with torch.cuda.device(x.device), _Timed(f"mlp_ln[M={M},C={C},hidden={hidden},stats={want_stats}]"):
         st = _capi.lib().sodt_mlp_ln_fwd(xa.data_ptr(), ldx, mr.data_ptr(), ln_boxes, float(ln_eps), colsum.data_ptr(), w1.data_ptr(),
                                          b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out.data_ptr(), C, _ptr(stats_out), M, C, hidden,
-                                         1, _stream())
+                                         int(hidden_fp16), 1, _stream())
     _capi.check(st, "sodt_mlp_ln_fwd")
     return (out, stats_out) if want_stats else out
 

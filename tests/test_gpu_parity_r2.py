@@ -379,9 +379,13 @@ def test_mlp_fused_vs_fp64(M, C, hidden):
             stats = torch.stack((xs.sum(-1), (xs * xs).sum(-1)), dim=-1).permute(1, 0, 2).contiguous()
         out, part = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2, want_stats=True)
         assert rel_err(out, ref) <= 4e-3
-        s = part.sum(0).double()
-        assert torch.allclose(s[:, 0], ref.sum(1), atol=2e-2, rtol=2e-3)
-        assert torch.allclose(s[:, 1], (ref * ref).sum(1), atol=2e-2, rtol=2e-3)
+        outb = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2, hidden_fp16=False)      # bf16 hidden operand: the GEMM pair's bits
+        pair = o.linear(o.linear(x, w1, b1, act="gelu", ln=(stats, gam, bet, 1e-5)), w2, b2, residual=x)
+        assert torch.equal(outb, pair)
+        s = part.sum(0).double()        # statistics of the fp32 values before the bf16 rounding of `out`: 192 roundings of <= 2^-9 |v| apart
+        od = out.double()
+        assert torch.allclose(s[:, 0], od.sum(1), atol=0.15, rtol=5e-3)
+        assert torch.allclose(s[:, 1], (od * od).sum(1), atol=0.3, rtol=1e-2)
     out2 = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2)
     assert torch.equal(out2, out)
 

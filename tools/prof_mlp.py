@@ -24,14 +24,15 @@ def pair(x, st):
     return ops.linear(h, w2, b2, residual=x, want_stats=True)
 
 
-def fused(x, st):
-    return ops.mlp_ln(x, (st, gam, bet, 1e-5), w1, b1, w2, b2, want_stats=True)
+def fused(x, st, f16=True):
+    return ops.mlp_ln(x, (st, gam, bet, 1e-5), w1, b1, w2, b2, want_stats=True, hidden_fp16=f16)
 
 
 def check(M):
     x = torch.randn(M, C, device=dev, generator=g).to(torch.bfloat16)
     st = ops.row_stats(x, 1e-5)
     o, so = fused(x, st)
+    ob, _ = fused(x, st, False)
     torch.cuda.synchronize()
     xd = x.double()
     y = torch.nn.functional.layer_norm(xd, (C,), gam.double(), bet.double(), 1e-5)
@@ -41,7 +42,8 @@ def check(M):
     errp = ((op.double() - ref).norm() / ref.norm()).item()
     s = so.sum(0)
     serr = ((s[:, 0] - ref.sum(1).float()).abs().max() / ref.sum(1).abs().max()).item()
-    print(f"M={M}: fused rel err {err:.3e} (GEMM pair {errp:.3e}); stats sum err {serr:.2e}; max abs {float((o.double()-ref).abs().max()):.3e}")
+    errb = ((ob.double() - ref).norm() / ref.norm()).item()
+    print(f"M={M}: fused rel err fp16-hidden {err:.3e} bf16-hidden {errb:.3e} (GEMM pair {errp:.3e}); stats sum err {serr:.2e}; max abs {float((o.double()-ref).abs().max()):.3e}")
 
 
 def timed(fn, reps=10):
@@ -61,7 +63,8 @@ for M in (128, 200, 4096 + 64, 148 * 128 * 3 + 5):
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 32 * 256 * 256
 x = torch.randn(M, C, device=dev, generator=g).to(torch.bfloat16)
 st = ops.row_stats(x, 1e-5)
-o, _ = fused(x, st)
+o, _ = fused(x, st, False)
 op, _ = pair(x, st)
-print("full M: fused vs pair rel diff", ((o.float() - op.float()).norm() / op.float().norm()).item())
-print(f"M={M}: GEMM pair {timed(lambda: pair(x, st)):.3f} ms, fused {timed(lambda: fused(x, st)):.3f} ms")
+print("full M: fused (bf16 hidden) vs pair rel diff", ((o.float() - op.float()).norm() / op.float().norm()).item())
+print(f"M={M}: GEMM pair {timed(lambda: pair(x, st)):.3f} ms, fused bf16-hidden {timed(lambda: fused(x, st, False)):.3f} ms, "
+      f"fp16-hidden {timed(lambda: fused(x, st, True)):.3f} ms")
