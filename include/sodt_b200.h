@@ -167,6 +167,22 @@ int sodt_frontend_u8_fwd(const void* rgb, long long rb, long long rc, long long 
                          int B, int H, int W, int E, int pad_r, float eps, int dtype, void* stream);
 
 /*
+ * The whole front end as one tcgen05 kernel, straight from the uint8 images (bf16 output only):
+ *   sodt_frontend_u8_fwd (four 4x4/4 channel embeddings + window-1 cross-channel block + concat, backbone_vit.py:69-98,
+ *   469-561,210) followed by the 1x1 patch embedding Linear(4E -> embed_dim) + bias + absolute position embedding
+ *   (backbone_vit.py:212-214) -- the convs run as K = 16 GEMMs, the concat tile stays in shared memory as the A operand of
+ *   the patch-embedding GEMM.  rgb uint8 [B,3,H,W] / ir uint8 [B,>=1,H,W] with unit pixel stride and 4-byte aligned rows;
+ *   conv_w bf16 [4][E][16] (streams R,G,B,IR; taps ky*4+kx), conv_b / ln_w / ln_b fp32 [4][E]; pe_w bf16 [embed_dim, 4E],
+ *   pe_b fp32; pos bf16 [pos_rows = H/4*W/4, embed_dim] (broadcast over the batch) or NULL with pos_rows = 0;
+ *   out bf16 [B*H/4*W/4, embed_dim]; stats_out (optional) [embed_dim/64][M][2] partial row statistics for the first norm1.
+ *   E = 48, embed_dim = 192, H and W multiples of 4, (H/4*W/4) % 128 == 0 when pos is given.
+ */
+int sodt_frontend_embed_u8_supported(int B, int H, int W, int E, int embed_dim, int pos_rows);
+int sodt_frontend_embed_u8_fwd(const void* rgb, long long rb, long long rc, long long ry, const void* ir, long long ib,
+                               long long iy, const void* conv_w, const float* conv_b, const float* ln_w, const float* ln_b,
+                               const void* pe_w, const float* pe_b, const void* pos, int pos_rows, void* out,
+                               float* stats_out, int B, int H, int W, int E, int embed_dim, int pad_r, float eps, void* stream);
+/*
  * YOLOv5 Detect decode for one level.  Replaces model.py:55-64 (view/permute/contiguous,
  * sigmoid, grid + anchor decode, view) for the output of the level's 1x1 conv (model.py:53).
  *

@@ -33,6 +33,9 @@ SIGNATURES = {
                                   _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _p]),
     "sodt_frontend_fwd": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
     "sodt_frontend_u8_fwd": (_i, [_p, _ll, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _i, _p]),
+    "sodt_frontend_embed_u8_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "sodt_frontend_embed_u8_fwd": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p,
+                                        _i, _i, _i, _i, _i, _i, _f, _p]),
     "sodt_detect_decode": (_i, [_p, _ll, _ll, _ll, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _f, _ll, _ll, _i, _p]),
     "sodt_nms_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "sodt_nms": (_i, [_p, _p, _i, _p, _p, _p, _p, _sz, _i, _i, _i, _f, _d, _i, _i, _i, _i, _i, _i, _f, _p]),

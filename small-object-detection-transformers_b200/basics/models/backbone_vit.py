@@ -540,11 +540,23 @@ class ImageEncoderViT(nn.Module):
 
     def forward(self, x: torch.Tensor, ir_u8: Optional[torch.Tensor] = None):
         """x [B,4,H,W] in the model dtype, or (extension) x = uint8 RGB [B,3,H,W] with ``ir_u8`` uint8 [B,>=1,H,W]."""
-        x = self._front_end(x, ir_u8)                            # [B,h,w,192], the reference's concat
         pos = self.pos_embed                                     # silently skipped on a size mismatch, like the reference
-        if pos is not None and x.shape[1] != pos.shape[1]:
-            pos = None
-        x, st = self.patch_embed.forward_tokens(x, pos, want_stats=True)
+        st = None
+        if ir_u8 is not None and self.patch_embed.proj.weight.dtype == torch.bfloat16:
+            # uint8 images to patch-embedded tokens in one kernel: the 192-channel concat never reaches HBM
+            cb, e, pe = self.chan_block, self.channel_embed_r.proj, self.patch_embed.proj
+            pos_f = pos if pos is not None and pos.shape[1] == x.shape[2] // 4 and pos.shape[2] == x.shape[3] // 4 else None
+            if (cb.window_size == 1 and e.out_channels == 48 and e.kernel_size == (4, 4) and e.stride == (4, 4)
+                    and self.channel_embed_g.proj.padding == (0, 0) and e.padding in ((1, 1), (0, 0)) and pe.kernel_size == (1, 1)
+                    and ops.frontend_embed_u8_supported(x, ir_u8, 48, pe.out_channels, pos_f)):
+                cw, cbias, lw, lb = self._front_end_params()
+                x, st = ops.frontend_embed_u8(x, ir_u8, cw, cbias, lw, lb, pe.weight, pe.bias, pos_f, pad_r=e.padding[0],
+                                              eps=cb.norm1.eps, want_stats=True)
+        if st is None:
+            x = self._front_end(x, ir_u8)                        # [B,h,w,192], the reference's concat
+            if pos is not None and x.shape[1] != pos.shape[1]:
+                pos = None
+            x, st = self.patch_embed.forward_tokens(x, pos, want_stats=True)
         B, h, w, C = x.shape
         x = x.reshape(B, h * w, C)
         kept = []

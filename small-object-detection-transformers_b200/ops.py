@@ -328,6 +328,55 @@ def frontend_u8(rgb_u8, ir_u8, conv_w, conv_b, ln_w, ln_b, dtype, pad_r=1, eps=1
     return out
 
 
+USE_FUSED_FRONTEND = True   # uint8 images -> patch-embedded tokens in one tcgen05 kernel (False: frontend_u8 + the embedding GEMM)
+
+
+def frontend_embed_u8_supported(rgb_u8, ir_u8, E, embed_dim, pos):
+    """True if ``frontend_embed_u8`` can run on these uint8 images (CUDA, unit pixel stride, 4-byte aligned rows)."""
+    if not (USE_FUSED_FRONTEND and USE_TC_LINEAR and rgb_u8.is_cuda and rgb_u8.dtype == torch.uint8 and ir_u8.dtype == torch.uint8):
+        return False
+    B, _, H, W = rgb_u8.shape
+    rb, rc, ry, rx = rgb_u8.stride()
+    ib, _, iy, ix = ir_u8.stride()
+    if rx != 1 or ix != 1 or any(v % 4 for v in (rb, rc, ry, ib, iy, rgb_u8.data_ptr(), ir_u8.data_ptr())):
+        return False
+    pos_rows = 0 if pos is None else pos.numel() // embed_dim
+    return bool(_capi.lib().sodt_frontend_embed_u8_supported(B, H, W, E, embed_dim, pos_rows))
+
+
+def frontend_embed_u8(rgb_u8, ir_u8, conv_w, conv_b, ln_w, ln_b, pe_weight, pe_bias, pos=None, pad_r=1, eps=1e-5, want_stats=False):
+    """uint8 RGB [B,3,H,W] + IR [B,>=1,H,W] -> patch-embedded bf16 tokens [B, H/4, W/4, embed_dim] (+ the partial row
+    statistics [embed_dim/64, M, 2] for the first norm1): channel embeddings, window-1 cross-channel block, concat, 1x1 patch
+    embedding, bias and position embedding in one kernel (sodt_frontend_embed_u8_fwd).  conv_w [4,E,16] / conv_b / ln_w / ln_b
+    [4,E] fp32 as for ``frontend``; pe_weight [embed_dim, 4E] (or the conv's [embed_dim, 4E, 1, 1]); pos [1,h,w,embed_dim]."""
+    _require_cuda(rgb_u8, ir_u8, conv_w, conv_b, ln_w, ln_b, pe_weight, pe_bias, pos)
+    B, _, H, W = rgb_u8.shape
+    E = conv_w.shape[1]
+    D = pe_weight.shape[0]
+    if not frontend_embed_u8_supported(rgb_u8, ir_u8, E, D, pos):
+        raise _capi.SodtError("frontend_embed_u8: unsupported geometry / strides (frontend_embed_u8_supported)")
+    cw = cached_derived(conv_w, "bf16", lambda t: t.detach().to(torch.bfloat16).contiguous())
+    pw = cached_derived(pe_weight, "pe_bf16", lambda t: t.detach().reshape(t.shape[0], -1).to(torch.bfloat16).contiguous())
+    pb = _as_f32(pe_bias) if pe_bias is not None else cached_derived(pe_weight, "zero_bias", lambda w: torch.zeros(
+        w.shape[0], dtype=torch.float32, device=w.device))
+    posr = None
+    if pos is not None:
+        posr = cached_derived(pos, "pos_bf16", lambda t: t.detach().reshape(-1, D).to(torch.bfloat16).contiguous())
+    h, w = H // 4, W // 4
+    M = B * h * w
+    out = torch.empty((B, h, w, D), dtype=torch.bfloat16, device=rgb_u8.device)
+    stats = torch.empty((D // 64, M, 2), dtype=torch.float32, device=rgb_u8.device) if want_stats else None
+    rb, rc, ry, _ = rgb_u8.stride()
+    ib, _, iy, _ = ir_u8.stride()
+    with torch.cuda.device(rgb_u8.device), _Timed(f"frontend_embed_u8[B={B},H={H},W={W}]"):
+        st = _capi.lib().sodt_frontend_embed_u8_fwd(rgb_u8.data_ptr(), rb, rc, ry, ir_u8.data_ptr(), ib, iy, cw.data_ptr(),
+                                                    conv_b.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), pw.data_ptr(), pb.data_ptr(),
+                                                    _ptr(posr), 0 if posr is None else posr.shape[0], out.data_ptr(), _ptr(stats),
+                                                    B, H, W, E, D, pad_r, float(eps), _stream())
+    _capi.check(st, "sodt_frontend_embed_u8_fwd")
+    return (out, stats) if want_stats else out
+
+
 def detect_decode(raw, anchors_px, stride, want_perm=True, z=None, rows_total=None, row_offset=0):
     """raw [B, na*no, ny, nx] (any strides) -> (z [B, na*ny*nx, no] fp32, x_perm [B,na,ny,nx,no] or None)."""
     _require_cuda(raw, anchors_px, z)

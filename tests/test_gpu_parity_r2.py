@@ -406,3 +406,50 @@ def test_swin_block_fused_mlp_matches_gemm_pair():
             o.USE_FUSED_MLP = True
     assert rel_err(y1, y0) <= 4e-3
     assert torch.allclose(s1.sum(0), s0.sum(0), atol=5e-2, rtol=5e-3)
+
+
+# ------------------------------------------------------------------ one-kernel front end (sodt_frontend_embed_u8_fwd)
+@pytest.mark.parametrize("B,H,W,pad,with_pos", [(2, 256, 256, 1, True), (1, 128, 512, 1, True), (3, 64, 96, 1, False),
+                                                (1, 512, 512, 0, True), (2, 36, 44, 1, False)])
+def test_frontend_embed_u8_fused_vs_two_kernels_and_fp64(B, H, W, pad, with_pos):
+    """uint8 images -> patch-embedded tokens in one tcgen05 kernel (reference backbone_vit.py:69-98,469-561,210-214) against
+    (a) the front-end kernel followed by the embedding GEMM (the same arithmetic, other summation order) and (b) a float64
+    evaluation of the reference formulas on the same bf16 parameters."""
+    o = ops()
+    g = torch.Generator().manual_seed(B * H + W)
+    rgb = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8).cuda()
+    ir = torch.randint(0, 256, (B, 1, H, W), generator=g, dtype=torch.uint8).cuda()
+    E, D = 48, 192
+    bf = lambda t: t.to(torch.bfloat16).float()
+    cw = bf(torch.randn(4, E, 16, generator=g) / 4).cuda()
+    cb = bf(0.1 * torch.randn(4, E, generator=g)).cuda()
+    lw = bf(1 + 0.1 * torch.randn(4, E, generator=g)).cuda()
+    lb = bf(0.1 * torch.randn(4, E, generator=g)).cuda()
+    pw = (torch.randn(D, 4 * E, generator=g) / 14).cuda().to(torch.bfloat16)
+    pb = bf(0.1 * torch.randn(D, generator=g)).cuda()
+    h, w = H // 4, W // 4
+    pos = (0.5 * torch.randn(1, h, w, D, generator=g)).cuda().to(torch.bfloat16) if with_pos else None
+    out, st = o.frontend_embed_u8(rgb, ir, cw, cb, lw, lb, pw, pb, pos, pad_r=pad, eps=1e-6, want_stats=True)
+    cat = o.frontend_u8(rgb, ir, cw, cb, lw, lb, torch.bfloat16, pad_r=pad, eps=1e-6)
+    two = o.linear(cat, pw, pb, residual=pos) if with_pos else o.linear(cat, pw, pb)
+    assert rel_err(out, two) <= 3e-3
+    # float64 reference: conv as unfold, pair sums, LayerNorm, concat, linear, + pos
+    x = torch.cat((rgb, ir), 1).double() / 255.0
+    x = x.float().to(torch.bfloat16).double()                    # pixels are rounded to the model dtype
+    embeds = []
+    for s in range(4):
+        xs = x[:, s:s + 1]
+        p_ = pad if s == 0 else 0
+        e = torch.nn.functional.conv2d(xs, cw[s].double().view(E, 1, 4, 4), cb[s].double(), stride=4, padding=p_)
+        embeds.append(e.permute(0, 2, 3, 1))
+    pairs = ((0, 1), (1, 2), (2, 3), (3, 1))
+    cat64 = torch.cat([torch.nn.functional.layer_norm(embeds[a] + embeds[k], (E,), lw[q].double(), lb[q].double(), 1e-6)
+                       for q, (a, k) in enumerate(pairs)], -1)
+    ref = cat64 @ pw.double().t() + pb.double()
+    if with_pos:
+        ref = ref + pos.double()
+    assert rel_err(out, ref) <= 6e-3            # includes the bf16 rounding of the concat tile (the GEMM's A operand)
+    od = out.double().reshape(-1, D)
+    s = st.sum(0).double()
+    assert torch.allclose(s[:, 0], od.sum(1), atol=0.15, rtol=5e-3)
+    assert torch.allclose(s[:, 1], (od * od).sum(1), atol=0.3, rtol=1e-2)
