@@ -25,6 +25,7 @@
 //                             memory, one TMA store per box (full 128-byte lines; per-thread 16-byte row stores capped
 //                             the kernel at ~1.9 TB/s)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "linear_tc.h"
@@ -75,6 +76,19 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
                  ::"r"(dst), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+// CTA-pair forms: the transaction bytes complete on the LEADER's mbarrier (a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* tmap, uint32_t bar_addr, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const void* tmap, uint32_t bar_addr, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 ::"r"(dst), "l"(tmap), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
@@ -108,14 +122,22 @@ constexpr int epi_code(bool bias, bool ln, bool res, bool stats, int act) {
 // (qkv, fc1) ran at the L2 -> SM rate (~9 TB/s measured), not at the HBM rate.
 constexpr int MAX_STAGES = 8;
 
-template <int BN, int EPI, bool WRES>
+// CTA2 ("CTA pair", cta_group::2): two CTAs of a cluster share one 256-row tile: each loads its own 128 rows of A and HALF of
+// the W tile, the leader issues M = 256 MMAs over both shared memories, each CTA runs the epilogue of its own 128 rows.
+// Per SM the operand bytes per output drop by a third at BN = 256 (the K >= 384 GEMMs run at the SM's operand ingest rate).
+template <int BN, int EPI, bool WRES, bool CTA2>
 __global__ void __launch_bounds__(NTHREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
                  const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_o,
                  const __grid_constant__ CUtensorMap tmap_r, const Epilogue ep,
                  const Addressing ad, int K, int num_n_tiles, int num_m_tiles, int stages) {
+    static_assert(!(WRES && CTA2), "the resident-W walk is a single-CTA schedule");
     constexpr int NACC = Cfg<BN>::NACC;
-    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int BNL = CTA2 ? BN / 2 : BN;                      // W rows this CTA loads
+    constexpr int B_BYTES = BNL * BK * 2;
+    const int crank = CTA2 ? (int)cluster_ctarank() : 0;
+    const int cid = CTA2 ? (int)blockIdx.x >> 1 : (int)blockIdx.x, ncl = CTA2 ? (int)gridDim.x >> 1 : (int)gridDim.x;   // tile walker id / count
+    constexpr int MT_ROWS = CTA2 ? 2 : 1;                        // 128-row tiles per M-tile of the walk
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES], acc_full[NACC], acc_empty[NACC], res_full[EPI_GROUPS], w_full;
     __shared__ uint32_t tmem_slot;
@@ -127,26 +149,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const uint32_t stage_bytes = A_BYTES + (WRES ? 0 : B_BYTES);
     const uint32_t staging_base = ring_base + stages * stage_bytes;
     // tile walk: WRES: N-tile nt0 is fixed, M-tiles mt0, mt0 + mstep, ...; otherwise tiles blockIdx.x, + gridDim.x, ... in (mt, nt) order
-    const int nt0 = WRES ? (int)blockIdx.x % num_n_tiles : 0;
-    const int mt0 = WRES ? (int)blockIdx.x / num_n_tiles : 0, mstep = WRES ? (int)gridDim.x / num_n_tiles : 1;
+    const int nt0 = WRES ? cid % num_n_tiles : 0;
+    const int mt0 = WRES ? cid / num_n_tiles : 0, mstep = WRES ? ncl / num_n_tiles : 1;
     const int num_tiles = num_n_tiles * num_m_tiles;
     const int n_iter = WRES ? (mt0 < num_m_tiles ? (num_m_tiles - mt0 + mstep - 1) / mstep : 0)
-                            : ((int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+                            : (cid < num_tiles ? (num_tiles - cid + ncl - 1) / ncl : 0);
     auto tile_at = [&](int i, int& mt, int& nt) {
         if (WRES) { mt = mt0 + i * mstep; nt = nt0; }
-        else { const int tile = (int)blockIdx.x + i * (int)gridDim.x; mt = tile / num_n_tiles; nt = tile - mt * num_n_tiles; }
+        else { const int tile = cid + i * ncl; mt = tile / num_n_tiles; nt = tile - mt * num_n_tiles; }
     };
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32 * MT_ROWS); }   // pair: both CTAs' epilogues
         for (int g = 0; g < EPI_GROUPS; ++g) mbar_init(&res_full[g], 1);
         mbar_init(&w_full, 1);
         fence_barrier_init();
     }
-    if (warp == MMA_WARP) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+    if (warp == MMA_WARP) {
+        if (CTA2) { tmem_alloc2(&tmem_slot, 512); tmem_relinquish2(); }
+        else { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+    }
     fence_before_sync();
-    __syncthreads();
+    if (CTA2) cluster_sync_all();                                // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     fence_after_sync();
     const uint32_t tm = tmem_slot;
 
@@ -160,7 +186,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             for (int it = 0; it < n_iter; ++it) {
                 int mt, nt;
                 tile_at(it, mt, nt);
-                const int row0 = mt * BM;
+                const int row0 = (mt * MT_ROWS + crank) * BM;
                 int p0 = 0, p1 = 0, p2 = 0;                      // conv: x0, y0, b;  merge: j0, bi0
                 if (ad.mode == MODE_CONV || ad.mode == MODE_UPCAT) {
                     p2 = row0 / ad.HW;
@@ -174,8 +200,29 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 int tap = 0, cc = 0;                             // running (tap, channel block) of the k loop
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (round > 0) mbar_wait(&empty[stage], (uint32_t)((round - 1) & 1));
-                    mbar_expect_tx(&full[stage], stage_bytes);
                     const uint32_t sa = ring_base + stage * stage_bytes;
+                    if (CTA2) {
+                        // both CTAs' boxes complete on the leader's barrier, armed by the leader for the bytes of the pair
+                        if (crank == 0) mbar_expect_tx(&full[stage], 2 * stage_bytes);
+                        const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (ad.mode == MODE_PLAIN) {
+                            if (kb < ad.k_split) tma_load_2d_pair(sa, &tmap_x, fb, kb * BK, row0);
+                            else tma_load_2d_pair(sa, &tmap_x2, fb, (kb - ad.k_split) * BK, row0);
+                        } else if (ad.mode == MODE_CONV) {
+                            const int ky = tap / ad.kw, kx = tap - ky * ad.kw;
+                            tma_load_4d_pair(sa, &tmap_x, fb, cc * BK, p0 + kx - ad.pad_l, p1 + ky - ad.pad_t, p2);
+                        } else if (ad.mode == MODE_UPCAT) {
+                            if (kb < ad.k_split) tma_load_5d_pair(sa, &tmap_x, fb, kb * BK, 0, p0 >> 1, 0, p2 * (ad.pad_t >> 1) + (p1 >> 1));
+                            else tma_load_4d_pair(sa, &tmap_x2, fb, (kb - ad.k_split) * BK, p0, p1, p2);
+                        } else {
+                            tma_load_5d_pair(sa, &tmap_x, fb, cc * BK, tap >> 1, p0, tap & 1, p1);
+                        }
+                        if (++cc == ad.cpb) { cc = 0; ++tap; }
+                        tma_load_2d_pair(sa + A_BYTES, &tmap_w, fb, kb * BK, nt * BN + crank * BNL);
+                        if (++stage == stages) { stage = 0; ++round; }
+                        continue;
+                    }
+                    mbar_expect_tx(&full[stage], stage_bytes);
                     if (ad.mode == MODE_PLAIN) {
                         if (kb < ad.k_split) tma_load_2d(sa, &tmap_x, &full[stage], kb * BK, row0);
                         else tma_load_2d(sa, &tmap_x2, &full[stage], (kb - ad.k_split) * BK, row0);
@@ -197,8 +244,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             }
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_bf16(BM, BN, false, false);
+        if (lane == 0 && crank == 0) {                           // pair: the leader issues for both CTAs
+            constexpr uint32_t idesc = idesc_bf16(BM * MT_ROWS, BN, false, false);
             int stage = 0, round = 0;
             if (WRES && n_iter > 0) { mbar_wait(&w_full, 0); fence_after_sync(); }
             for (int it = 0; it < n_iter; ++it) {
@@ -211,11 +258,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     const uint32_t sa = ring_base + stage * stage_bytes;
                     const uint64_t da = desc_sw128(sa), db = desc_sw128(WRES ? sbase + kb * B_BYTES : sa + A_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) mma_ss(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
-                    mma_commit(&empty[stage]);
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        if (CTA2) mma_ss2(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
+                        else mma_ss(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
+                    }
+                    if (CTA2) mma_commit2(&empty[stage]); else mma_commit(&empty[stage]);
                     if (++stage == stages) { stage = 0; ++round; }
                 }
-                mma_commit(&acc_full[a]);
+                if (CTA2) mma_commit2(&acc_full[a]); else mma_commit(&acc_full[a]);
             }
         }
     } else {
@@ -242,7 +292,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (has_ln && i < n_iter) {
                 int mt_, nt_;
                 tile_at(i, mt_, nt_);
-                const int gr = mt_ * BM + row_in_tile;
+                const int gr = (mt_ * MT_ROWS + crank) * BM + row_in_tile;
                 if (gr < ep.M) {
                     if (ep.ln_boxes == 0) {
                         r = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + gr);
@@ -263,7 +313,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int a = it % NACC;
             int mt, nt;
             tile_at(it, mt, nt);
-            const int grow = mt * BM + row_in_tile;                      // global output row of this thread
+            const int mrow = mt * MT_ROWS + crank;                       // this CTA's 128-row tile
+            const int grow = mrow * BM + row_in_tile;                    // global output row of this thread
             const float2 mr = mr_next;
             mr_next = load_mr(it + 1);
             mbar_wait(&acc_full[a], (uint32_t)((it / NACC) & 1));
@@ -276,7 +327,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     tma_store_wait_read();                               // the previous box of this group has left smem
                     if (has_residual) {                                  // residual box lands in the staging buffer (TMA, swizzled)
                         mbar_expect_tx(&res_full[eg], BOX_BYTES);
-                        tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, (mt % ep.res_tiles) * BM);
+                        tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, (mrow % ep.res_tiles) * BM);
                     }
                 }
                 // accumulator columns in chunks of 16, the next chunk in flight while this one is processed (the kernel
@@ -288,6 +339,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");      // staging box reusable for everyone
                 if (has_residual) { mbar_wait(&res_full[eg], res_phase); res_phase ^= 1; }
                 const float rstd = mr.y, nmr = -mr.x * mr.y;                      // rstd and -mean * rstd of the A row
+                const uint64_t rstd2 = pack2(rstd, rstd), nmr2 = pack2(nmr, nmr);
                 float so = 0.f, sso = 0.f;                                        // statistics of the output row
 #pragma unroll
                 for (int j = 0; j < 64; j += 8) {
@@ -308,7 +360,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                         const float4 c1 = __ldg(reinterpret_cast<const float4*>(ep.ln_colsum + col0 + j + 4));
                         const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = fmaf(rstd, v[e], fmaf(nmr, cs[e], bb[e]));
+                        for (int e = 0; e < 8; e += 2)          // packed fp32x2: two columns per FFMA2
+                            unpack2(ffma2(rstd2, pack2(v[e], v[e + 1]), ffma2(nmr2, pack2(cs[e], cs[e + 1]), pack2(bb[e], bb[e + 1]))), v[e], v[e + 1]);
                     } else if (bias != nullptr) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] += bb[e];
@@ -343,16 +396,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     reinterpret_cast<float2*>(ep.stats_out)[(size_t)(col0 >> 6) * ep.M + grow] = make_float2(so, sso);
                 fence_proxy_async();
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-                if (issuer) { tma_store_2d(&tmap_o, stage_box, col0, mt * BM); tma_store_commit(); }
+                if (issuer) { tma_store_2d(&tmap_o, stage_box, col0, mrow * BM); tma_store_commit(); }
             }
             fence_before_sync();
-            mbar_arrive(&acc_empty[a]);
+            if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));      // the leader's MMA thread waits for both epilogues
+            else mbar_arrive(&acc_empty[a]);
         }
         if (issuer) tma_store_wait_all();
     }
     fence_before_sync();
-    __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem_slot, 512);
+    if (CTA2) cluster_sync_all();                                // no CTA leaves while its peer may still signal its barriers / read its smem
+    else __syncthreads();
+    if (warp == MMA_WARP) { if (CTA2) tmem_dealloc2(tmem_slot, 512); else tmem_dealloc(tmem_slot, 512); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -390,40 +445,65 @@ bool make_map_2d(CUtensorMap* m, const void* base, long long rows, long long col
 
 constexpr int SMEM_LIMIT = 227 * 1024;
 
-template <int BN, int EPI, bool WRES>
+template <int BN, int EPI, bool WRES, bool CTA2>
 int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream) {
+    constexpr int BNL = CTA2 ? BN / 2 : BN, MT = CTA2 ? 2 * BM : BM;
     CUtensorMap mw, mo, mr;
-    if (!make_map_2d(&mw, g.w, g.N, g.K, g.K, BN, false) || !make_map_2d(&mo, g.out, g.M, g.N, g.ldo, BM, true)) return SODT_ERR_CUDA;
+    if (!make_map_2d(&mw, g.w, g.N, g.K, g.K, BNL, false) || !make_map_2d(&mo, g.out, g.M, g.N, g.ldo, BM, true)) return SODT_ERR_CUDA;
     const int res_rows = g.residual && g.res_rows > 0 ? g.res_rows : g.M;
     if (!make_map_2d(&mr, g.residual ? g.residual : g.out, res_rows, g.N, g.residual ? g.ldr : g.ldo, BM, true)) return SODT_ERR_CUDA;
-    const int num_n_tiles = g.N / BN, num_m_tiles = (g.M + BM - 1) / BM;
+    const int num_n_tiles = g.N / BN, num_m_tiles = (g.M + MT - 1) / MT;
     const long long tiles = (long long)num_n_tiles * num_m_tiles;
     if (tiles > 2147483647LL) return SODT_ERR_UNSUPPORTED;
-    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int B_BYTES = BNL * BK * 2;
     const int fixed = EPI_GROUPS * BOX_BYTES + 1024 + (WRES ? (g.K / BK) * B_BYTES : 0);
     int stages = (SMEM_LIMIT - fixed) / (A_BYTES + (WRES ? 0 : B_BYTES));
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return SODT_ERR_UNSUPPORTED;
     const size_t smem = (size_t)fixed + (size_t)stages * (A_BYTES + (WRES ? 0 : B_BYTES));
-    auto kern = linear_tc_kernel<BN, EPI, WRES>;
+    auto kern = linear_tc_kernel<BN, EPI, WRES, CTA2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    int grid = (int)(tiles < num_sms ? tiles : num_sms);
+    const int walkers = CTA2 ? num_sms / 2 : num_sms;            // CTAs, or CTA pairs
+    int grid = (int)(tiles < walkers ? tiles : walkers);
     if (WRES) grid = (num_sms / num_n_tiles) * num_n_tiles;      // a multiple of the N-tile count: CTA c keeps N-tile c % num_n_tiles
     Epilogue ep{};
     ep.bias = g.bias; ep.ln_stats = g.ln_stats; ep.ln_colsum = g.ln_colsum; ep.stats_out = g.stats_out;
     ep.M = g.M; ep.has_residual = g.residual != nullptr ? 1 : 0; ep.act = g.act;
     ep.res_tiles = (res_rows + BM - 1) / BM;
     ep.ln_boxes = g.ln_boxes; ep.ln_inv_k = 1.f / (float)g.K; ep.ln_eps = g.ln_eps;
+    if (CTA2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const int K = g.K;
+        e = cudaLaunchKernelEx(&cfg, kern, mx, mx2, mw, mo, mr, ep, ad, K, num_n_tiles, num_m_tiles, stages);
+        if (e != cudaSuccess) return cuda_status(e);
+        return check_launch();
+    }
     kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, ep, ad, g.K, num_n_tiles, num_m_tiles, stages);
     return check_launch();
 }
 
-// W stays resident when the CTA's W tile plus >= 3 A stages fit (K <= 192 at BN = 256 / 192) and the M-tiles fill the machine
+bool use_pairs() {          // SODT_NO_CTA2=1 keeps every GEMM on single-CTA tiles (A/B measurements)
+    static const bool on = [] { const char* v = getenv("SODT_NO_CTA2"); return !(v && v[0] == '1'); }();
+    return on;
+}
+
+// W stays resident when the CTA's W tile plus >= 3 A stages fit (K <= 192 at BN = 256 / 192) and the M-tiles fill the machine;
+// otherwise wide tiles with a long K loop run on CTA pairs
 template <int BN, int EPI>
 int launch_res(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, const LinearTcArgs& g, int num_sms, cudaStream_t stream, bool wres) {
-    if (wres) return launch<BN, EPI, true>(mx, mx2, ad, g, num_sms, stream);
-    return launch<BN, EPI, false>(mx, mx2, ad, g, num_sms, stream);
+    if (wres) return launch<BN, EPI, true, false>(mx, mx2, ad, g, num_sms, stream);
+    if constexpr (BN >= 128) {
+        // measured on B200 (tools/prof_pairs.py): +6-11 % at K >= 768 (1315 TFLOP/s at K = 3072), -5 % at K = 384 where the six
+        // k-blocks of a tile do not amortise the pair's hand-shakes
+        if (use_pairs() && g.K >= 768 && (long long)g.M >= 256LL * (num_sms / 2)) return launch<BN, EPI, false, true>(mx, mx2, ad, g, num_sms, stream);
+    }
+    return launch<BN, EPI, false, false>(mx, mx2, ad, g, num_sms, stream);
 }
 
 template <int EPI>
