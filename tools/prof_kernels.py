@@ -42,12 +42,22 @@ for _ in range(reps):
     ops.linear(x1, wq, bq, ln=(mr, gam, bet))                                                 # norm1 + qkv
     hid = ops.linear(x1, w1, b1, act="gelu", ln=(mr, gam, bet))                               # norm2 + fc1 + GELU
     ops.linear(hid, w(192, 768), bias(192), residual=xt, want_stats=True)                # fc2 + residual
+    ops.mlp_ln(x1, (mr, gam, bet, 1e-5), w1, b1, w(192, 768), bias(192), want_stats=True)       # the same MLP half as one kernel
     ops.conv2d_nhwc(xt.view(B, 256, 256, 192), w(192, 4 * 192), bias(192), (2, 2), (0, 0), "gelu")
     ops.patch_merge_linear(xt.view(B, 256, 256, 192), w(384, 768))
     ops.add_layernorm(xt, None, torch.ones(192, device=dev), torch.zeros(192, device=dev), 1e-5)
     ops.row_stats(xt, 1e-5)
     del hid, x1, part, mr
 del xt
+# stage-3 GEMMs (K >= 768: CTA pairs, cta_group::2)
+x3 = torch.randn(B * 64 * 64, 768, device=dev, generator=g).to(torch.bfloat16)
+g3, b3 = 1.0 + 0.1 * torch.randn(768, device=dev, generator=g), 0.1 * torch.randn(768, device=dev, generator=g)
+mr3 = ops.row_stats(x3, 1e-5)
+for _ in range(reps):
+    h3 = ops.linear(x3, w(3072, 768), bias(3072), act="gelu", ln=(mr3, g3, b3))
+    ops.linear(h3, w(768, 3072), bias(768), residual=x3, want_stats=True)
+    del h3
+del x3
 # head: 1x1 conv over cat(up2x(low), skip) through zero-stride TMA dimensions
 low = torch.randn(B, 128, 128, 128, device=dev, generator=g).to(torch.bfloat16)
 skip = torch.randn(B, 256, 256, 256, device=dev, generator=g).to(torch.bfloat16)
@@ -59,6 +69,13 @@ cw, cb = 0.3 * torch.randn(4, 48, 16, device=dev, generator=g), 0.1 * torch.rand
 for _ in range(reps):
     ops.frontend(img, cw, cb, torch.ones(4, 48, device=dev), torch.zeros(4, 48, device=dev), pad_r=1, eps=1e-5)
 del img
+rgb = torch.randint(0, 256, (B, 3, 1024, 1024), generator=g, dtype=torch.uint8, device=dev)
+ir = torch.randint(0, 256, (B, 1, 1024, 1024), generator=g, dtype=torch.uint8, device=dev)
+pos = (0.5 * torch.randn(1, 256, 256, 192, device=dev, generator=g)).to(torch.bfloat16)
+for _ in range(reps):       # uint8 images -> patch-embedded tokens in one kernel
+    ops.frontend_embed_u8(rgb, ir, cw, cb, torch.ones(4, 48, device=dev), torch.zeros(4, 48, device=dev), w(192, 192), bias(192), pos,
+                          pad_r=1, eps=1e-6, want_stats=True)
+del rgb, ir, pos
 torch.cuda.synchronize()
 streams = [torch.randn(B, 48, 256, 256, device=dev, generator=g).to(torch.bfloat16).permute(0, 2, 3, 1) for _ in range(4)]
 ln_w, ln_b = torch.ones(4, 48, device=dev), torch.zeros(4, 48, device=dev)
