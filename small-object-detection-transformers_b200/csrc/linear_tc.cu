@@ -161,7 +161,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32 * MT_ROWS); }   // pair: both CTAs' epilogues
+        for (int a = 0; a < NACC; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * MT_ROWS); }   // one arrival per epilogue warp (pair: of both CTAs)
         for (int g = 0; g < EPI_GROUPS; ++g) mbar_init(&res_full[g], 1);
         mbar_init(&w_full, 1);
         fence_barrier_init();
@@ -399,8 +399,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (issuer) { tma_store_2d(&tmap_o, stage_box, col0, mrow * BM); tma_store_commit(); }
             }
             fence_before_sync();
-            if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));      // the leader's MMA thread waits for both epilogues
-            else mbar_arrive(&acc_empty[a]);
+            __syncwarp();                                                // every lane's accumulator loads have completed
+            if (lane == 0) {
+                if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));  // the leader's MMA thread waits for both epilogues
+                else mbar_arrive(&acc_empty[a]);
+            }
         }
         if (issuer) tma_store_wait_all();
     }
@@ -488,6 +491,11 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     return check_launch();
 }
 
+int pair_min_k() {           // experiments: SODT_PAIR_MIN_K overrides the K threshold
+    static const int k = [] { const char* v = getenv("SODT_PAIR_MIN_K"); return v ? atoi(v) : 768; }();
+    return k;
+}
+
 bool use_pairs() {          // SODT_NO_CTA2=1 keeps every GEMM on single-CTA tiles (A/B measurements)
     static const bool on = [] { const char* v = getenv("SODT_NO_CTA2"); return !(v && v[0] == '1'); }();
     return on;
@@ -501,7 +509,7 @@ int launch_res(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& 
     if constexpr (BN >= 128) {
         // measured on B200 (tools/prof_pairs.py): +6-11 % at K >= 768 (1315 TFLOP/s at K = 3072), -5 % at K = 384 where the six
         // k-blocks of a tile do not amortise the pair's hand-shakes
-        if (use_pairs() && g.K >= 768 && (long long)g.M >= 256LL * (num_sms / 2)) return launch<BN, EPI, false, true>(mx, mx2, ad, g, num_sms, stream);
+        if (use_pairs() && g.K >= pair_min_k() && (long long)g.M >= 256LL * (num_sms / 2)) return launch<BN, EPI, false, true>(mx, mx2, ad, g, num_sms, stream);
     }
     return launch<BN, EPI, false, false>(mx, mx2, ad, g, num_sms, stream);
 }

@@ -300,14 +300,13 @@ class ShardedDetector:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-
-    def local_slice(self, n_images):
-        return shard_range(n_images, self.rank, self.world)
-
         self.comm_stream = torch.cuda.Stream(detector.device) if detector.device.type == "cuda" else None
         self._recv = {}                 # ring of receive buffers per batch size
         self._step = 0
         self._pending = None            # gather of the previous step (its send buffer is the next step's NMS output)
+
+    def local_slice(self, n_images):
+        return shard_range(n_images, self.rank, self.world)
 
     @torch.no_grad()
     def detect_device(self, rgb_u8_local, ir_u8_local):
@@ -316,6 +315,12 @@ class ShardedDetector:
         straight into the buffer NCCL sends; the all-gather runs on a side stream and overlaps the next step, which only waits
         for it before its own NMS output could overwrite the send buffer."""
         det = self.detector
+        if self.comm_stream is None:                          # host tensors (gloo; the CPU tests of the host logic): a synchronous gather
+            buf = det.detect_device(rgb_u8_local, ir_u8_local)
+            recv = torch.empty(self.world * buf.flat.numel(), dtype=torch.float32, device=buf.flat.device)
+            dist.all_gather_into_tensor(recv, buf.flat, group=self.group)
+            self._step += 1
+            return GatheredDetections(recv, self.world, buf.batch, buf.max_det)
         compute = torch.cuda.current_stream(det.device)
         if self._pending is not None:                     # the previous gather still reads the send buffer this step rewrites
             compute.wait_event(self._pending)

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sodt_b200.runtime import DetectionBuffer, allgather_detections, shard_range
+from sodt_b200.runtime import DetectionBuffer, ShardedDetector, allgather_detections, shard_range
 
 
 def _free_port():
@@ -69,4 +69,46 @@ def test_allgather_detections_world2_gloo():
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_worker, args=(world, port, n_images, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+class _FakeDetector:
+    """Stands in for runtime.Detector on the CPU: 'detects' the deterministic boxes of the global image indices it is handed."""
+    device = torch.device("cpu")
+
+    def detect_device(self, indices, _ir):
+        buf = DetectionBuffer(len(indices), "cpu")
+        for j, idx in enumerate(indices):
+            d, n = _fake_detections(int(idx))
+            buf.det[j].copy_(d)
+            buf.counts[j] = n
+        return buf
+
+
+def _sharded_worker(rank, world, port, n_images, results):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sh = ShardedDetector(_FakeDetector())
+        ok = sh.rank == rank and sh.world == world and sh._pending is None and sh._step == 0
+        lo, hi = sh.local_slice(n_images)
+        for step in range(2):                                   # two steps: the per-step state (receive ring, step counter) advances
+            g = sh.detect_device(list(range(lo, hi)), None)
+            det, counts = g.tensors()
+            ok = ok and det.shape == (n_images, 300, 6) and sh._step == step + 1
+            for idx in range(n_images):
+                d, n = _fake_detections(idx)
+                ok = ok and int(counts[idx]) == n and torch.equal(det[idx], d)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_detector_host_logic_world2_gloo():
+    """ShardedDetector end to end on the CPU (constructor state, local_slice, detect_device's gather, GatheredDetections views)."""
+    world, n_images = 2, 6
+    port = _free_port()
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_sharded_worker, args=(world, port, n_images, results), nprocs=world, join=True)
     assert dict(results) == {0: True, 1: True}
