@@ -33,7 +33,18 @@ using namespace tc;
 constexpr int TM = 128;            // query rows per CTA
 constexpr int TN = 128;            // keys per tile
 constexpr int HD = 64;             // head dim
-constexpr int NTHREADS = 192;
+#ifndef SODT_FLASH_TPR
+#define SODT_FLASH_TPR 1
+#endif
+// threads per score row: 2 = warps w and w + 4 split the 128 keys of a tile (twice the softmax issue slots, one shared-memory
+// exchange of the row maximum per tile).  Measured on B200 (B = 32, tools/prof_flash.py): TPR 1 0.771 ms, TPR 2 0.805 ms, with
+// 3 of 8 exponentials on the FMA pipe 0.781 / 0.846 ms: the kernel is bound by the latency of the per-tile chain
+// S -> TMEM load -> max -> exp -> P -> PV of the two resident CTAs, not by issue slots or the MUFU (48 % busy).
+constexpr int TPR = SODT_FLASH_TPR;
+constexpr int KPT = 128 / TPR;          // keys per thread and tile
+constexpr int SM_WARPS = 4 * TPR, PRODUCER_WARP = SM_WARPS, MMA_WARP = SM_WARPS + 1;
+constexpr int SM_THREADS = SM_WARPS * 32;
+constexpr int NTHREADS = (SM_WARPS + 2) * 32;
 constexpr int TILE_BYTES = TM * HD * 2;   // 16 KB
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
@@ -46,7 +57,8 @@ struct SmemLayout {
     static constexpr int Q = 0;
     static constexpr int K = Q + TILE_BYTES;            // 2 stages
     static constexpr int V = K + 2 * TILE_BYTES;        // 2 stages
-    static constexpr int TAB = V + 2 * TILE_BYTES;      // (2*WS-1)^2 floats
+    static constexpr int XCH = V + 2 * TILE_BYTES;      // row maxima [2 parities][2 halves][128] + row sums [2][128] exchanged between the two threads of a row
+    static constexpr int TAB = XCH + 6 * 128 * 4;       // (2*WS-1)^2 floats
 };
 
 // Transposes the bias table to [heads][(2ws-1)^2] and scales it by log2(e).
@@ -82,18 +94,18 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
         for (int s = 0; s < 2; ++s) { mbar_init(&bar_k_full[s], 1); mbar_init(&bar_v_full[s], 1); mbar_init(&bar_kv_empty[s], 1); }
         mbar_init(&bar_q_full, 1);
         mbar_init(&bar_s_full, 1);
-        mbar_init(&bar_s_free, TM);
-        mbar_init(&bar_p_full, TM);
+        mbar_init(&bar_s_free, SM_THREADS);
+        mbar_init(&bar_p_full, SM_THREADS);
         mbar_init(&bar_pv_done, 1);
         fence_barrier_init();
     }
-    if (warp == 5) { tmem_alloc(&tmem_slot, 256); tmem_relinquish(); }
+    if (warp == MMA_WARP) { tmem_alloc(&tmem_slot, 256); tmem_relinquish(); }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tm_S = tmem_slot, tm_P = tmem_slot + 128, tm_O = tmem_slot + 192;
 
-    if (warp == 4) {
+    if (warp == PRODUCER_WARP) {
         // ===================================================================== producer (one lane, TMA)
         if (lane == 0) {
             constexpr int RPT = TN / WS;                        // window rows per 128-token tile
@@ -108,7 +120,7 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
                 tma::load_3d(sbase + SmemLayout::V + s * TILE_BYTES, &in_map, &bar_v_full[s], 2 * C + head * HD, x0, y0 + t * RPT);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == MMA_WARP) {
         // =================================================================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc_bf16(TM, TN, false, false);
@@ -141,10 +153,13 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
         }
     } else {
         // ============================================================ softmax + epilogue
-        const int row = tid;                                  // 0..127, TMEM lane == row
-        const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-        for (int e = tid; e < SPAN * SPAN; e += TM) tab[e] = table_t[(long long)head * SPAN * SPAN + e];
-        asm volatile("bar.sync 1, 128;" ::: "memory");        // table visible to the 4 softmax warps
+        // TPR threads per query row: warp w handles TMEM lanes 32 (w % 4) .. and the keys [KPT (w / 4), KPT (w / 4 + 1)) of every tile;
+        // the partial row maxima (per tile) and row sums (once) are exchanged through shared memory
+        const int half = warp >> 2, row = (warp & 3) * 32 + lane;          // TMEM lane == row
+        const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+        float* xch = reinterpret_cast<float*>(smem + (sbase - smem_u32(smem)) + SmemLayout::XCH);
+        for (int e = tid; e < SPAN * SPAN; e += SM_THREADS) tab[e] = table_t[(long long)head * SPAN * SPAN + e];
+        asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");        // table visible to the softmax warps
         const int tq = qtile * TM + row;
         const int yq = tq / WS, xq = tq - yq * WS;
         const float* tab_q = tab + (yq + WS - 1) * SPAN + (xq + WS - 1);
@@ -157,40 +172,44 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
             // t*(TN/WS) + j/WS, column j%WS
             const float* tb = tab_q - (t * (TN / WS)) * SPAN;
             const uint64_t c2 = pack2(c, c);
-            uint64_t t2[TN / 2];
+            uint64_t t2[KPT / 2];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
+            for (int q4 = 0; q4 < KPT / 32; ++q4) {
                 uint32_t r[32];
-                tmem_ld32(tm_S + lane_addr + q4 * 32, r);
+                tmem_ld32(tm_S + lane_addr + half * KPT + q4 * 32, r);
                 tmem_wait_ld();
-                if (q4 == 3) { fence_before_sync(); mbar_arrive(&bar_s_free); }
+                if (q4 == KPT / 32 - 1) { fence_before_sync(); mbar_arrive(&bar_s_free); }
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const int k0 = q4 * 32 + j;
+                    const int k0 = half * KPT + q4 * 32 + j, kl = q4 * 32 + j;
                     const float b0 = tb[-((k0 / WS) * SPAN + (k0 % WS))], b1 = tb[-(((k0 + 1) / WS) * SPAN + ((k0 + 1) % WS))];
-                    t2[k0 >> 1] = ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(b0, b1));
+                    t2[kl >> 1] = ffma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), c2, pack2(b0, b1));
                 }
             }
             float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-            for (int j = 0; j < TN / 2; ++j) {
+            for (int j = 0; j < KPT / 2; ++j) {
                 float lo, hi;
                 unpack2(t2[j], lo, hi);
                 m4[j & 3] = fmax3(m4[j & 3], lo, hi);
             }
-            const float m_tile = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+            float m_tile = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+            if (TPR == 2) {                                   // the row maximum of the tile over both halves (both threads take the same decisions)
+                float* xm = xch + (t & 1) * 256;
+                xm[half * 128 + row] = m_tile;
+                asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");
+                m_tile = fmaxf(m_tile, xm[(half ^ 1) * 128 + row]);
+            }
             float alpha = 1.f;
             if (m_tile > m_used + RESCALE_THRESHOLD) {
                 alpha = fast_exp2(m_used - m_tile);   // 0 on the first tile (m_used = -inf)
                 m_used = m_tile;
             }
-            // exponentials: the MUFU delivers 16 per clock and SM, the tensor pipe wants 128 x 128 of them per 512 clocks of MMAs,
-            // so 3 of every 8 score pairs take the FMA-pipe polynomial (exp2_poly2) instead
             const uint64_t nm2 = pack2(-m_used, -m_used);
             uint64_t sum2[2] = {0ull, 0ull};
-            uint32_t pk[TN / 2];
+            uint32_t pk[KPT / 2];
 #pragma unroll
-            for (int j = 0; j < TN / 2; ++j) {
+            for (int j = 0; j < KPT / 2; ++j) {
                 const uint64_t x2 = fadd2(t2[j], nm2);
                 uint64_t p2;
                 if (POLY_EXP && ((j & 7) == 1 || (j & 7) == 4 || (j & 7) == 6)) {
@@ -211,29 +230,29 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
                 unpack2(fadd2(sum2[0], sum2[1]), a, b);
                 sum = a + b;
             }
-            l_run = l_run * alpha + sum;
+            l_run = l_run * alpha + sum;                       // this thread's keys only: the halves are added once at the end
             if (t > 0) {
                 mbar_wait(&bar_pv_done, (t - 1) & 1);          // P and O are free again
                 fence_after_sync();
-                if (__any_sync(0xffffffffu, alpha != 1.f)) {
+                if (__any_sync(0xffffffffu, alpha != 1.f)) {   // each thread rescales its HD / TPR accumulator columns
 #pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
+                    for (int h2 = 0; h2 < HD / TPR / 32; ++h2) {
                         uint32_t o[32];
-                        tmem_ld32(tm_O + lane_addr + h2 * 32, o);
+                        tmem_ld32(tm_O + lane_addr + half * (HD / TPR) + h2 * 32, o);
                         tmem_wait_ld();
 #pragma unroll
                         for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
-                        tmem_st32(tm_O + lane_addr + h2 * 32, o);
+                        tmem_st32(tm_O + lane_addr + half * (HD / TPR) + h2 * 32, o);
                     }
                 }
             }
             {
-                uint32_t half[32];
+                uint32_t part[32];
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
+                for (int h2 = 0; h2 < KPT / 64; ++h2) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) half[j] = pk[h2 * 32 + j];
-                    tmem_st32(tm_P + lane_addr + h2 * 32, half);
+                    for (int j = 0; j < 32; ++j) part[j] = pk[h2 * 32 + j];
+                    tmem_st32(tm_P + lane_addr + half * (KPT / 2) + h2 * 32, part);
                 }
             }
             tmem_wait_st();
@@ -242,17 +261,24 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
         }
         mbar_wait(&bar_pv_done, (T - 1) & 1);
         fence_after_sync();
+        if (TPR == 2) {
+            float* xl = xch + 512;
+            xl[half * 128 + row] = l_run;
+            asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");
+            l_run += xl[(half ^ 1) * 128 + row];
+        }
         const float inv = 1.f / l_run;
         // O / rowsum -> bf16 -> the (now idle) Q tile as a SWIZZLE_128B staging tile -> one TMA store of the window rows
         const uint32_t stg = sbase + SmemLayout::Q + (uint32_t)row * 128;
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
+        for (int h2 = 0; h2 < HD / TPR / 32; ++h2) {
             uint32_t o[32];
-            tmem_ld32(tm_O + lane_addr + h2 * 32, o);
+            const int col0 = half * (HD / TPR) + h2 * 32;
+            tmem_ld32(tm_O + lane_addr + col0, o);
             tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-                const uint32_t chunk = (uint32_t)((h2 * 32 + j) >> 3) ^ (uint32_t)(row & 7);
+                const uint32_t chunk = (uint32_t)((col0 + j) >> 3) ^ (uint32_t)(row & 7);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (chunk << 4)),
                              "r"(pack_bf16(__uint_as_float(o[j]) * inv, __uint_as_float(o[j + 1]) * inv)),
                              "r"(pack_bf16(__uint_as_float(o[j + 2]) * inv, __uint_as_float(o[j + 3]) * inv)),
@@ -261,7 +287,7 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
             }
         }
         fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(SM_THREADS) : "memory");
         if (tid == 0) {
             tma::store_3d(&out_map, sbase + SmemLayout::Q, head * HD, x0, y0 + qtile * (TM / WS));
             tma::store_commit();
@@ -270,7 +296,7 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 5) tmem_dealloc(tmem_slot, 256);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_slot, 256);
 }
 
 }  // namespace
