@@ -379,6 +379,8 @@ def test_mlp_fused_vs_fp64(M, C, hidden):
             stats = torch.stack((xs.sum(-1), (xs * xs).sum(-1)), dim=-1).permute(1, 0, 2).contiguous()
         out, part = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2, want_stats=True)
         assert rel_err(out, ref) <= 4e-3
+        out16 = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2, hidden_fp16=True)       # fp16 hidden operand (2 GELU against 0.5 W2)
+        assert rel_err(out16, ref) <= 4e-3
         outb = o.mlp_ln(x, (stats, gam, bet, 1e-5), w1, b1, w2, b2, hidden_fp16=False)      # bf16 hidden operand: the GEMM pair's bits
         pair = o.linear(o.linear(x, w1, b1, act="gelu", ln=(stats, gam, bet, 1e-5)), w2, b2, residual=x)
         assert torch.equal(outb, pair)
