@@ -368,7 +368,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                     if (act == 1) {                               // two elements per instruction: the GELU epilogue is issue-bound
 #pragma unroll
-                        for (int e = 0; e < 8; e += 2) gelu_fast2(v[e], v[e + 1]);
+                        for (int e = 0; e < 8; e += 2) unpack2(gelu_f32x2(pack2(v[e], v[e + 1])), v[e], v[e + 1]);
                     } else if (act == 2) {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);

@@ -252,17 +252,27 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cs.x), "=f"(cs.y), "=f"(cs.z), "=f"(cs.w) : "r"(vec_s + 4 * (col0 + j + e)));
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bb.x), "=f"(bb.y), "=f"(bb.z), "=f"(bb.w) : "r"(vec_s + 4 * (p.hidden + col0 + j + e)));
                     const uint32_t* a = j ? rb : ra;
-                    float v0, v1, v2, v3;
-                    unpack2(ffma2(rstd2, pack2(__uint_as_float(a[e]), __uint_as_float(a[e + 1])), ffma2(nmr2, pack2(cs.x, cs.y), pack2(bb.x, bb.y))), v0, v1);
-                    unpack2(ffma2(rstd2, pack2(__uint_as_float(a[e + 2]), __uint_as_float(a[e + 3])), ffma2(nmr2, pack2(cs.z, cs.w), pack2(bb.z, bb.w))), v2, v3);
+                    const uint64_t x01 = ffma2(rstd2, pack2(__uint_as_float(a[e]), __uint_as_float(a[e + 1])), ffma2(nmr2, pack2(cs.x, cs.y), pack2(bb.x, bb.y)));
+                    const uint64_t x23 = ffma2(rstd2, pack2(__uint_as_float(a[e + 2]), __uint_as_float(a[e + 3])), ffma2(nmr2, pack2(cs.z, cs.w), pack2(bb.z, bb.w)));
                     if (F16) {                                    // fp16 hidden operand holding 2 GELU (w2 carries the 0.5)
+                        float v0, v1, v2, v3;
+                        unpack2(x01, v0, v1);
+                        unpack2(x23, v2, v3);
                         pk[e >> 1] = gelu2x_f16x2(v0, v1);
                         pk[(e >> 1) + 1] = gelu2x_f16x2(v2, v3);
                     } else {
+#ifdef MLP_GELU_F16
+                        float v0, v1, v2, v3;
+                        unpack2(x01, v0, v1);
+                        unpack2(x23, v2, v3);
                         gelu_fast2(v0, v1);
                         gelu_fast2(v2, v3);
                         pk[e >> 1] = pack_bf16(v0, v1);
                         pk[(e >> 1) + 1] = pack_bf16(v2, v3);
+#else
+                        pk[e >> 1] = gelu_bf16x2_f32x2(x01);      // packed fp32x2 GELU: fewer instructions than the packed-fp16 form + conversions
+                        pk[(e >> 1) + 1] = gelu_bf16x2_f32x2(x23);
+#endif
                     }
                 }
                 tmem_st8(tsrc + (j >> 1), pk);
