@@ -260,8 +260,8 @@ int sodt_linear_strided_fwd(const void* x, int ldx, const void* x2, int ldx2, in
  *   sodt_stats_finalize  from the partial (sum, sum of squares) pairs, one per 64-column box, [N/64][M][2], that the GEMM
  *                        which WROTE x emitted through `stats_out` of this function (from its fp32 values before the bf16
  *                        rounding) - then no pass over the token tensor is left for the LayerNorm at all.
- * ln_boxes in 1..3: ln_mean_rstd points at that many partial pairs per row instead ([ln_boxes][M][2], i.e. the stats_out of
- * a GEMM with N <= 192) and the epilogue reduces them itself with ln_eps: no sodt_stats_finalize launch.
+ * ln_boxes in 1..6: ln_mean_rstd points at that many partial pairs per row instead ([ln_boxes][M][2], i.e. the stats_out of
+ * a GEMM with N <= 384) and the epilogue reduces them itself with ln_eps: no sodt_stats_finalize launch.
  * ln_mean_rstd == NULL: a plain Linear that only emits stats_out.  res_rows as in sodt_linear_strided_fwd (the patch
  * embedding adds the batch-broadcast pos_embed and emits the statistics for the first block's norm1).
  */

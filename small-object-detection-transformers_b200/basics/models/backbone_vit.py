@@ -326,8 +326,8 @@ class SwinTransformerBlock(nn.Module):
         if x.dtype == torch.bfloat16 and ops.USE_TC_LINEAR and ops.linear_ln_supported(x, C):
             # bf16, LayerNorms folded: qkv and fc1 read the raw residual stream and normalise in their epilogues from the row
             # statistics that the proj / fc2 GEMM (or the producer of x) emitted with its result
-            # row statistics: up to 3 partial pairs per row go to the GEMM as they are, more are reduced by a small kernel first
-            prep = lambda st, eps: st if st.shape[0] <= 3 else ops.finalize_stats(st, C, eps)
+            # row statistics: up to 6 partial pairs per row (C <= 384) go to the GEMM as they are, more are reduced by a small kernel first
+            prep = lambda st, eps: st if st.shape[0] <= 6 else ops.finalize_stats(st, C, eps)
             mr = prep(stats, self.norm1.eps) if stats is not None else ops.row_stats(x, self.norm1.eps)
             qkv = ops.linear(x, attn.qkv.weight, attn.qkv.bias, ln=(mr, self.norm1.weight, self.norm1.bias, self.norm1.eps))
             o = ops.window_attention(qkv.view(B, H, W, 3 * C), attn.relative_position_bias_table, attn.num_heads,

@@ -72,7 +72,7 @@ extern "C" int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_r
                                   float* stats_out, int M, int N, int K, int act, int dtype, void* stream) {
     using namespace sodt;
     if (!x || !w || !out || M <= 0 || N <= 0 || K <= 0 || act < 0 || act > 2) return SODT_ERR_INVALID_ARG;
-    if ((ln_mean_rstd && !ln_colsum) || res_rows < 0 || ln_boxes < 0 || ln_boxes > 3 || ln_eps < 0.f) return SODT_ERR_INVALID_ARG;
+    if ((ln_mean_rstd && !ln_colsum) || res_rows < 0 || ln_boxes < 0 || ln_boxes > 6 || ln_eps < 0.f) return SODT_ERR_INVALID_ARG;
     if (dtype != SODT_BF16 || !linear_tc_supported(M, N, K)) return SODT_ERR_UNSUPPORTED;
     if (!aligned16(x) || !aligned16(w) || !aligned16(out) || (bias && !aligned16(bias)) || (residual && !aligned16(residual)) ||
         (ln_colsum && !aligned16(ln_colsum)) || (reinterpret_cast<uintptr_t>(ln_mean_rstd) & 7) || (reinterpret_cast<uintptr_t>(stats_out) & 7))

@@ -296,13 +296,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 if (gr < ep.M) {
                     if (ep.ln_boxes == 0) {
                         r = __ldg(reinterpret_cast<const float2*>(ep.ln_stats) + gr);
-                    } else {        // up to three partial (sum, sum of squares) pairs from the GEMM that wrote the row: no finalize pass
+                    } else {        // partial (sum, sum of squares) pairs from the GEMM that wrote the row: no finalize pass
                         const float2* p = reinterpret_cast<const float2*>(ep.ln_stats) + gr;
-                        const float2 p0 = __ldg(p);
-                        const float2 p1 = ep.ln_boxes > 1 ? __ldg(p + ep.M) : make_float2(0.f, 0.f);
-                        const float2 p2 = ep.ln_boxes > 2 ? __ldg(p + 2 * (size_t)ep.M) : make_float2(0.f, 0.f);
-                        const float mean = (p0.x + p1.x + p2.x) * ep.ln_inv_k;
-                        r = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, (p0.y + p1.y + p2.y) * ep.ln_inv_k), 0.f) + ep.ln_eps));
+                        float sx = 0.f, sy = 0.f;                 // up to six partial pairs (C <= 384): issued together, one L2 round trip
+#pragma unroll
+                        for (int b = 0; b < 6; ++b) {
+                            const float2 q = b < ep.ln_boxes ? __ldg(p + (size_t)b * ep.M) : make_float2(0.f, 0.f);
+                            sx += q.x; sy += q.y;
+                        }
+                        const float mean = sx * ep.ln_inv_k;
+                        r = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, sy * ep.ln_inv_k), 0.f) + ep.ln_eps));
                     }
                 }
             }
@@ -556,7 +559,7 @@ bool linear_tc_supported(int M, int N, int K) { return M > 0 && K % BK == 0 && K
 
 int linear_tc(const LinearTcArgs& g, const void* x2, int ldx2, int k_split, int num_sms, cudaStream_t stream) {
     if (!linear_tc_supported(g.M, g.N, g.K)) return SODT_ERR_UNSUPPORTED;
-    if (g.ln_stats && (!g.ln_colsum || x2 != nullptr || g.ln_boxes < 0 || g.ln_boxes > 3)) return SODT_ERR_INVALID_ARG;
+    if (g.ln_stats && (!g.ln_colsum || x2 != nullptr || g.ln_boxes < 0 || g.ln_boxes > 6)) return SODT_ERR_INVALID_ARG;
     if (g.residual && g.res_rows > 0 && g.res_rows != g.M && (g.res_rows % BM || g.M % g.res_rows)) return SODT_ERR_INVALID_ARG;
     if (g.ldx % 8 || g.ldo % 8 || (g.residual && g.ldr % 8) || g.ldx < (x2 ? k_split : g.K) || g.ldo < g.N) return SODT_ERR_INVALID_ARG;
     Addressing ad{};

@@ -503,7 +503,7 @@ def linear_ln_supported(x, n_out):
 def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=None, want_stats=False):
     """act(cat(x, x2) @ weight.T + bias) (+ residual) over the last dim.
     ``ln=(stats, ln_weight, ln_bias[, eps])``: computes ``Linear(LayerNorm(x))`` from the raw rows ``x`` and their statistics:
-    ``stats`` = [M, 2] (mean, rstd) from row_stats / finalize_stats, or the [boxes <= 3, M, 2] partial sums a ``want_stats``
+    ``stats`` = [M, 2] (mean, rstd) from row_stats / finalize_stats, or the [boxes <= 6, M, 2] partial sums a ``want_stats``
     GEMM emitted (reduced in the epilogue with ``eps``); the LayerNorm is folded into the weights (cached) and the epilogue.
     ``want_stats``: also return the [N/64, M, 2] partial (sum, sum of squares) of the result rows -> (out, partials).
     Both need a shape for which linear_ln_supported() holds.  bf16 shapes the tcgen05 kernel supports run there with the
@@ -549,8 +549,8 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
                 raise ValueError("ln statistics must be contiguous fp32 [M, 2] or [boxes, M, 2]")
             if mr.dim() == 3:
                 ln_boxes = mr.shape[0]
-                if ln_boxes > 3:
-                    raise ValueError("more than 3 partial pairs per row: reduce them with finalize_stats first")
+                if ln_boxes > 6:
+                    raise ValueError("more than 6 partial pairs per row: reduce them with finalize_stats first")
         stats_out = torch.empty((N // 64, M, 2), dtype=torch.float32, device=x.device) if want_stats else None
         label = f"linear[M={M},N={N},K={K},act={act},res={residual is not None},ln={ln is not None},stats={want_stats}]"
         if ln is not None or want_stats:
