@@ -101,19 +101,30 @@ def candidates(pred_img, conf_thres, multi_label, classes=None):
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
                         multi_label=False, max_det=300, max_nms=30000, max_wh=4096, merge=True,
-                        redundant=True, return_indices=False, early_stop=False):
+                        redundant=True, return_indices=False, early_stop=False, labels=()):
     """general.py:425-512 on a float32 numpy array [B, R, 5+nc].
 
     Returns a list of [n_i, 6] float32 arrays; with ``return_indices`` also, per image,
     the kept row numbers into that image's candidate matrix after the max_nms cut
     (the quantity that must be bit-exact).  The 10 s wall-clock watchdog
     (general.py:439,508-510) is deliberately not restated.
+    ``labels`` (general.py:451-458, autolabelling): per image an array [n, 5] of (class, cx, cy, w, h); every label joins
+    the image's candidates AFTER the objectness filter as a row with objectness 1 and a one-hot class score of 1.
     """
     prediction = np.asarray(prediction, dtype=F32)
     nc = prediction.shape[2] - 5
     multi_label = bool(multi_label) and nc > 1
     outs, idxs = [], []
-    for img in prediction:
+    for xi, img in enumerate(prediction):
+        if labels and len(labels[xi]):
+            # rows with objectness 1 pass the objectness filter whenever conf_thres < 1 (and die at the class-confidence filter
+            # otherwise, as in the reference), so appending them before the filter gives the reference's candidate list and order
+            l = np.asarray(labels[xi], dtype=F32)
+            v = np.zeros((l.shape[0], nc + 5), dtype=F32)
+            v[:, :4] = l[:, 1:5]
+            v[:, 4] = 1.0
+            v[np.arange(l.shape[0]), l[:, 0].astype(np.int64) + 5] = 1.0
+            img = np.concatenate([img, v], 0)
         x = candidates(img, conf_thres, multi_label, classes)
         n = x.shape[0]
         if n == 0:

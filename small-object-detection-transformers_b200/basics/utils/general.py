@@ -41,10 +41,22 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     """Reference signature (general.py:425): list of [n_i, 6] tensors (xyxy, conf, cls), one per image.
 
     The whole batch is processed by one sequence of kernels; the only host sync is the read of
-    the per-image counts needed to build the Python list.  ``labels`` (autolabelling apriori
-    boxes) is not supported.  The reference's 10 s watchdog does not exist here.
+    the per-image counts needed to build the Python list.  ``labels`` (autolabelling, general.py:451-458): per image a tensor
+    [n, 5] of (class, cx, cy, w, h); each label joins its image's candidates as a row with objectness 1 and a one-hot class
+    score -- here as extra prediction rows behind the image's own (images with fewer labels are padded with objectness-0 rows,
+    which the scan drops).  The reference's 10 s watchdog does not exist here.
     """
-    if labels:
-        raise NotImplementedError("apriori labels are not supported by the CUDA NMS")
-    det, counts, _ = ops.nms(prediction.float(), conf_thres, iou_thres, classes, agnostic, multi_label)
+    prediction = prediction.float()
+    if labels and any(len(l) for l in labels):
+        B, _, no = prediction.shape
+        n_max = max(len(l) for l in labels)
+        extra = torch.zeros((B, n_max, no), dtype=torch.float32, device=prediction.device)
+        for i, l in enumerate(labels):
+            if len(l):
+                l = torch.as_tensor(l, dtype=torch.float32, device=prediction.device)
+                extra[i, :len(l), :4] = l[:, 1:5]
+                extra[i, :len(l), 4] = 1.0
+                extra[i, torch.arange(len(l), device=prediction.device), l[:, 0].long() + 5] = 1.0
+        prediction = torch.cat((prediction, extra), dim=1)
+    det, counts, _ = ops.nms(prediction, conf_thres, iou_thres, classes, agnostic, multi_label)
     return [det[i, :n] for i, n in enumerate(counts.tolist())]

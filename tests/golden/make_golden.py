@@ -117,13 +117,22 @@ NMS_CASES = {
     "dense_no_merge": (1, 16384, 192, 0.9, 4, dict(conf_thres=0.05, iou_thres=0.3)),
     "cap_30000": (1, 49152, 1024, 0.2, 5, dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)),
     "empty": (2, 512, 256, 0.0, 6, dict(conf_thres=0.25, iou_thres=0.45)),
+    "apriori_labels": (3, 2048, 256, 0.2, 7, dict(conf_thres=0.25, iou_thres=0.45, labels_seed=9)),
 }
+import importlib.util  # noqa: E402
+_gc = importlib.util.spec_from_file_location("_golden_cases", os.path.join(os.path.dirname(HERE), "golden_cases.py"))
+_gcm = importlib.util.module_from_spec(_gc)
+_gc.loader.exec_module(_gcm)
+nms_kwargs = _gcm.nms_kwargs          # expands labels_seed into the reference's `labels` argument
 
 
 def gen_nms():
     out = {}
     for name, (B, R, img, active, seed, kw) in NMS_CASES.items():
         pred = torch.from_numpy(fx.synthetic_predictions(B, R, 8, img, active, seed))
+        kw = nms_kwargs(kw, B, img)
+        if "labels" in kw:
+            kw["labels"] = [torch.from_numpy(l) for l in kw["labels"]]
         dets = ge.non_max_suppression(pred.clone(), **kw)
         padded = np.zeros((B, 300, 6), dtype=np.float32)
         counts = np.zeros((B,), dtype=np.int32)

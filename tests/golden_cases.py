@@ -34,7 +34,28 @@ NMS_CASES = {
     "dense_no_merge": (1, 16384, 192, 0.9, 4, dict(conf_thres=0.05, iou_thres=0.3)),
     "cap_30000": (1, 49152, 1024, 0.2, 5, dict(conf_thres=0.001, iou_thres=0.6, multi_label=True)),
     "empty": (2, 512, 256, 0.0, 6, dict(conf_thres=0.25, iou_thres=0.45)),
+    # autolabelling: apriori label boxes join the candidates with confidence 1 (reference general.py:451-458); image 1 has none
+    "apriori_labels": (3, 2048, 256, 0.2, 7, dict(conf_thres=0.25, iou_thres=0.45, labels_seed=9)),
 }
+
+
+def nms_kwargs(kw, B, img):
+    """NMS_CASES kwargs with ``labels_seed`` expanded to the reference's ``labels`` argument: per image a float32 array
+    [n, 5] of (class, cx, cy, w, h) in pixels, deterministic in the seed (image 1 gets no labels)."""
+    import numpy as np
+    kw = dict(kw)
+    seed = kw.pop("labels_seed", None)
+    if seed is not None:
+        r = np.random.RandomState(seed)
+        labels = []
+        for i in range(B):
+            n = 0 if i == 1 else int(r.randint(3, 9))
+            cls = r.randint(0, 8, size=(n, 1)).astype(np.float32)
+            cxy = r.uniform(0.1 * img, 0.9 * img, size=(n, 2)).astype(np.float32)
+            wh = r.uniform(0.03 * img, 0.25 * img, size=(n, 2)).astype(np.float32)
+            labels.append(np.concatenate([cls, cxy, wh], 1))
+        kw["labels"] = labels
+    return kw
 
 DETECT_ANCHORS = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119]]
 DETECT_STRIDES = (4.0, 8.0)

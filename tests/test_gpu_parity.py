@@ -15,7 +15,7 @@ from oracle import attention_ref as A
 from oracle import fixtures as fx
 from oracle import model_ref, nms_ref
 from oracle.detect_ref import detect_decode as detect_oracle
-from tests.golden_cases import (CATTN_CASES, DETECT_ANCHORS, DETECT_FEATS, DETECT_STRIDES, NMS_CASES, SWIN_CASES,
+from tests.golden_cases import (CATTN_CASES, DETECT_ANCHORS, DETECT_FEATS, DETECT_STRIDES, NMS_CASES, SWIN_CASES, nms_kwargs,
                                 swin_state_shapes)
 
 pytestmark = pytest.mark.gpu
@@ -506,6 +506,17 @@ def test_nms_vs_reference_golden_and_oracle(golden, name):
     B, R, img, active, seed, kw = NMS_CASES[name]
     g = golden("nms")
     pred = fx.synthetic_predictions(B, R, 8, img, active, seed)
+    if "labels_seed" in kw:         # apriori labels (general.py:451-458) are a feature of the reference-signature wrapper
+        from sodt_b200.basics.utils.general import non_max_suppression
+        kwl = nms_kwargs(kw, B, img)
+        dets = non_max_suppression(torch.from_numpy(pred).cuda(), **{**kwl, "labels": [torch.from_numpy(l) for l in kwl["labels"]]})
+        outs = nms_ref.non_max_suppression(pred, early_stop=True, **kwl)
+        assert [d.shape[0] for d in dets] == list(g[name + "/count"])
+        for i, d in enumerate(dets):
+            d, ref = d.cpu().numpy(), g[name + "/det"][i, :d.shape[0]]
+            assert np.array_equal(d[:, 4:], ref[:, 4:]) and np.array_equal(d[:, 4:], outs[i][:, 4:])
+            assert np.abs(d[:, :4] - ref[:, :4]).max(initial=0.0) < 1e-3
+        return
     det, counts, keep = run_cuda_nms(pred, kw)
     outs, idxs = nms_ref.non_max_suppression(pred, return_indices=True, early_stop=True, **kw)
     assert np.array_equal(counts, g[name + "/count"])

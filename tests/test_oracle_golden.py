@@ -12,7 +12,8 @@ from oracle import fixtures as fx
 from oracle import model_ref, nms_ref
 from oracle.detect_ref import detect_decode
 from tests.golden_cases import (CATTN_CASES, DETECT_ANCHORS, DETECT_FEATS, DETECT_STRIDES, MF_SHAPES, NMS_CASES, SAM_CASES,
-                                SWIN_BIG_CASES, SWIN_CASES, V2ATTN_CASES, sam_state_shapes, swin_state_shapes, v2attn_state_shapes)
+                                SWIN_BIG_CASES, SWIN_CASES, V2ATTN_CASES, nms_kwargs, sam_state_shapes, swin_state_shapes,
+                                v2attn_state_shapes)
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -121,7 +122,7 @@ def test_nms_matches_reference(golden, name):
     B, R, img, active, seed, kw = NMS_CASES[name]
     g = golden("nms")
     pred = fx.synthetic_predictions(B, R, 8, img, active, seed)
-    outs = nms_ref.non_max_suppression(pred, early_stop=(name == "cap_30000"), **kw)
+    outs = nms_ref.non_max_suppression(pred, early_stop=(name == "cap_30000"), **nms_kwargs(kw, B, img))
     for i, d in enumerate(outs):
         n = int(g[name + "/count"][i])
         assert d.shape[0] == n, (name, i)
