@@ -387,9 +387,23 @@ class CAttention(nn.Module):
 
     def forward(self, q, k, v, dimensions=None, mask=None):
         """q, k, v [B_, N, C] (+ mask [nW, N, N]) -> [B_, N, C] with the reference's order of operations (scores, + mask
-        BEFORE scaling, / sqrt(C / heads), softmax; backbone_vit.py:589-616).  Standalone use only: inside the detector
-        CAttentionBlock runs the four cross attentions and their LayerNorms in one kernel, this method is library math in
-        fp32 on the tensors' device."""
+        BEFORE scaling, / sqrt(C / heads), softmax; backbone_vit.py:589-616).  Standalone use (inside the detector
+        CAttentionBlock runs the four cross attentions and their LayerNorms in one kernel).  CUDA tensors whose windows are
+        square run on the exact attention kernel (every window a one-window image of cat(q, k, v); (s + mask) / sqrt(d) =
+        s / sqrt(d) + mask / sqrt(d), so the mask goes in pre-scaled); host tensors and other shapes: library math in fp32."""
+        B_, N, C = q.shape
+        ws = math.isqrt(N)
+        if (q.is_cuda and ws * ws == N and ws > 1 and C % self.num_heads == 0 and q.dtype in (torch.float32, torch.bfloat16)
+                and k.shape == q.shape and v.shape == q.shape):
+            hd = C // self.num_heads
+            scale = 1.0 / math.sqrt(hd)
+            table = torch.zeros((2 * ws - 1) ** 2, self.num_heads, dtype=torch.float32, device=q.device)      # no position bias
+            try:
+                o = ops.window_attention_ex(torch.cat((q, k, v), dim=-1).view(B_, ws, ws, 3 * C), table, self.num_heads, ws, 0,
+                                            scale=scale, dense_mask=None if mask is None else mask.float() * scale)
+                return o.view(B_, N, C)
+            except ops._capi.SodtError:           # a shape the exact kernel does not cover (head_dim > 64, huge windows)
+                pass
         B_, N, C = q.shape
         h = self.num_heads
         c = C // h
