@@ -3,6 +3,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <utility>
 
 #include "../../include/sodt_b200.h"
 
@@ -26,6 +29,38 @@ inline int cuda_status(cudaError_t e) {
     if (e == cudaSuccess) return SODT_OK;
     g_last_cuda_error = e;
     return SODT_ERR_CUDA;
+}
+
+// Programmatic dependent launch.  The kernels of the detector step are launched with programmatic stream serialization: their
+// CTAs may become resident while the previous kernel of the stream is still draining (each kernel calls pdl_trigger() at its
+// start, so its dependents are released as soon as every CTA of the grid has started), run their prologue (barrier
+// initialisation, tensor-memory allocation) and then block in pdl_wait() until the previous grid has completed and its memory
+// is visible.  NO global memory is read or written before pdl_wait() -- not even weights or prepared tables: a caller may have
+// produced them with the launch just before.  What overlaps is the launch latency, the CTA ramp-up and the prologue.
+// SODT_PDL=0 in the environment launches every kernel fully serialised (the griddepcontrol instructions are no-ops then).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SODT_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// Launches `kern` with the programmatic-stream-serialization attribute (`pdl` false: a plain, fully serialised launch).
+// Only for kernels that call pdl_wait() before their first global memory access.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl && pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

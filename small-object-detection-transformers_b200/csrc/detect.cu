@@ -21,6 +21,8 @@ detect_decode_kernel(const T* __restrict__ raw, long long sb, long long sc, long
                      const float* __restrict__ anchors_px, float* __restrict__ z, T* __restrict__ x_perm,
                      int na_rt, int no_rt, int ny, int nx, float stride, long long rows_total, long long row_offset) {
     extern __shared__ float tile[];  // [na*no][XT+1]
+    pdl_trigger();
+    pdl_wait();                      // programmatic dependent launch (common.cuh)
     const int na = NA_ > 0 ? NA_ : na_rt, no = NO_ > 0 ? NO_ : no_rt;
     const int CH = na * no;
     const int x0 = blockIdx.x * XT;
@@ -100,16 +102,16 @@ extern "C" int sodt_detect_decode(const void* raw, long long sb, long long sc, l
     if (smem > 48 * 1024) return SODT_ERR_UNSUPPORTED;
     dim3 grid((nx + XT - 1) / XT, ny, B);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
     if (dtype == SODT_F32)
-        detect_decode_kernel<float, 0, 0><<<grid, THREADS, smem, s>>>(static_cast<const float*>(raw), sb, sc, sy, sx, anchors_px, z,
-                                                                     static_cast<float*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
+        e = launch_pdl(detect_decode_kernel<float, 0, 0>, grid, dim3(THREADS), smem, s, true, static_cast<const float*>(raw), sb, sc, sy, sx, anchors_px, z,
+                       static_cast<float*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
     else if (na == 3 && no == 13)
-        detect_decode_kernel<__nv_bfloat16, 3, 13><<<grid, THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx, anchors_px,
-                                                                              z, static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride,
-                                                                              rows_total, row_offset);
+        e = launch_pdl(detect_decode_kernel<__nv_bfloat16, 3, 13>, grid, dim3(THREADS), smem, s, true, static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx,
+                       anchors_px, z, static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
     else
-        detect_decode_kernel<__nv_bfloat16, 0, 0><<<grid, THREADS, smem, s>>>(static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx, anchors_px, z,
-                                                                             static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride,
-                                                                             rows_total, row_offset);
+        e = launch_pdl(detect_decode_kernel<__nv_bfloat16, 0, 0>, grid, dim3(THREADS), smem, s, true, static_cast<const __nv_bfloat16*>(raw), sb, sc, sy, sx,
+                       anchors_px, z, static_cast<__nv_bfloat16*>(x_perm), na, no, ny, nx, stride, rows_total, row_offset);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }

@@ -100,6 +100,8 @@ frontend_tc_kernel(const __grid_constant__ CUtensorMap tmap_wpe, const __grid_co
         fence_barrier_init();
     }
     if (warp == MMA_WARP) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+    pdl_trigger();
+    pdl_wait();                                      // programmatic dependent launch (common.cuh): no global memory is touched above
     // parameters: LayerNorm input of pair q is e_a + e_k + (conv_b[a] + conv_b[k]); pairs (a, k) = (R,G), (G,B), (B,IR), (IR,G)
     for (int i = tid; i < C; i += NTHREADS) {
         const int q = i / E, c = i - q * E, k = q == 3 ? 1 : q + 1;
@@ -457,6 +459,7 @@ extern "C" int sodt_frontend_embed_u8_fwd(const void* rgb, long long rb, long lo
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = p.num_tiles < sms ? p.num_tiles : sms;
-    kern<<<grid, NTHREADS, smem, static_cast<cudaStream_t>(stream)>>>(mw, mp, mo, p);
+    e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, static_cast<cudaStream_t>(stream), true, mw, mp, mo, p);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }

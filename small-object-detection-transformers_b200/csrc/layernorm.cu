@@ -115,6 +115,8 @@ add_layernorm_bf16_vec_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bf
     constexpr int C = 24 * THR;
     constexpr int RPW = 32 / THR;                       // rows per warp
     __shared__ __align__(16) float sw[C], sb[C], se[C];
+    pdl_trigger();
+    pdl_wait();                                         // programmatic dependent launch (common.cuh)
     for (int e = threadIdx.x; e < C; e += blockDim.x) { sw[e] = w[e]; sb[e] = b[e]; se[e] = extra_bias ? extra_bias[e] : 0.f; }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -190,9 +192,10 @@ int launch_vec(const void* a, const void* r, const float* w, const float* b, con
     long long blocks = (rows + 8 * RPW - 1) / (8 * RPW);
     const long long resident = 148LL * 8;
     if (blocks > resident) blocks = resident;
-    add_layernorm_bf16_vec_kernel<THR><<<(unsigned)blocks, 256, 0, stream>>>(
+    const cudaError_t e = launch_pdl(add_layernorm_bf16_vec_kernel<THR>, dim3((unsigned)blocks), dim3(256), 0, stream, true,
         static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(r), w, b, extra_bias,
         static_cast<__nv_bfloat16*>(sum_out), static_cast<__nv_bfloat16*>(y), rows, eps);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }
 
@@ -225,6 +228,8 @@ row_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ 
     const int sub = threadIdx.x & 7;
     const int chunks = C >> 3;
     const float inv = 1.f / (float)C;
+    pdl_trigger();
+    pdl_wait();
     for (long long row = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); row < rows; row += (long long)gridDim.x * 32) {
         const uint4* src = reinterpret_cast<const uint4*>(x + row * ld);
         float s1 = 0.f, s2 = 0.f;
@@ -251,6 +256,8 @@ row_stats_bf16_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ 
 // Partial (sum, sum of squares) per 64-column box, [boxes][rows][2] as emitted by the GEMM epilogue, -> (mean, rstd) per row.
 __global__ void __launch_bounds__(256)
 stats_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ stats, long long rows, int boxes, float inv, float eps) {
+    pdl_trigger();
+    pdl_wait();
     for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < rows; row += (long long)gridDim.x * 256) {
         float s1 = 0.f, s2 = 0.f;
         for (int b = 0; b < boxes; b += 4) {
@@ -275,8 +282,9 @@ extern "C" int sodt_row_stats(const void* x, long long ld, float* mean_rstd, lon
     if (!aligned16(x) || (reinterpret_cast<uintptr_t>(mean_rstd) & 7)) return SODT_ERR_ALIGNMENT;
     long long blocks = (rows + 31) / 32;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    row_stats_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), reinterpret_cast<float2*>(mean_rstd), rows, C, ld, eps);
+    const cudaError_t e = launch_pdl(row_stats_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), true,
+        static_cast<const __nv_bfloat16*>(x), reinterpret_cast<float2*>(mean_rstd), rows, C, (long long)ld, eps);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }
 
@@ -286,8 +294,9 @@ extern "C" int sodt_stats_finalize(const float* partials, int boxes, float* mean
     if ((reinterpret_cast<uintptr_t>(partials) & 7) || (reinterpret_cast<uintptr_t>(mean_rstd) & 7)) return SODT_ERR_ALIGNMENT;
     long long blocks = (rows + 255) / 256;             // one row per thread: latency-bound with fewer threads
     if (blocks > 148 * 64) blocks = 148 * 64;
-    stats_finalize_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const cudaError_t e = launch_pdl(stats_finalize_kernel, dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), true,
         reinterpret_cast<const float2*>(partials), reinterpret_cast<float2*>(mean_rstd), rows, boxes, 1.f / (float)C, eps);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }
 

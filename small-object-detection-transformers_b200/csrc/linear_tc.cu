@@ -44,7 +44,15 @@ constexpr int EPI_WARPS = EPI_GROUPS * 4;
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int NTHREADS = (EPI_WARPS + 2) * 32;
 
-enum { MODE_PLAIN = 0, MODE_CONV = 1, MODE_MERGE = 2, MODE_UPCAT = 3 };
+enum { MODE_PLAIN = 0, MODE_CONV = 1, MODE_MERGE = 2, MODE_UPCAT = 3, MODE_HALO = 4 };
+// MODE_HALO: the conv taps of one kernel row read ONE halo tile.  A 128-pixel tile of an image row needs the pixels
+// [x0 - pad_l, x0 - pad_l + 128 + kw - 1) of input row y + ky - pad_t for its kw taps (ky, 0..kw-1): they are loaded once as a
+// (64 channels, 128 + kw - 1) box and tap kx is the A operand that STARTS kx ROWS (kx * 128 B) into the SWIZZLE_128B tile -- the
+// tensor core applies the swizzle to absolute shared-memory address bits, so a start address that is not a multiple of the
+// 1024-byte atom is exact with the descriptor's base-offset field left 0 (tests/probes/rowshift_probe.cu, all shifts 0-9 on a
+// B200).  A k-stage is one (ky, 64-channel block) with kw k-blocks of W: the conv GEMMs run at the SM's operand ingest rate, and
+// this halves (2x2) / thirds (3x3) the A bytes a tile pulls from L2.
+constexpr int HALO_BYTES = 17 * 1024;       // (128 + kw - 1 <= 136) rows x 128 B, rounded to the swizzle atom
 
 struct Epilogue {
     const float* bias;
@@ -144,9 +152,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int nkb = K / BK;
+    const bool halo = ad.mode == MODE_HALO;
+    const int sub = halo ? ad.kw : 1;                            // k-blocks per ring stage
+    const int nst = nkb / sub;                                   // ring stages per tile
+    const uint32_t a_stage = halo ? HALO_BYTES : A_BYTES;
     // shared memory: [resident W: nkb k-blocks][ring of A (+ B) stages][4 staging boxes]
     const uint32_t ring_base = sbase + (WRES ? nkb * B_BYTES : 0);
-    const uint32_t stage_bytes = A_BYTES + (WRES ? 0 : B_BYTES);
+    const uint32_t stage_bytes = a_stage + (WRES ? 0 : sub * B_BYTES);
     const uint32_t staging_base = ring_base + stages * stage_bytes;
     // tile walk: WRES: N-tile nt0 is fixed, M-tiles mt0, mt0 + mstep, ...; otherwise tiles blockIdx.x, + gridDim.x, ... in (mt, nt) order
     const int nt0 = WRES ? cid % num_n_tiles : 0;
@@ -175,6 +187,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     else __syncthreads();
     fence_after_sync();
     const uint32_t tm = tmem_slot;
+    pdl_trigger();
+    pdl_wait();                                                  // programmatic dependent launch: no global memory is touched above
 
     if (warp == PRODUCER_WARP) {
         if (lane == 0 && n_iter > 0) {
@@ -188,7 +202,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 tile_at(it, mt, nt);
                 const int row0 = (mt * MT_ROWS + crank) * BM;
                 int p0 = 0, p1 = 0, p2 = 0;                      // conv: x0, y0, b;  merge: j0, bi0
-                if (ad.mode == MODE_CONV || ad.mode == MODE_UPCAT) {
+                if (ad.mode == MODE_CONV || ad.mode == MODE_UPCAT || halo) {
                     p2 = row0 / ad.HW;
                     const int rem = row0 - p2 * ad.HW;
                     p1 = rem / ad.W;
@@ -198,6 +212,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     p0 = row0 - p1 * ad.W;
                 }
                 int tap = 0, cc = 0;                             // running (tap, channel block) of the k loop
+                if (halo) {                                      // stage = (kernel row ky, channel block cc): one halo box + kw blocks of W
+                    const uint32_t tx = (uint32_t)(BM + ad.kw - 1) * 128u + (WRES ? 0u : (uint32_t)(ad.kw * B_BYTES));
+                    int ky = 0;
+                    for (int ks = 0; ks < nst; ++ks) {
+                        if (round > 0) mbar_wait(&empty[stage], (uint32_t)((round - 1) & 1));
+                        const uint32_t sa = ring_base + stage * stage_bytes;
+                        if (CTA2) {
+                            if (crank == 0) mbar_expect_tx(&full[stage], 2 * tx);
+                            const uint32_t fb = mapa_u32(smem_u32(&full[stage]), 0);
+                            tma_load_4d_pair(sa, &tmap_x, fb, cc * BK, p0 - ad.pad_l, p1 + ky - ad.pad_t, p2);
+                            for (int kx = 0; kx < ad.kw; ++kx)
+                                tma_load_2d_pair(sa + HALO_BYTES + kx * B_BYTES, &tmap_w, fb, ((ky * ad.kw + kx) * ad.cpb + cc) * BK, nt * BN + crank * BNL);
+                        } else {
+                            mbar_expect_tx(&full[stage], tx);
+                            tma_load_4d(sa, &tmap_x, &full[stage], cc * BK, p0 - ad.pad_l, p1 + ky - ad.pad_t, p2);
+                            if (!WRES)
+                                for (int kx = 0; kx < ad.kw; ++kx)
+                                    tma_load_2d(sa + HALO_BYTES + kx * B_BYTES, &tmap_w, &full[stage], ((ky * ad.kw + kx) * ad.cpb + cc) * BK, nt * BN);
+                        }
+                        if (++cc == ad.cpb) { cc = 0; ++ky; }
+                        if (++stage == stages) { stage = 0; ++round; }
+                    }
+                    continue;
+                }
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (round > 0) mbar_wait(&empty[stage], (uint32_t)((round - 1) & 1));
                     const uint32_t sa = ring_base + stage * stage_bytes;
@@ -252,17 +290,22 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 const int a = it % NACC;
                 if (it >= NACC) mbar_wait(&acc_empty[a], (uint32_t)(((it / NACC) - 1) & 1));
                 fence_after_sync();
-                for (int kb = 0; kb < nkb; ++kb) {
+                int ky = 0, cc = 0;                              // halo: (kernel row, channel block) of the stage
+                for (int st = 0; st < nst; ++st) {
                     mbar_wait(&full[stage], (uint32_t)(round & 1));
                     fence_after_sync();
                     const uint32_t sa = ring_base + stage * stage_bytes;
-                    const uint64_t da = desc_sw128(sa), db = desc_sw128(WRES ? sbase + kb * B_BYTES : sa + A_BYTES);
+                    for (int kx = 0; kx < sub; ++kx) {           // halo: tap kx = the tile's rows kx .. kx + 127
+                        const int kb = halo ? (ky * sub + kx) * ad.cpb + cc : st;
+                        const uint64_t da = desc_sw128(sa + kx * 128), db = desc_sw128(WRES ? sbase + kb * B_BYTES : sa + a_stage + kx * B_BYTES);
 #pragma unroll
-                    for (int ks = 0; ks < BK / 16; ++ks) {
-                        if (CTA2) mma_ss2(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
-                        else mma_ss(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
+                        for (int ks = 0; ks < BK / 16; ++ks) {
+                            if (CTA2) mma_ss2(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (st | kx | ks) != 0);
+                            else mma_ss(tm + a * BN, da + 2 * ks, db + 2 * ks, idesc, (st | kx | ks) != 0);
+                        }
                     }
                     if (CTA2) mma_commit2(&empty[stage]); else mma_commit(&empty[stage]);
+                    if (halo && ++cc == ad.cpb) { cc = 0; ++ky; }
                     if (++stage == stages) { stage = 0; ++round; }
                 }
                 if (CTA2) mma_commit2(&acc_full[a]); else mma_commit(&acc_full[a]);
@@ -463,10 +506,11 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     if (tiles > 2147483647LL) return SODT_ERR_UNSUPPORTED;
     constexpr int B_BYTES = BNL * BK * 2;
     const int fixed = EPI_GROUPS * BOX_BYTES + 1024 + (WRES ? (g.K / BK) * B_BYTES : 0);
-    int stages = (SMEM_LIMIT - fixed) / (A_BYTES + (WRES ? 0 : B_BYTES));
+    const int stage_bytes = ad.mode == MODE_HALO ? HALO_BYTES + (WRES ? 0 : ad.kw * B_BYTES) : A_BYTES + (WRES ? 0 : B_BYTES);
+    int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return SODT_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)fixed + (size_t)stages * (A_BYTES + (WRES ? 0 : B_BYTES));
+    const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
     auto kern = linear_tc_kernel<BN, EPI, WRES, CTA2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
@@ -481,16 +525,19 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     if (CTA2) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(2 * grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         const int K = g.K;
         e = cudaLaunchKernelEx(&cfg, kern, mx, mx2, mw, mo, mr, ep, ad, K, num_n_tiles, num_m_tiles, stages);
         if (e != cudaSuccess) return cuda_status(e);
         return check_launch();
     }
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mx2, mw, mo, mr, ep, ad, g.K, num_n_tiles, num_m_tiles, stages);
+    e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, mx, mx2, mw, mo, mr, ep, ad, g.K, num_n_tiles, num_m_tiles, stages);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }
 
@@ -523,7 +570,7 @@ int dispatch_bn(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing&
     const long long m_tiles = (g.M + BM - 1) / BM;
     auto fits = [&](int bn) {          // resident W tile + 3 A stages + staging within the shared-memory limit, enough M-tiles per CTA
         const int n_nt = g.N / bn;
-        return g.N % bn == 0 && nkb * bn * BK * 2 + 3 * A_BYTES + EPI_GROUPS * BOX_BYTES + 1024 <= SMEM_LIMIT && n_nt <= num_sms &&
+        return g.N % bn == 0 && nkb * bn * BK * 2 + 3 * (ad.mode == MODE_HALO ? HALO_BYTES : A_BYTES) + EPI_GROUPS * BOX_BYTES + 1024 <= SMEM_LIMIT && n_nt <= num_sms &&
                m_tiles >= 4LL * (num_sms / n_nt);
     };
     // the tile width is the widest that divides N; W stays resident only if it fits at that width (narrower resident
@@ -603,8 +650,18 @@ int conv_tc(const void* x, int ldx, const void* w, const float* bias, void* out,
     Addressing ad{};
     ad.mode = MODE_CONV; ad.k_split = 0; ad.cpb = Cin / BK; ad.kw = kw; ad.pad_t = pad_t; ad.pad_l = pad_l; ad.HW = H * W; ad.W = W;
     const long long dims[4] = {Cin, W, H, B}, strides[3] = {ldx, (long long)W * ldx, (long long)H * W * ldx};
-    const int box[4] = {64, bw, bh, 1};
     CUtensorMap mx;
+    // tiles inside one image row and kw >= 2: the kw taps of a kernel row share one halo box (MODE_HALO);
+    // SODT_CONV_HALO=0 keeps one box per tap (A/B measurements)
+    static const bool halo_on = [] { const char* v = getenv("SODT_CONV_HALO"); return !(v && v[0] == '0'); }();
+    if (halo_on && bh == 1 && kw >= 2 && BM + kw - 1 <= HALO_BYTES / 128) {
+        const int hbox[4] = {64, BM + kw - 1, 1, 1};
+        if (make_map(&mx, x, 4, dims, strides, hbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) {
+            ad.mode = MODE_HALO;
+            return dispatch(mx, mx, ad, g, num_sms, stream);
+        }
+    }
+    const int box[4] = {64, bw, bh, 1};
     if (!make_map(&mx, x, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) return SODT_ERR_CUDA;
     return dispatch(mx, mx, ad, g, num_sms, stream);
 }

@@ -105,6 +105,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant_
     __syncthreads();
     fence_after_sync();
     const uint32_t tm = tmem_slot;
+    pdl_trigger();
+    pdl_wait();                                      // programmatic dependent launch: the prologue above overlaps the previous kernel's tail
 
     if (warp == PRODUCER_WARP) {
         if (lane == 0 && n_iter > 0) {
@@ -392,7 +394,8 @@ int launch(const MlpTcArgs& g, int num_sms, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int grid = p.num_m_tiles < num_sms ? p.num_m_tiles : num_sms;
-    kern<<<grid, NTHREADS, smem, stream>>>(mx, mw1, mw2, mo, p);
+    e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, mx, mw1, mw2, mo, p);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }
 

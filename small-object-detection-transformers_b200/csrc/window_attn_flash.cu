@@ -104,6 +104,8 @@ window_attn_flash_kernel(const __grid_constant__ CUtensorMap in_map, const __gri
     __syncthreads();
     fence_after_sync();
     const uint32_t tm_S = tmem_slot, tm_P = tmem_slot + 128, tm_O = tmem_slot + 192;
+    pdl_trigger();
+    pdl_wait();                    // programmatic dependent launch (common.cuh): no global memory is touched above
 
     if (warp == PRODUCER_WARP) {
         // ===================================================================== producer (one lane, TMA)
@@ -337,7 +339,8 @@ int window_attn_flash(const void* qkv, const float* table, void* out, void* work
             !tma::make_map_bf16(&out_map, out, 3, dout, sout, box, CU_TENSOR_MAP_L2_PROMOTION_NONE)) return SODT_ERR_CUDA;
     }
     dim3 grid(ws * ws / TM, heads, (unsigned)nwin);
-    kern<<<grid, NTHREADS, smem, stream>>>(in_map, out_map, table_t, H, W, C, heads, scale);
+    e = launch_pdl(kern, grid, dim3(NTHREADS), smem, stream, true, in_map, out_map, table_t, H, W, C, heads, scale);
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }
 

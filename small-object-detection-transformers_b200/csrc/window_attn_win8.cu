@@ -188,6 +188,8 @@ window_attn_win8_kernel(const __grid_constant__ Maps in_maps, const __grid_const
         fence_barrier_init();
     }
     if (warp == MMA_WARP0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
+    pdl_trigger();
+    pdl_wait();                    // programmatic dependent launch (common.cuh): no global memory is touched above
     {
         const int n4 = TAB_COPIES * tab_copy_stride(heads) / 4;
         const float4* src = reinterpret_cast<const float4*>(table_p);
@@ -549,13 +551,14 @@ int window_attn_win8(const void* qkv, const float* table, void* out, void* works
         auto kern = window_attn_win8_kernel<16>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e);
-        kern<<<grid, NTHREADS, smem, stream>>>(in_maps, out_maps, static_cast<const float*>(workspace), geo, C, heads, scale, mask_value);
+        e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, in_maps, out_maps, static_cast<const float*>(workspace), geo, C, heads, scale, mask_value);
     } else {
         auto kern = window_attn_win8_kernel<32>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_status(e);
-        kern<<<grid, NTHREADS, smem, stream>>>(in_maps, out_maps, static_cast<const float*>(workspace), geo, C, heads, scale, mask_value);
+        e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, in_maps, out_maps, static_cast<const float*>(workspace), geo, C, heads, scale, mask_value);
     }
+    if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }
 

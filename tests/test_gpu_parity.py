@@ -247,6 +247,11 @@ def test_linear_tc_batch_broadcast_residual():
     (2, 32, 32, 64, 128, (1, 1), (0, 0), "silu"),        # four rows per tile
     (2, 4, 256, 128, 64, (1, 1), (0, 0), None),
     (1, 16, 16, 64, 64, (3, 3), (1, 1), None),           # eight rows per tile
+    (4, 32, 256, 192, 192, (2, 2), (0, 0), "gelu"),      # enough rows for CTA pairs: halo tiles on cta_group::2
+    (2, 128, 128, 128, 128, (3, 3), (1, 1), "silu"),     # 3x3 halo tiles on CTA pairs (K = 1152)
+    (2, 8, 256, 64, 64, (2, 2), (1, 1), None),           # 2x2 with the padding above / left
+    (1, 8, 128, 64, 128, (3, 2), (2, 0), "silu"),        # kh != kw, two padding rows above
+    (1, 4, 384, 64, 64, (1, 3), (0, 2), None),           # three tiles per image row
 ])
 def test_conv2d_nhwc_tap_gemm_vs_torch(B, H, W, Cin, Cout, k, pad, act):
     x = fx.det_input(f"cv_x:{B}:{H}:{W}:{Cin}", (B, H, W, Cin)).to("cuda", torch.bfloat16)
