@@ -130,6 +130,14 @@ constexpr int epi_code(bool bias, bool ln, bool res, bool stats, int act) {
 // (qkv, fc1) ran at the L2 -> SM rate (~9 TB/s measured), not at the HBM rate.
 constexpr int MAX_STAGES = 8;
 
+// LIN_TRACE (experiments only, tools/trace_linear.py): CTA 0 records clock64 at the hand-offs of its first 64 tiles
+#ifdef LIN_TRACE
+__device__ long long g_lin_trace[6][64][16];
+#define LTRACE(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 64) g_lin_trace[role][tile][ev] = clock64(); } while (0)
+#else
+#define LTRACE(role, tile, ev) do { } while (0)
+#endif
+
 // CTA2 ("CTA pair", cta_group::2): two CTAs of a cluster share one 256-row tile: each loads its own 128 rows of A and HALF of
 // the W tile, the leader issues M = 256 MMAs over both shared memories, each CTA runs the epilogue of its own 128 rows.
 // Per SM the operand bytes per output drop by a third at BN = 256 (the K >= 384 GEMMs run at the SM's operand ingest rate).
@@ -238,6 +246,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
                 for (int kb = 0; kb < nkb; ++kb) {
                     if (round > 0) mbar_wait(&empty[stage], (uint32_t)((round - 1) & 1));
+                    if (kb < 16) LTRACE(1, it, kb);
                     const uint32_t sa = ring_base + stage * stage_bytes;
                     if (CTA2) {
                         // both CTAs' boxes complete on the leader's barrier, armed by the leader for the bytes of the pair
@@ -288,11 +297,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (WRES && n_iter > 0) { mbar_wait(&w_full, 0); fence_after_sync(); }
             for (int it = 0; it < n_iter; ++it) {
                 const int a = it % NACC;
+                LTRACE(0, it, 0);
                 if (it >= NACC) mbar_wait(&acc_empty[a], (uint32_t)(((it / NACC) - 1) & 1));
+                LTRACE(0, it, 1);
                 fence_after_sync();
                 int ky = 0, cc = 0;                              // halo: (kernel row, channel block) of the stage
                 for (int st = 0; st < nst; ++st) {
                     mbar_wait(&full[stage], (uint32_t)(round & 1));
+                    if (st < 13) LTRACE(0, it, 2 + st);
                     fence_after_sync();
                     const uint32_t sa = ring_base + stage * stage_bytes;
                     for (int kx = 0; kx < sub; ++kx) {           // halo: tap kx = the tile's rows kx .. kx + 127
@@ -309,6 +321,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     if (++stage == stages) { stage = 0; ++round; }
                 }
                 if (CTA2) mma_commit2(&acc_full[a]); else mma_commit(&acc_full[a]);
+                LTRACE(0, it, 15);
             }
         }
     } else {
@@ -363,14 +376,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             const int grow = mrow * BM + row_in_tile;                    // global output row of this thread
             const float2 mr = mr_next;
             mr_next = load_mr(it + 1);
+            if (issuer) LTRACE(2 + eg, it, 0);
             mbar_wait(&acc_full[a], (uint32_t)((it / NACC) & 1));
+            if (issuer) LTRACE(2 + eg, it, 1);
             fence_after_sync();
 #pragma unroll 1
             for (int bx = 0; bx < NBOX; ++bx) {
                 if (((it * NBOX + bx) & (EPI_GROUPS - 1)) != eg) continue;
                 const int col0 = nt * BN + bx * 64;
                 if (issuer) {
+                    LTRACE(2 + eg, it, 2 + 4 * bx);
                     tma_store_wait_read();                               // the previous box of this group has left smem
+                    LTRACE(2 + eg, it, 3 + 4 * bx);
                     if (has_residual) {                                  // residual box lands in the staging buffer (TMA, swizzled)
                         mbar_expect_tx(&res_full[eg], BOX_BYTES);
                         tma_load_2d(stage_box, &tmap_r, &res_full[eg], col0, (mrow % ep.res_tiles) * BM);
@@ -442,7 +459,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     reinterpret_cast<float2*>(ep.stats_out)[(size_t)(col0 >> 6) * ep.M + grow] = make_float2(so, sso);
                 fence_proxy_async();
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-                if (issuer) { tma_store_2d(&tmap_o, stage_box, col0, mrow * BM); tma_store_commit(); }
+                if (issuer) { LTRACE(2 + eg, it, 4 + 4 * bx); tma_store_2d(&tmap_o, stage_box, col0, mrow * BM); tma_store_commit(); }
             }
             fence_before_sync();
             __syncwarp();                                                // every lane's accumulator loads have completed
@@ -509,6 +526,8 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad, 
     const int stage_bytes = ad.mode == MODE_HALO ? HALO_BYTES + (WRES ? 0 : ad.kw * B_BYTES) : A_BYTES + (WRES ? 0 : B_BYTES);
     int stages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    static const int stage_cap = [] { const char* v = getenv("SODT_MAX_STAGES"); return v ? atoi(v) : MAX_STAGES; }();   // experiments
+    if (stages > stage_cap && stage_cap >= 2) stages = stage_cap;
     if (stages < 2) return SODT_ERR_UNSUPPORTED;
     const size_t smem = (size_t)fixed + (size_t)stages * stage_bytes;
     auto kern = linear_tc_kernel<BN, EPI, WRES, CTA2>;
@@ -602,6 +621,12 @@ int dispatch(const CUtensorMap& mx, const CUtensorMap& mx2, const Addressing& ad
 
 }  // namespace
 
+#ifdef LIN_TRACE
+extern "C" int sodt_debug_trace(void* host, size_t bytes) {
+    return cudaMemcpyFromSymbol(host, g_lin_trace, bytes < sizeof(g_lin_trace) ? bytes : sizeof(g_lin_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 bool linear_tc_supported(int M, int N, int K) { return M > 0 && K % BK == 0 && K >= BK && N % 64 == 0 && N >= 64; }
 
 int linear_tc(const LinearTcArgs& g, const void* x2, int ldx2, int k_split, int num_sms, cudaStream_t stream) {
@@ -658,7 +683,7 @@ int conv_tc(const void* x, int ldx, const void* w, const float* bias, void* out,
         const int hbox[4] = {64, BM + kw - 1, 1, 1};
         if (make_map(&mx, x, 4, dims, strides, hbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) {
             ad.mode = MODE_HALO;
-            return dispatch(mx, mx, ad, g, num_sms, stream);
+                    return dispatch(mx, mx, ad, g, num_sms, stream);
         }
     }
     const int box[4] = {64, bw, bh, 1};
