@@ -153,7 +153,10 @@ def test_window_attention_microbench_geometries(H, C, ws, shift):
 @pytest.mark.parametrize("M,N,K,act,res", [(1000, 576, 192, None, False), (777, 768, 192, "gelu", False), (4096, 192, 768, None, True),
                                            (300, 192, 192, None, True), (129, 1152, 384, None, False), (2048, 1536, 384, "gelu", False),
                                            (513, 384, 1536, None, True), (640, 3072, 768, "gelu", False), (100, 768, 3072, None, True),
-                                           (50000, 768, 192, "gelu", False)])
+                                           (50000, 768, 192, "gelu", False),
+                                           # K = 384 with enough rows for the resident-W CTA pairs (ragged last tile, odd tile count)
+                                           (13000, 1152, 384, None, False), (20077, 384, 384, None, True), (20000, 1536, 384, "gelu", False),
+                                           (16500, 256, 384, None, False)])
 def test_linear_tc_vs_torch(M, N, K, act, res):
     x = fx.det_input(f"lin_x:{M}:{K}", (M, K)).to("cuda", torch.bfloat16)
     w = (fx.det_input(f"lin_w:{N}:{K}", (N, K)) / K ** 0.5).to("cuda", torch.bfloat16)
@@ -198,7 +201,8 @@ def test_linear_tc_strided_operands_and_split_k_sources():
     assert (obuf[:, :N] == 7).all() and (obuf[:, 2 * N:] == 7).all()      # neighbours of the slice untouched
 
 
-@pytest.mark.parametrize("M,K,N,act", [(1000, 192, 576, None), (515, 384, 1536, "gelu"), (300, 768, 768, None), (4096, 192, 192, None)])
+@pytest.mark.parametrize("M,K,N,act", [(1000, 192, 576, None), (515, 384, 1536, "gelu"), (300, 768, 768, None), (4096, 192, 192, None),
+                                       (16384 + 300, 384, 1152, None)])      # resident-W CTA pairs on both GEMMs
 def test_linear_tc_layernorm_fold_vs_torch(M, K, N, act):
     """LayerNorm folded into the GEMM: statistics from row_stats and from the producing GEMM's epilogue (want_stats)."""
     o = ops()
