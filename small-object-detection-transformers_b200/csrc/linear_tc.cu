@@ -380,6 +380,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&acc_full[a], (uint32_t)((it / NACC) & 1));
             if (issuer) LTRACE(2 + eg, it, 1);
             fence_after_sync();
+            bool released = false;
 #pragma unroll 1
             for (int bx = 0; bx < NBOX; ++bx) {
                 if (((it * NBOX + bx) & (EPI_GROUPS - 1)) != eg) continue;
@@ -454,6 +455,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[0], v[1])), "r"(pack_bf16(v[2], v[3])),
                                  "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
                     if ((j & 15) == 8 && j + 8 < 64) tmem_wait_ld();              // the prefetched chunk has landed
+                    if (j == 40) {
+                        // The box's last accumulator columns are in registers (a group takes at most one box of a tile): the
+                        // warp releases the accumulator NOW, not after the remaining arithmetic and the store -- with two
+                        // accumulator buffers (BN >= 192) the MMA issuer waited ~500 cycles per tile for the epilogue otherwise
+                        fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));
+                            else mbar_arrive(&acc_empty[a]);
+                        }
+                        released = true;
+                    }
                 }
                 if (has_stats && grow < ep.M)
                     reinterpret_cast<float2*>(ep.stats_out)[(size_t)(col0 >> 6) * ep.M + grow] = make_float2(so, sso);
@@ -461,11 +474,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
                 if (issuer) { LTRACE(2 + eg, it, 4 + 4 * bx); tma_store_2d(&tmap_o, stage_box, col0, mrow * BM); tma_store_commit(); }
             }
-            fence_before_sync();
-            __syncwarp();                                                // every lane's accumulator loads have completed
-            if (lane == 0) {
-                if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));  // the leader's MMA thread waits for both epilogues
-                else mbar_arrive(&acc_empty[a]);
+            if (!released) {                                             // no box of this tile for this group
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[a]), 0));  // the leader's MMA thread waits for both epilogues
+                    else mbar_arrive(&acc_empty[a]);
+                }
             }
         }
         if (issuer) tma_store_wait_all();
