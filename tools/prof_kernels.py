@@ -64,6 +64,13 @@ skip = torch.randn(B, 256, 256, 256, device=dev, generator=g).to(torch.bfloat16)
 for _ in range(reps):
     ops.upcat_conv1x1(ops.UpCat(low.permute(0, 3, 1, 2), skip.permute(0, 3, 1, 2)), w(128, 384), bias(128), "silu")
 del low, skip
+# conv-shaped GEMMs on halo tiles: head 3x3 (64 -> 64 at 256^2) and the stage-2 conv-MLP taps (2x2, 384 -> 384 at 128^2)
+xc = torch.randn(B, 256, 256, 64, device=dev, generator=g).to(torch.bfloat16)
+xc2 = torch.randn(B, 128, 128, 384, device=dev, generator=g).to(torch.bfloat16)
+for _ in range(reps):
+    ops.conv2d_nhwc(xc, w(64, 9 * 64), bias(64), (3, 3), (1, 1), "silu")
+    ops.conv2d_nhwc(xc2, w(384, 4 * 384), bias(384), (2, 2), (0, 0), "gelu")
+del xc, xc2
 img = torch.rand(B, 4, 1024, 1024, device=dev, generator=g).to(torch.bfloat16)
 cw, cb = 0.3 * torch.randn(4, 48, 16, device=dev, generator=g), 0.1 * torch.randn(4, 48, device=dev, generator=g)
 for _ in range(reps):
