@@ -281,6 +281,21 @@ int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, int ln
  * either way, so the fp16 form skips two conversions per pair).  C in {64, 128, 192}, hidden a multiple of 128 and >= 256,
  * bf16 activations only; out may alias neither x nor weights.
  */
+/*
+ * The attention half of a Swin block up to the projection as one kernel (backbone_vit.py:1090-1123: norm1, roll, window
+ * partition, WindowAttention's qkv Linear :968 and attention core :969-989, reverse partition / roll):
+ *   out = window_attention( LayerNorm(x) w_qkv^T + b_qkv )
+ * x bf16 [B, H, W, C] is the raw residual stream; the LayerNorm is folded exactly as in sodt_linear_ln_fwd (w_qkv = qkv.weight *
+ * diag(ln_weight) in bf16 [3C, C], ln_colsum its fp32 row sums, b_qkv = qkv.bias + qkv.weight . ln_bias; ln_mean_rstd / ln_boxes
+ * as there, indexed by the token's row in [B*H*W]).  The [B, H, W, 3C] qkv tensor never exists; the result is bit-identical to
+ * sodt_linear_ln_fwd followed by sodt_window_attn_fwd_prepared.  `workspace` = the bias-table image sodt_window_attn_prepare
+ * wrote for the same (C, heads, ws = 8).  8 x 8 windows, C = 192 with head_dim 16 or 32, H % 8 == 0, W % 16 == 0, 0 <= shift < 8,
+ * bf16 only; proj + residual remain sodt_linear_ln_fwd.
+ */
+int sodt_attn_block_supported(int B, int H, int W, int C, int heads, int ws, int shift, int dtype);
+int sodt_attn_block_fwd(const void* x, const float* ln_mean_rstd, int ln_boxes, float ln_eps, const float* ln_colsum,
+                        const void* w_qkv, const float* b_qkv, void* out, int B, int H, int W, int C, int heads, int ws, int shift,
+                        int dtype, float scale, float mask_value, const void* workspace, size_t workspace_bytes, void* stream);
 int sodt_mlp_supported(int M, int C, int hidden, int dtype);
 int sodt_mlp_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, int ln_boxes, float ln_eps, const float* ln_colsum,
                     const void* w1, const float* b1, const void* w2, const float* b2, void* out, int ldo,

@@ -43,6 +43,8 @@ SIGNATURES = {
     "sodt_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "sodt_linear_strided_fwd": (_i, [_p, _i, _p, _i, _i, _p, _p, _p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "sodt_linear_ln_fwd": (_i, [_p, _i, _p, _i, _f, _p, _p, _p, _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "sodt_attn_block_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "sodt_attn_block_fwd": (_i, [_p, _p, _i, _f, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _p, _sz, _p]),
     "sodt_mlp_supported": (_i, [_i, _i, _i, _i]),
     "sodt_mlp_ln_fwd": (_i, [_p, _i, _p, _i, _f, _p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _p]),
     "sodt_row_stats": (_i, [_p, _ll, _p, _ll, _i, _f, _i, _p]),

@@ -29,6 +29,11 @@ int window_attn_win8_prepare(const float* table, void* workspace, int heads, cud
 int window_attn_win8(const void* qkv, const float* table, void* out, void* workspace, int B, int H, int W, int C,
                      int heads, int shift, float scale, float mask_value, int num_sms, bool prepared, cudaStream_t stream);
 
+bool attn_block_supported(int H, int W, int C, int heads, int ws, int shift);
+int attn_block(const void* x, const float* ln_stats, int ln_boxes, float ln_eps, const void* w, const float* colsum, const float* bias,
+               const void* table_ws, void* out, int B, int H, int W, int C, int heads, int shift, float scale, float mask_value,
+               int num_sms, cudaStream_t stream);
+
 static int sm_count() {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
@@ -79,6 +84,26 @@ extern "C" int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_r
         return SODT_ERR_ALIGNMENT;
     LinearTcArgs g{x, ldx, w, bias, residual, ldr, res_rows, out, ldo, M, N, K, act, ln_mean_rstd, ln_colsum, stats_out, ln_boxes, ln_eps};
     return linear_tc(g, nullptr, 0, 0, sm_count(), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sodt_attn_block_supported(int B, int H, int W, int C, int heads, int ws, int shift, int dtype) {
+    return B > 0 && dtype == SODT_BF16 && sodt::attn_block_supported(H, W, C, heads, ws, shift) ? 1 : 0;
+}
+
+extern "C" int sodt_attn_block_fwd(const void* x, const float* ln_mean_rstd, int ln_boxes, float ln_eps, const float* ln_colsum,
+                                   const void* w_qkv, const float* b_qkv, void* out, int B, int H, int W, int C, int heads, int ws, int shift,
+                                   int dtype, float scale, float mask_value, const void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace sodt;
+    if (!x || !ln_mean_rstd || !ln_colsum || !w_qkv || !b_qkv || !out || !workspace || B <= 0 || H <= 0 || W <= 0 || C <= 0 || heads <= 0)
+        return SODT_ERR_INVALID_ARG;
+    if (ln_boxes < 0 || ln_boxes > 6 || ln_eps < 0.f) return SODT_ERR_INVALID_ARG;
+    if (dtype != SODT_BF16 || !attn_block_supported(H, W, C, heads, ws, shift)) return SODT_ERR_UNSUPPORTED;
+    if (workspace_bytes < window_attn_win8_workspace(heads)) return SODT_ERR_WORKSPACE;
+    if (!aligned16(x) || !aligned16(w_qkv) || !aligned16(out) || !aligned16(b_qkv) || !aligned16(ln_colsum) || !aligned16(workspace) ||
+        (reinterpret_cast<uintptr_t>(ln_mean_rstd) & 7))
+        return SODT_ERR_ALIGNMENT;
+    return attn_block(x, ln_mean_rstd, ln_boxes, ln_eps, w_qkv, ln_colsum, b_qkv, workspace, out, B, H, W, C, heads, shift, scale, mask_value,
+                      sm_count(), static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sodt_mlp_supported(int M, int C, int hidden, int dtype) {

@@ -582,6 +582,59 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
     return y
 
 
+USE_FUSED_ATTN = True   # norm1 + qkv Linear + window attention of the C = 192 Swin blocks as one kernel (no qkv tensor)
+
+
+def attn_block_supported(x, heads, ws, shift):
+    """True if ``attn_block`` covers ``x`` [B, H, W, C] (bf16, C = 192, 8 x 8 windows, head_dim 16 / 32)."""
+    if not (USE_FUSED_ATTN and USE_LN_FOLD and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+        return False
+    B, H, W, C = x.shape
+    return bool(_capi.lib().sodt_attn_block_supported(B, H, W, C, heads, ws, shift, 1))
+
+
+def attn_block(x, ln, qkv_weight, qkv_bias, bias_table, heads, ws, shift=0, scale=None, mask_value=-100.0):
+    """``window_attention(Linear(LayerNorm(x)))`` -> [B, H, W, C] in one kernel (sodt_attn_block_fwd): the qkv tensor never exists.
+    ``ln=(stats, ln_weight, ln_bias[, eps])`` as in ``linear``; bit-identical to ``window_attention(linear(x, ..., ln=ln), ...)``."""
+    _require_cuda(x, qkv_weight, qkv_bias, bias_table)
+    if not attn_block_supported(x, heads, ws, shift):
+        raise _capi.SodtError("attn_block: unsupported shape (see sodt_attn_block_fwd)")
+    B, H, W, C = x.shape
+    M = B * H * W
+    mr, ln_w, ln_b, ln_eps = (tuple(ln) + (1e-5,))[:4]
+    if mr.dtype != torch.float32 or not mr.is_contiguous() or tuple(mr.shape[-2:]) != (M, 2) or mr.dim() > 3:
+        raise ValueError("ln statistics must be contiguous fp32 [M, 2] or [boxes, M, 2]")
+    ln_boxes = mr.shape[0] if mr.dim() == 3 else 0
+    if ln_boxes > 6:
+        raise ValueError("more than 6 partial pairs per row: reduce them with finalize_stats first")
+    span = (2 * ws - 1) ** 2
+    if tuple(bias_table.shape) != (span, heads):
+        raise ValueError(f"bias_table must be [{span}, {heads}], got {tuple(bias_table.shape)}")
+    x = x.contiguous()
+    w, colsum, b32 = fold_layernorm(qkv_weight, qkv_bias, ln_w, ln_b)
+    lib = _capi.lib()
+
+    def prepare(t):
+        t32 = _as_f32(t)
+        buf = torch.empty(max(int(lib.sodt_window_attn_workspace_bytes(C, heads, ws)), 16), dtype=torch.uint8, device=t.device)
+        with torch.cuda.device(t.device):
+            _capi.check(lib.sodt_window_attn_prepare(t32.data_ptr(), B, H, W, C, heads, ws, shift, 1, buf.data_ptr(), buf.numel(), _stream()),
+                        "sodt_window_attn_prepare")
+        buf.record_stream(torch.cuda.current_stream(t.device))
+        return buf
+    kclass = lib.sodt_window_attn_kernel_class(B, H, W, C, heads, ws, shift, 1)
+    wsp = cached_derived(bias_table, ("wattn_image", kclass, ws), prepare)
+    out = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=x.device)
+    if scale is None:
+        scale = (C // heads) ** -0.5
+    with torch.cuda.device(x.device), _Timed(f"attn_block[B={B},H={H},W={W},C={C},heads={heads},ws={ws},shift={shift}]"):
+        st = lib.sodt_attn_block_fwd(x.data_ptr(), mr.data_ptr(), ln_boxes, float(ln_eps), colsum.data_ptr(), w.data_ptr(), b32.data_ptr(),
+                                     out.data_ptr(), B, H, W, C, heads, ws, shift, 1, float(scale), float(mask_value),
+                                     wsp.data_ptr(), wsp.numel(), _stream())
+    _capi.check(st, "sodt_attn_block_fwd")
+    return out
+
+
 USE_FUSED_MLP = True    # fc1 + GELU + fc2 + residual of the linear-MLP Swin blocks as one kernel (hidden stays in TMEM)
 
 

@@ -476,3 +476,39 @@ def test_cattention_module_forward_kernel_path_vs_reference_golden(golden, dtype
     assert rel_err(y, m(q, k, v, (8, 8), mask)) <= TOL[dtype]
     y2 = m(q.cuda().to(dtype), k.cuda().to(dtype), v.cuda().to(dtype))          # no mask
     assert rel_err(y2, m(q, k, v)) <= TOL[dtype]
+
+
+# ------------------------------------------------------------------ fused attention half (sodt_attn_block_fwd)
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,heads,shift,stats", [(2, 32, 32, 12, 0, "final"), (2, 32, 32, 12, 2, "partial"), (1, 16, 48, 6, 3, "final"),
+                                                       (3, 24, 16, 12, 5, "partial"), (5, 64, 64, 12, 2, "partial"), (1, 8, 16, 12, 0, "final")])
+def test_attn_block_is_bit_identical_to_the_qkv_gemm_plus_window_attention(B, H, W, heads, shift, stats):
+    """norm1 + qkv + window attention as ONE kernel == linear(ln=...) followed by window_attention, bit for bit (incl. the masked
+    border windows of a shifted frame), and both match the float64 composition."""
+    import torch
+    from sodt_b200 import ops
+    C, ws = 192, 8
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H + shift)
+    M = B * H * W
+    if stats == "partial":          # the residual stream as a producing GEMM leaves it: bf16 rows + partial (sum, sum of squares) pairs
+        a = torch.randn(M, C, device="cuda", generator=g).to(torch.bfloat16)
+        wp = (torch.randn(C, C, device="cuda", generator=g) / C ** 0.5).to(torch.bfloat16)
+        r = (2.0 * torch.randn(M, C, device="cuda", generator=g) + 0.7).to(torch.bfloat16)
+        x, st = ops.linear(a, wp, None, residual=r, want_stats=True)
+    else:
+        x = (1.5 * torch.randn(M, C, device="cuda", generator=g) + 0.3).to(torch.bfloat16)
+        st = ops.row_stats(x, 1e-5)
+    x = x.view(B, H, W, C)
+    wq = (torch.randn(3 * C, C, device="cuda", generator=g) / C ** 0.5).to(torch.bfloat16)
+    bq = (0.2 * torch.randn(3 * C, device="cuda", generator=g)).to(torch.bfloat16)
+    gam = (1.0 + 0.2 * torch.randn(C, device="cuda", generator=g)).to(torch.bfloat16)
+    bet = (0.1 * torch.randn(C, device="cuda", generator=g)).to(torch.bfloat16)
+    table = 0.5 * torch.randn((2 * ws - 1) ** 2, heads, device="cuda", generator=g)
+    assert ops.attn_block_supported(x, heads, ws, shift)
+    ln = (st, gam, bet, 1e-5)
+    qkv = ops.linear(x, wq, bq, ln=ln)
+    ref = ops.window_attention(qkv, table, heads, ws, shift)
+    out = ops.attn_block(x, ln, wq, bq, table, heads, ws, shift)
+    torch.cuda.synchronize()
+    assert out.shape == (B, H, W, C) and out.dtype == torch.bfloat16
+    assert torch.equal(out, ref), f"max abs diff {(out.float() - ref.float()).abs().max().item()}"
