@@ -329,10 +329,17 @@ class SwinTransformerBlock(nn.Module):
             # row statistics: up to 6 partial pairs per row (C <= 384) go to the GEMM as they are, more are reduced by a small kernel first
             prep = lambda st, eps: st if st.shape[0] <= 6 else ops.finalize_stats(st, C, eps)
             mr = prep(stats, self.norm1.eps) if stats is not None else ops.row_stats(x, self.norm1.eps)
-            qkv = ops.linear(x, attn.qkv.weight, attn.qkv.bias, ln=(mr, self.norm1.weight, self.norm1.bias, self.norm1.eps))
-            o = ops.window_attention(qkv.view(B, H, W, 3 * C), attn.relative_position_bias_table, attn.num_heads,
-                                     self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
-                                     mask_value=MASK_VALUE)
+            ln1 = (mr, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+            if (ops.USE_FUSED_ATTN and (self.shift_size == 0 or ops.FUSED_ATTN_SHIFTED)
+                    and ops.attn_block_supported(x.view(B, H, W, C), attn.num_heads, self.window_size, self.shift_size)):
+                # norm1 + qkv + window attention as one kernel: the qkv tensor never exists (bit-identical to the two kernels below)
+                o = ops.attn_block(x.view(B, H, W, C), ln1, attn.qkv.weight, attn.qkv.bias, attn.relative_position_bias_table,
+                                   attn.num_heads, self.window_size, self.shift_size, scale=attn.scale, mask_value=MASK_VALUE)
+            else:
+                qkv = ops.linear(x, attn.qkv.weight, attn.qkv.bias, ln=ln1)
+                o = ops.window_attention(qkv.view(B, H, W, 3 * C), attn.relative_position_bias_table, attn.num_heads,
+                                         self.window_size, self.shift_size, pad_qkv=attn.qkv.bias, scale=attn.scale,
+                                         mask_value=MASK_VALUE)
             x, st = ops.linear(o.view(B, L, C), attn.proj.weight, attn.proj.bias, residual=x, want_stats=True)
             if (mlp.linear and isinstance(mlp.act, nn.GELU) and mlp.act.approximate == "none"
                     and ops.mlp_ln_supported(x, mlp.fc1.weight.shape[0]) and mlp.fc2.weight.shape[0] == C):

@@ -16,11 +16,12 @@
 //   convert   the eight softmax warps read D from tensor memory, apply rstd * acc + (b' - mean * rstd * colsum) -- the folded
 //             LayerNorm, in the operation order of linear_tc's epilogue, so the values are bit-identical to the qkv tensor --
 //             and write bf16 K | Q | V operand tiles per window: exactly the stage layout window_attn_win8 loads by TMA
-//   attention softmax group g takes window g of the tile: lane-masked QK^T into S (two heads per 128 lanes), softmax with the
+//   attention per window: lane-masked QK^T into S (two heads per 128 lanes), softmax with the
 //             relative position bias and the shifted-window mask, P written IN PLACE over S (packed bf16), O = P V accumulated
 //             in the S columns the softmax has already read (tensor memory: D 192 + 2 groups x 2 head pairs x 64 = 448 columns)
 //   epilogue  O / rowsum -> bf16 -> the window's (dead) Q tile as staging -> TMA store of the un-rolled image tile
-// The K | Q | V tiles are double-buffered, so the conversion of unit u + 1 runs while the tensor core computes P V of unit u.
+// The two softmax groups own alternate units (their own K | Q | V buffer each) and run half a unit apart, so that one group's
+// softmax covers the other's conversion, MMA round trips and epilogue.
 // Warps: 0-7 softmax / convert / epilogue (two groups of four), 8-9 attention MMA issuers (one per group), 10 GEMM issuer,
 // 11 TMA producer (x tiles, W ring).
 #include "common.cuh"
@@ -49,6 +50,15 @@ constexpr int TAB_ROW = 16, TAB_HEAD = (2 * WS - 1) * TAB_ROW, TAB_COPIES = 2;  
 __host__ __device__ constexpr int tab_copy_stride(int heads) { return ((heads * TAB_HEAD * 4 + 95) / 128 * 128 + 32) / 4; }
 constexpr uint32_t TM_D = 0, TM_S = 192;                     // tensor memory: D [0, 192); group g, head pair pr: S / P / O at 192 + g * 128 + pr * 64
 constexpr uint32_t ALL = 0xFFFFFFFFu;
+
+// ATTN_TRACE (experiments only, tools/trace_attn_block.py): CTA 0 records clock64 at the hand-offs of its first 64 units
+#ifdef ATTN_TRACE
+__device__ long long g_attn_trace[6][64][16];
+__device__ long long g_cta_cycles[256][2];
+#define ATRACE(role, idx, ev) do { if (blockIdx.x == 0 && (idx) < 64) g_attn_trace[role][idx][ev] = clock64(); } while (0)
+#else
+#define ATRACE(role, idx, ev) do { } while (0)
+#endif
 
 struct Geo {
     int H, W, nww, nwh, nW, shift;
@@ -136,22 +146,25 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
     constexpr int HPB = G / 2;                // head pairs per unit
     constexpr uint32_t O_OFF = HD == 16 ? 32 : 64;    // O of a pair: the high half of its S columns (2 x 16) or the group's second 64 columns (2 x 32)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t x_full, x_empty, w_full[WSTAGES], w_empty[WSTAGES], d_full, d_free, tiles_ready[2], s_full[NG], s_free[NG], p_full[NG], pv_done[NG];
+    __shared__ uint64_t x_full, x_empty, w_full[WSTAGES], w_empty[WSTAGES], d_full[NG], d_free, qk_ready[NG], v_ready[NG], s_full[NG][2], s_free[NG], p_full[NG][2], pv_done[NG];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     float* tab = reinterpret_cast<float*>(smem_raw + (sbase - smem_u32(smem_raw)) + OFF_TAB);
+    float* lnp = tab + TAB_COPIES * tab_copy_stride(p.heads);      // [3C] folded bias, [3C] column sums: read by every conversion
     const int heads = p.heads, C = p.C;
     int my_tiles = 0;
     if ((long long)blockIdx.x < geo.total_tiles) my_tiles = (int)((geo.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     const int n_units = my_tiles * KB;        // unit u = (tile u / 3, head group u % 3)
 
     if (tid == 0) {
-        mbar_init(&x_full, 1); mbar_init(&x_empty, 1); mbar_init(&d_full, 1); mbar_init(&d_free, NG * SM_WARPS);
+        mbar_init(&x_full, 1); mbar_init(&x_empty, 1); mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1); mbar_init(&d_free, SM_WARPS);
         for (int s = 0; s < WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-        for (int b = 0; b < 2; ++b) mbar_init(&tiles_ready[b], NG * SM_WARPS);
-        for (int g = 0; g < NG; ++g) { mbar_init(&s_full[g], 1); mbar_init(&s_free[g], ROWS); mbar_init(&p_full[g], ROWS); mbar_init(&pv_done[g], 1); }
+        for (int g = 0; g < NG; ++g) {
+            mbar_init(&qk_ready[g], SM_WARPS); mbar_init(&v_ready[g], SM_WARPS); mbar_init(&s_free[g], ROWS); mbar_init(&pv_done[g], 1);
+            for (int pr = 0; pr < 2; ++pr) { mbar_init(&s_full[g][pr], 1); mbar_init(&p_full[g][pr], ROWS); }
+        }
         fence_barrier_init();
     }
     if (warp == MMA_WARP0) { tmem_alloc(&tmem_slot, 512); tmem_relinquish(); }
@@ -162,11 +175,15 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         const float4* src = reinterpret_cast<const float4*>(p.table);
         float4* dst = reinterpret_cast<float4*>(tab);
         for (int e = tid; e < n4; e += NTHREADS) dst[e] = src[e];
+        for (int e = tid; e < 3 * p.C; e += NTHREADS) { lnp[e] = p.bias[e]; lnp[3 * p.C + e] = p.colsum[e]; }
     }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tm = tmem_slot;
+#ifdef ATTN_TRACE
+    const long long cta_t0 = clock64();
+#endif
 
     if (warp == TMA_WARP) {
         // ======================================================= producer: x tile of every window pair, W ring of every unit
@@ -176,12 +193,14 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
             if (lane == 0) {
                 if (t > 0) mbar_wait(&x_empty, (uint32_t)((t - 1) & 1));
+                ATRACE(5, t, 0);
                 tma::expect_tx(&x_full, X_BYTES);
             }
             __syncwarp();
             load_window(in_maps, geo, win_box(geo, 2 * tile), sbase + OFF_X, &x_full, lane);
             load_window(in_maps, geo, win_box(geo, 2 * tile + 1), sbase + OFF_X + WIN_BYTES, &x_full, lane);
             if (lane == 0) {
+                ATRACE(5, t, 1);
                 for (int cg = 0; cg < KB; ++cg) {
                     for (int kb = 0; kb < KB; ++kb, ++kbc) {
                         const int s = kbc % WSTAGES;
@@ -202,65 +221,81 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             constexpr uint32_t idesc = idesc_bf16(ROWS, 192, false, false);
             int kbc = 0;
             for (int t = 0; t < my_tiles; ++t) {
+                ATRACE(0, t * KB, 6);
                 mbar_wait(&x_full, (uint32_t)(t & 1));
+                ATRACE(0, t * KB, 7);
                 for (int cg = 0; cg < KB; ++cg) {
                     const int u = t * KB + cg;
+                    ATRACE(0, u, 0);
                     if (u > 0) mbar_wait(&d_free, (uint32_t)((u - 1) & 1));
+                    ATRACE(0, u, 1);
                     fence_after_sync();
                     for (int kb = 0; kb < KB; ++kb, ++kbc) {
                         const int s = kbc % WSTAGES;
                         mbar_wait(&w_full[s], (uint32_t)((kbc / WSTAGES) & 1));
+                        ATRACE(0, u, 2 + kb);
                         fence_after_sync();
                         const uint64_t da = tma::desc_sw128(sbase + OFF_X + kb * XKB_BYTES), db = tma::desc_sw128(sbase + OFF_W + s * WST_BYTES);
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) mma_ss(tm + TM_D, da + 2 * ks, db + 2 * ks, idesc, (kb | ks) != 0);
                         mma_commit(&w_empty[s]);
                     }
-                    mma_commit(&d_full);
+                    ATRACE(0, u, 5);
+                    mma_commit(&d_full[u & 1]);                     // one barrier per softmax group: a waiter is never two phases behind
                     if (cg == KB - 1) mma_commit(&x_empty);
                 }
             }
         }
     } else if (warp >= MMA_WARP0) {
-        // ======================================================= attention MMA issuers: group g = window g of every tile
+        // ======================================================= attention MMA issuers: group g takes the units g, g + 2, ...
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc_bf16(ROWS, NTOK, false, false);
             constexpr uint32_t idesc_o = idesc_bf16(ROWS, 2 * HD, false, true);
             const int g = warp - MMA_WARP0;
             const uint64_t d0 = tma::desc_sw128(sbase + OFF_QKV);
             const uint32_t tS = tm + TM_S + g * 128;
-            for (int u = 0; u < n_units; ++u) {
-                const int buf = u & 1;
-                const uint32_t stage = (uint32_t)((buf * NG + g) * STAGE_BYTES);
-                mbar_wait_spin(&tiles_ready[buf], (uint32_t)((u >> 1) & 1));
-                if (u > 0) mbar_wait_spin(&s_free[g], (uint32_t)((u - 1) & 1));
-                fence_after_sync();
+            int k = 0;                                              // windows this group has processed
+            for (int u = g, j = 0; u < n_units; u += NG, ++j) {
+#pragma unroll 1
+                for (int w = 0; w < 2; ++w, ++k) {                  // the two windows of the unit, one after the other
+                    const uint32_t stage = (uint32_t)((g * 2 + w) * STAGE_BYTES);
+                    if (w == 0) mbar_wait_spin(&qk_ready[g], (uint32_t)(j & 1));      // K and Q tiles of both windows are written (V follows)
+                    if (k > 0) mbar_wait_spin(&s_free[g], (uint32_t)((k - 1) & 1));
+                    ATRACE(1 + g, k, 0);
+                    fence_after_sync();
 #pragma unroll
-                for (int pr = 0; pr < HPB; ++pr) {            // see window_attn_win8.cu: both heads of a pair read the same Q tile
-                    const uint32_t off = (stage + pr * (2 * HD * 2)) >> 4;
-                    const uint64_t qd = d0 + off + (OFF_Q >> 4), kd = d0 + off + (OFF_K >> 4);
-                    const uint64_t qd_odd = qd - (WIN_BYTES >> 4) + ((HD * 2) >> 4), kd_odd = kd + ((HD * 2) >> 4);
+                    for (int pr = 0; pr < HPB; ++pr) {          // see window_attn_win8.cu: both heads of a pair read the same Q tile
+                        const uint32_t off = (stage + pr * (2 * HD * 2)) >> 4;
+                        const uint64_t qd = d0 + off + (OFF_Q >> 4), kd = d0 + off + (OFF_K >> 4);
+                        const uint64_t qd_odd = qd - (WIN_BYTES >> 4) + ((HD * 2) >> 4), kd_odd = kd + ((HD * 2) >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd + 2 * ks, kd + 2 * ks, idesc_s, ks > 0, 0u, 0u, ALL, ALL);
+                        for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd + 2 * ks, kd + 2 * ks, idesc_s, ks > 0, 0u, 0u, ALL, ALL);
 #pragma unroll
-                    for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd_odd + 2 * ks, kd_odd + 2 * ks, idesc_s, ks > 0, ALL, ALL, 0u, 0u);
-                }
-                mma_commit(&s_full[g]);
-                mbar_wait_spin(&p_full[g], (uint32_t)(u & 1));
-                fence_after_sync();
-#pragma unroll
-                for (int ks = 0; ks < NTOK / 16; ++ks) {      // O[128 x 2hd] = P [V_even | V_odd]: P in the low 32 columns of the pair's S, O in the high 32
-#pragma unroll
-                    for (int pr = 0; pr < HPB; ++pr) {
-                        const uint64_t vd = d0 + ((stage + OFF_V + pr * (2 * HD * 2)) >> 4);
-                        mma_ts(tS + pr * 64 + O_OFF, tS + pr * 64 + ks * 8, vd + ks * (2048 >> 4), idesc_o, ks > 0);
+                        for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd_odd + 2 * ks, kd_odd + 2 * ks, idesc_s, ks > 0, ALL, ALL, 0u, 0u);
+                        mma_commit(&s_full[g][pr]);             // per head pair: the softmax of pair 0 starts while pair 1's scores are computed
                     }
+                    ATRACE(1 + g, k, 1);
+                    if (w == 0) mbar_wait_spin(&v_ready[g], (uint32_t)(j & 1));
+#pragma unroll
+                    for (int pr = 0; pr < HPB; ++pr) {          // O[128 x 2hd] = P [V_even | V_odd]: P in the low 32 columns of the pair's S;
+                        mbar_wait_spin(&p_full[g][pr], (uint32_t)(k & 1));      // pair 0's P V runs during the softmax of pair 1
+                        if (pr == 0) ATRACE(1 + g, k, 2);
+                        fence_after_sync();
+                        const uint64_t vd = d0 + ((stage + OFF_V + pr * (2 * HD * 2)) >> 4);
+#pragma unroll
+                        for (int ks = 0; ks < NTOK / 16; ++ks)
+                            mma_ts(tS + pr * 64 + O_OFF, tS + pr * 64 + ks * 8, vd + ks * (2048 >> 4), idesc_o, ks > 0);
+                    }
+                    mma_commit(&pv_done[g]);
+                    ATRACE(1 + g, k, 3);
                 }
-                mma_commit(&pv_done[g]);
             }
         }
     } else {
-        // ======================================================= softmax groups: convert D -> K | Q | V tiles, softmax, epilogue
+        // ======================================================= softmax groups: group g owns the units g, g + 2, ... : it converts
+        // D into the K | Q | V tiles of both windows (buffer g) and then runs the attention of the two windows one after the
+        // other.  The groups work on different units, half a unit apart: one group's softmax covers the other's conversion,
+        // MMA round trips and epilogue (the D hand-off alternates between them).
         const int g = warp / SM_WARPS, quarter = warp & 3;
         const int row = quarter * 32 + lane;                       // TMEM lane: D row = token of the pair; S row = 64 * head parity + token
         const int hp = row >> 6, ti = row & 63, ty = ti >> 3, tx = ti & 7;
@@ -276,9 +311,6 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         const uint64_t xhi = s_ > 0 ? 0x0101010101010101ull * (uint64_t)((0xFFu << (WS - s_)) & 0xFFu) : 0ull;
         const uint32_t srow = (uint32_t)ti * 128, sw = (uint32_t)(ti & 7);
         const bool storer = quarter == 0;                          // warp 0 of the group issues the group's TMA stores
-        uint64_t mbits = 0;
-        bool any_mask = false;
-        WinBox my_box{};                                            // the group's window of the current attention tile
 
         // (mean, rstd) of D row `row` of tile t: the token's row in the un-rolled [B*H*W] image
         auto load_mr = [&](int t) {
@@ -306,173 +338,196 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             return r;
         };
         float2 mr_cur = make_float2(0.f, 1.f), mr_next = load_mr(0);
+        int cur_t = -1, next_t = 0;
+        int k = 0;                                                  // windows this group has processed
 
-        // D of unit u -> bf16 K | Q | V tiles of both windows in buffer u % 2 (this group: D columns [96 g, 96 g + 96))
-        auto convert = [&](int u) {
-            const int cg = u % KB, buf = u & 1;
-            if (cg == 0) { mr_cur = mr_next; mr_next = load_mr(u / KB + 1); }
-            mbar_wait(&d_full, (uint32_t)(u & 1));
+        for (int u = g; u < n_units; u += NG) {
+            const int t = u / KB, cg = u - t * KB;
+            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+            // ---------------------------------------------------------------- D of unit u -> bf16 K | Q | V tiles of both windows
+            if (t != cur_t) { mr_cur = mr_next; cur_t = t; }
+            {
+                const int nt = (u + NG) / KB;                       // the tile of the group's next unit: its statistics one unit ahead
+                if (nt != next_t) { mr_next = load_mr(nt); next_t = nt; }
+            }
+            if (tid == g * 128) ATRACE(3 + g, u >> 1, 0);
+            mbar_wait(&d_full[g], (uint32_t)((u >> 1) & 1));
+            if (tid == g * 128) ATRACE(3 + g, u >> 1, 1);
             fence_after_sync();
-            if (u >= 2) {
-                // buffer u % 2 was read by unit u - 2: its P V (waited for in that unit's epilogue) and its output stores
+            if (u >= NG) {
+                // buffer g was read by the group's previous unit: its P V (waited for in its epilogues) and its output stores
                 if (storer) tma::store_wait_read<0>();
-                asm volatile("bar.sync 4, 256;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
             }
-            const float rstd = mr_cur.y, nmr = -mr_cur.x * mr_cur.y;
-            const uint64_t rstd2 = pack2(rstd, rstd), nmr2 = pack2(nmr, nmr);
-            const uint32_t wbase = sbase + OFF_QKV + (uint32_t)((buf * NG + hp) * STAGE_BYTES) + srow;
+            {
+                const float rstd = mr_cur.y, nmr = -mr_cur.x * mr_cur.y;
+                const uint64_t rstd2 = pack2(rstd, rstd), nmr2 = pack2(nmr, nmr);
+                const uint32_t wbase = sbase + OFF_QKV + (uint32_t)((g * 2 + hp) * STAGE_BYTES) + srow;
+                const float* lb = lnp + cg * 64;                        // bias / colsum of D column c: lb[(c / 64) * C + c % 64] (+ 3C)
+                uint32_t ra[32], rb[32];
+                tmem_ld32(tD, ra);
 #pragma unroll
-            for (int ch = 0; ch < 6; ++ch) {
-                const int c0 = g * 96 + ch * 16, part = c0 >> 6, cw = c0 & 63;
-                uint32_t ra[16];
-                tmem_ld16(tD + c0, ra);
-                tmem_wait_ld();
-                if (ch == 5) {                                          // D is in registers: the next unit's GEMM may overwrite it
-                    fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&d_free);
-                }
-                const int n0 = part * C + cg * 64 + cw;
-                const uint32_t tile_off = part == 0 ? OFF_Q : part == 1 ? OFF_K : OFF_V;
-#pragma unroll
-                for (int j = 0; j < 16; j += 8) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j + 4));
-                    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.colsum + n0 + j)), s1 = __ldg(reinterpret_cast<const float4*>(p.colsum + n0 + j + 4));
-                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w}, cs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                    float v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; e += 2)          // rstd acc + (bias - mean rstd colsum): the arithmetic of linear_tc's epilogue
-                        unpack2(ffma2(rstd2, pack2(__uint_as_float(ra[j + e]), __uint_as_float(ra[j + e + 1])),
-                                      ffma2(nmr2, pack2(cs[e], cs[e + 1]), pack2(bb[e], bb[e + 1]))), v[e], v[e + 1]);
-                    const uint32_t chunk = (uint32_t)((cw + j) >> 3) ^ sw;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wbase + tile_off + (chunk << 4)), "r"(pack_bf16(v[0], v[1])),
-                                 "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
-                }
-            }
-            fence_proxy_async();                                        // generic-proxy writes -> visible to the tensor core
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tiles_ready[buf]);
-        };
-
-        float row_sum[HPB] = {};
-        if (n_units > 0) convert(0);
-        for (int u = 0; u < n_units; ++u) {
-            const int t = u / KB, cg = u - t * KB, buf = u & 1, par = u & 1;
-            if (cg == 0) {                                          // new tile: this group's window and its mask bits
-                const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
-                my_box = win_box(geo, 2 * tile + g);
-                uint64_t mb = 0;
-                if (s_ > 0) {
-                    if (my_box.last_row) mb |= (ty >= WS - s_) ? ~yhi : yhi;
-                    if (my_box.last_col) mb |= (tx >= WS - s_) ? ~xhi : xhi;
-                }
-                mbits = mb;
-                any_mask = s_ > 0 && (my_box.last_row || my_box.last_col);
-            }
-            // ---------------------------------------------------------------- softmax of unit u (window g, head group cg)
-            mbar_wait(&s_full[g], (uint32_t)par);
-            fence_after_sync();
-#pragma unroll
-            for (int pr = 0; pr < HPB; ++pr) {
-                const int h = cg * G + 2 * pr + hp;
-                uint64_t tt[NTOK / 2];
-                uint32_t pk[NTOK / 2];
-#pragma unroll
-                for (int part = 0; part < 2; ++part) {
-                    uint32_t ra[32];
-                    tmem_ld32(tS + pr * 64 + part * 32, ra);
+                for (int ch = 0; ch < 6; ++ch) {                        // 32 columns per step, the next step's load in flight
                     tmem_wait_ld();
-                    const float* tb = tab_row + h * TAB_HEAD - part * 4 * TAB_ROW;
+                    if (ch + 1 < 6) { if (ch & 1) tmem_ld32(tD + (ch + 1) * 32, ra); else tmem_ld32(tD + (ch + 1) * 32, rb); }
+                    if (ch == 5) {                                      // D is in registers: the next unit's GEMM may overwrite it
+                        fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&d_free);
+                    }
+                    const int c0 = ch * 32, part = c0 >> 6, cw = c0 & 63;
+                    const float* lc = lb + part * C + cw;
+                    const uint32_t tile_off = part == 0 ? OFF_Q : part == 1 ? OFF_K : OFF_V;
 #pragma unroll
-                    for (int yj = 0; yj < 4; ++yj) {
+                    for (int j = 0; j < 32; j += 8) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(lc + j), b1 = *reinterpret_cast<const float4*>(lc + j + 4);
+                        const float4 s0 = *reinterpret_cast<const float4*>(lc + 3 * C + j), s1 = *reinterpret_cast<const float4*>(lc + 3 * C + j + 4);
+                        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w}, cs[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        float v[8];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
-                            tt[part * 16 + yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
+                        for (int e = 0; e < 8; e += 2) {        // rstd acc + (bias - mean rstd colsum): the arithmetic of linear_tc's epilogue
+                            const uint32_t a0 = (ch & 1) ? rb[j + e] : ra[j + e], a1 = (ch & 1) ? rb[j + e + 1] : ra[j + e + 1];
+                            unpack2(ffma2(rstd2, pack2(__uint_as_float(a0), __uint_as_float(a1)),
+                                          ffma2(nmr2, pack2(cs[e], cs[e + 1]), pack2(bb[e], bb[e + 1]))), v[e], v[e + 1]);
                         }
+                        const uint32_t chunk = (uint32_t)((cw + j) >> 3) ^ sw;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wbase + tile_off + (chunk << 4)), "r"(pack_bf16(v[0], v[1])),
+                                     "r"(pack_bf16(v[2], v[3])), "r"(pack_bf16(v[4], v[5])), "r"(pack_bf16(v[6], v[7])) : "memory");
+                    }
+                    if (ch == 3) {                                      // Q and K of both windows are written: the scores may be issued
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&qk_ready[g]);
+                    }
+                    if (ch == 5) {
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&v_ready[g]);
                     }
                 }
-                if (any_mask) {
+                if (tid == g * 128) ATRACE(3 + g, u >> 1, 2);
+            }
+            // ---------------------------------------------------------------- attention of the unit's two windows
+#pragma unroll 1
+            for (int w = 0; w < 2; ++w, ++k) {
+                const WinBox my_box = win_box(geo, 2 * tile + w);
+                uint64_t mbits = 0;
+                if (s_ > 0) {
+                    if (my_box.last_row) mbits |= (ty >= WS - s_) ? ~yhi : yhi;
+                    if (my_box.last_col) mbits |= (tx >= WS - s_) ? ~xhi : xhi;
+                }
+                const bool any_mask = s_ > 0 && (my_box.last_row || my_box.last_col);
+                const uint32_t par = (uint32_t)(k & 1);
+                float row_sum[HPB];
+#pragma unroll
+                for (int pr = 0; pr < HPB; ++pr) {
+                    mbar_wait(&s_full[g][pr], par);
+                    if (pr == 0 && tid == g * 128) ATRACE(3 + g, u >> 1, 3 + 4 * w);
+                    fence_after_sync();
+                    const int h = cg * G + 2 * pr + hp;
+                    uint64_t tt[NTOK / 2];
+                    uint32_t pk[NTOK / 2];
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        uint32_t ra[32];
+                        tmem_ld32(tS + pr * 64 + part * 32, ra);
+                        tmem_wait_ld();
+                        const float* tb = tab_row + h * TAB_HEAD - part * 4 * TAB_ROW;
+#pragma unroll
+                        for (int yj = 0; yj < 4; ++yj) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
+                                tt[part * 16 + yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
+                            }
+                        }
+                    }
+                    if (any_mask) {
+#pragma unroll
+                        for (int j = 0; j < NTOK / 2; ++j) {
+                            float lo, hi;
+                            unpack2(tt[j], lo, hi);
+                            if ((mbits >> (2 * j)) & 1ull) lo += mv2;
+                            if ((mbits >> (2 * j + 1)) & 1ull) hi += mv2;
+                            tt[j] = pack2(lo, hi);
+                        }
+                    }
+                    float m4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float lo, hi;
+                        unpack2(tt[q], lo, hi);
+                        m4[q] = fmaxf(lo, hi);
+                    }
+#pragma unroll
+                    for (int j = 4; j < NTOK / 2; ++j) {
+                        float lo, hi;
+                        unpack2(tt[j], lo, hi);
+                        m4[j & 3] = fmax3(m4[j & 3], lo, hi);
+                    }
+                    const float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+                    const uint64_t nmx2 = pack2(-mx, -mx);
+                    uint64_t sum2 = 0ull;
 #pragma unroll
                     for (int j = 0; j < NTOK / 2; ++j) {
                         float lo, hi;
-                        unpack2(tt[j], lo, hi);
-                        if ((mbits >> (2 * j)) & 1ull) lo += mv2;
-                        if ((mbits >> (2 * j + 1)) & 1ull) hi += mv2;
-                        tt[j] = pack2(lo, hi);
+                        unpack2(fadd2(tt[j], nmx2), lo, hi);
+                        const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
+                        sum2 = fadd2(sum2, pack2(p0, p1));
+                        pk[j] = pack_bf16(p0, p1);
+                    }
+                    float a, b;
+                    unpack2(sum2, a, b);
+                    row_sum[pr] = a + b;
+                    tmem_st(tS + pr * 64, pk);                  // P in place: this lane's scores of the pair are all in registers
+                    tmem_wait_st();
+                    fence_before_sync();
+                    mbar_arrive(&p_full[g][pr]);                // the pair's P V starts while the next pair's softmax runs
+                }
+                if (tid == g * 128) ATRACE(3 + g, u >> 1, 4 + 4 * w);
+                // -------------------------------------------------------------- epilogue of the window
+                mbar_wait(&pv_done[g], par);
+                if (tid == g * 128) ATRACE(3 + g, u >> 1, 5 + 4 * w);
+                fence_after_sync();
+                uint32_t o[HPB][HD];
+#pragma unroll
+                for (int pr = 0; pr < HPB; ++pr) {
+                    if constexpr (HD == 16) tmem_ld16(tS + pr * 64 + O_OFF + hp * HD, o[pr]);
+                    else tmem_ld32(tS + pr * 64 + O_OFF + hp * HD, o[pr]);
+                }
+                tmem_wait_ld();
+                fence_before_sync();
+                mbar_arrive(&s_free[g]);                        // S / P / O columns of the group are free: the next scores may be issued
+                const uint32_t tile_s = sbase + OFF_QKV + (uint32_t)((g * 2 + w) * STAGE_BYTES) + OFF_Q;      // the window's Q tile is dead: staging
+#pragma unroll
+                for (int pr = 0; pr < HPB; ++pr) {
+                    const float inv = fast_rcp(row_sum[pr]);
+#pragma unroll
+                    for (int j = 0; j < HD; j += 8) {
+                        const uint32_t chunk = (uint32_t)(((2 * pr + hp) * HD + j) >> 3) ^ sw;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
+                                     "r"(pack_bf16(__uint_as_float(o[pr][j]) * inv, __uint_as_float(o[pr][j + 1]) * inv)),
+                                     "r"(pack_bf16(__uint_as_float(o[pr][j + 2]) * inv, __uint_as_float(o[pr][j + 3]) * inv)),
+                                     "r"(pack_bf16(__uint_as_float(o[pr][j + 4]) * inv, __uint_as_float(o[pr][j + 5]) * inv)),
+                                     "r"(pack_bf16(__uint_as_float(o[pr][j + 6]) * inv, __uint_as_float(o[pr][j + 7]) * inv)) : "memory");
                     }
                 }
-                float m4[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float lo, hi;
-                    unpack2(tt[q], lo, hi);
-                    m4[q] = fmaxf(lo, hi);
+                fence_proxy_async();
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");      // the window's tile is complete
+                if (storer) {
+                    store_tile(out_maps, geo, my_box, tile_s, cg * 64, lane);
+                    tma::store_commit();
                 }
-#pragma unroll
-                for (int j = 4; j < NTOK / 2; ++j) {
-                    float lo, hi;
-                    unpack2(tt[j], lo, hi);
-                    m4[j & 3] = fmax3(m4[j & 3], lo, hi);
-                }
-                const float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
-                const uint64_t nmx2 = pack2(-mx, -mx);
-                uint64_t sum2 = 0ull;
-#pragma unroll
-                for (int j = 0; j < NTOK / 2; ++j) {
-                    float lo, hi;
-                    unpack2(fadd2(tt[j], nmx2), lo, hi);
-                    const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
-                    sum2 = fadd2(sum2, pack2(p0, p1));
-                    pk[j] = pack_bf16(p0, p1);
-                }
-                float a, b;
-                unpack2(sum2, a, b);
-                row_sum[pr] = a + b;
-                tmem_st(tS + pr * 64, pk);                      // P in place: this lane's scores of the pair are all in registers
-            }
-            tmem_wait_st();
-            fence_before_sync();
-            mbar_arrive(&p_full[g]);
-            // ---------------------------------------------------------------- conversion of the next unit while P V runs
-            if (u + 1 < n_units) convert(u + 1);
-            // ---------------------------------------------------------------- epilogue of unit u
-            mbar_wait(&pv_done[g], (uint32_t)par);
-            fence_after_sync();
-            uint32_t o[HPB][HD];
-#pragma unroll
-            for (int pr = 0; pr < HPB; ++pr) {
-                if constexpr (HD == 16) tmem_ld16(tS + pr * 64 + O_OFF + hp * HD, o[pr]);
-                else tmem_ld32(tS + pr * 64 + O_OFF + hp * HD, o[pr]);
-            }
-            tmem_wait_ld();
-            fence_before_sync();
-            mbar_arrive(&s_free[g]);                            // S / P / O columns of the group are free: the next scores may be issued
-            const uint32_t tile_s = sbase + OFF_QKV + (uint32_t)((buf * NG + g) * STAGE_BYTES) + OFF_Q;      // the window's Q tile is dead: staging
-#pragma unroll
-            for (int pr = 0; pr < HPB; ++pr) {
-                const float inv = fast_rcp(row_sum[pr]);
-#pragma unroll
-                for (int j = 0; j < HD; j += 8) {
-                    const uint32_t chunk = (uint32_t)(((2 * pr + hp) * HD + j) >> 3) ^ sw;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
-                                 "r"(pack_bf16(__uint_as_float(o[pr][j]) * inv, __uint_as_float(o[pr][j + 1]) * inv)),
-                                 "r"(pack_bf16(__uint_as_float(o[pr][j + 2]) * inv, __uint_as_float(o[pr][j + 3]) * inv)),
-                                 "r"(pack_bf16(__uint_as_float(o[pr][j + 4]) * inv, __uint_as_float(o[pr][j + 5]) * inv)),
-                                 "r"(pack_bf16(__uint_as_float(o[pr][j + 6]) * inv, __uint_as_float(o[pr][j + 7]) * inv)) : "memory");
-                }
-            }
-            fence_proxy_async();
-            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");      // the group's tile is complete
-            if (storer) {
-                store_tile(out_maps, geo, my_box, tile_s, cg * 64, lane);
-                tma::store_commit();
+                if (tid == g * 128) ATRACE(3 + g, u >> 1, 6 + 4 * w);
             }
         }
         if (storer) tma::store_wait_all();
     }
     fence_before_sync();
     __syncthreads();
+#ifdef ATTN_TRACE
+    if (tid == 0 && blockIdx.x < 256) { g_cta_cycles[blockIdx.x][0] = clock64() - cta_t0; g_cta_cycles[blockIdx.x][1] = my_tiles; }
+#endif
     if (warp == MMA_WARP0) tmem_dealloc(tmem_slot, 512);
 }
 
@@ -485,9 +540,18 @@ bool make_maps(Maps* m, const void* base, int B, int H, int W, int Cfull, int sh
            tma::make_map_bf16(&m->row_a, base, 3, dims, strides, ba, promo) && tma::make_map_bf16(&m->row_b, base, 3, dims, strides, bb, promo);
 }
 
-size_t smem_bytes(int heads) { return (size_t)OFF_TAB + (size_t)TAB_COPIES * tab_copy_stride(heads) * sizeof(float) + 1024; }
+size_t smem_bytes(int heads) { return (size_t)OFF_TAB + (size_t)TAB_COPIES * tab_copy_stride(heads) * sizeof(float) + 2 * 3 * KB * 64 * sizeof(float) + 1024; }
 
 }  // namespace
+
+#ifdef ATTN_TRACE
+extern "C" int sodt_attn_cta_cycles(void* host, size_t bytes) {
+    return cudaMemcpyFromSymbol(host, g_cta_cycles, bytes < sizeof(g_cta_cycles) ? bytes : sizeof(g_cta_cycles)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int sodt_attn_trace(void* host, size_t bytes) {
+    return cudaMemcpyFromSymbol(host, g_attn_trace, bytes < sizeof(g_attn_trace) ? bytes : sizeof(g_attn_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 bool attn_block_supported(int H, int W, int C, int heads, int ws, int shift) {
     if (ws != WS || C != KB * 64 || heads <= 0 || C % heads || H % WS || W % (2 * WS) || shift < 0 || shift >= WS) return false;

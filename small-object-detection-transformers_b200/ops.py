@@ -582,12 +582,17 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
     return y
 
 
-USE_FUSED_ATTN = True   # norm1 + qkv Linear + window attention of the C = 192 Swin blocks as one kernel (no qkv tensor)
+# norm1 + qkv Linear + window attention of the C = 192 Swin blocks as one kernel (no qkv tensor).  Bit-identical to the two kernels
+# and 8 % faster than them on an idle GPU (1.38 vs 1.50 ms, shift 0), but inside the power-capped step (SM clock ~1.6 GHz) the
+# latency-bound fused kernel slows down with the clock (1.66 ms) while the memory-bound qkv GEMM does not (0.71 + 0.88 ms), so the
+# model keeps the two kernels by default; ``attn_block`` / sodt_attn_block_fwd stay available (and tested) as an op.
+USE_FUSED_ATTN = False
+FUSED_ATTN_SHIFTED = False   # also for the shifted blocks (1.66-1.78 vs 1.51 ms on an idle GPU)
 
 
 def attn_block_supported(x, heads, ws, shift):
     """True if ``attn_block`` covers ``x`` [B, H, W, C] (bf16, C = 192, 8 x 8 windows, head_dim 16 / 32)."""
-    if not (USE_FUSED_ATTN and USE_LN_FOLD and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
+    if not (USE_LN_FOLD and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4):
         return False
     B, H, W, C = x.shape
     return bool(_capi.lib().sodt_attn_block_supported(B, H, W, C, heads, ws, shift, 1))

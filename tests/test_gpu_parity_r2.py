@@ -512,3 +512,28 @@ def test_attn_block_is_bit_identical_to_the_qkv_gemm_plus_window_attention(B, H,
     torch.cuda.synchronize()
     assert out.shape == (B, H, W, C) and out.dtype == torch.bfloat16
     assert torch.equal(out, ref), f"max abs diff {(out.float() - ref.float()).abs().max().item()}"
+
+
+@pytest.mark.gpu
+def test_swin_block_with_the_fused_attention_half_is_bit_identical():
+    """SwinTransformerBlock with ops.USE_FUSED_ATTN (norm1 + qkv + attention as one kernel) == the default three-kernel attention half."""
+    import torch
+    from sodt_b200 import ops
+    from sodt_b200.basics.models.backbone_vit import SwinTransformerBlock
+    torch.manual_seed(3)
+    for shift in (0, 2):
+        blk = SwinTransformerBlock(192, (32, 48), 12, window_size=8, shift_size=shift).cuda().to(torch.bfloat16).eval()
+        x = torch.randn(2, 32 * 48, 192, device="cuda").to(torch.bfloat16)
+        old = (ops.USE_FUSED_ATTN, ops.FUSED_ATTN_SHIFTED)
+        try:
+            with torch.no_grad():
+                ops.USE_FUSED_ATTN, ops.FUSED_ATTN_SHIFTED = False, False
+                ref = blk(x)
+                ops.USE_FUSED_ATTN, ops.FUSED_ATTN_SHIFTED = True, True
+                ops.reset_launch_count()
+                out = blk(x)
+                n_fused = ops.launch_count()
+        finally:
+            ops.USE_FUSED_ATTN, ops.FUSED_ATTN_SHIFTED = old
+        assert torch.equal(out, ref)
+        assert n_fused >= 1
