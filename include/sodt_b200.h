@@ -289,7 +289,7 @@ int sodt_linear_ln_fwd(const void* x, int ldx, const float* ln_mean_rstd, int ln
  * diag(ln_weight) in bf16 [3C, C], ln_colsum its fp32 row sums, b_qkv = qkv.bias + qkv.weight . ln_bias; ln_mean_rstd / ln_boxes
  * as there, indexed by the token's row in [B*H*W]).  The [B, H, W, 3C] qkv tensor never exists; the result is bit-identical to
  * sodt_linear_ln_fwd followed by sodt_window_attn_fwd_prepared.  `workspace` = the bias-table image sodt_window_attn_prepare
- * wrote for the same (C, heads, ws = 8).  8 x 8 windows, C = 192 with head_dim 16 or 32, H % 8 == 0, W % 16 == 0, 0 <= shift < 8,
+ * wrote for the same (C, heads, ws = 8).  8 x 8 windows, C = 192 with head_dim 16 (12 heads), H % 8 == 0, W % 16 == 0, 0 <= shift < 8,
  * bf16 only; proj + residual remain sodt_linear_ln_fwd.
  */
 int sodt_attn_block_supported(int B, int H, int W, int C, int heads, int ws, int shift, int dtype);

@@ -143,10 +143,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ Maps out_maps, const __grid_constant__ CUtensorMap w_map,
                   const Params p, const Geo geo) {
     constexpr int G = 64 / HD;                // heads per 64-channel group
-    constexpr int HPB = G / 2;                // head pairs per unit
     constexpr uint32_t O_OFF = HD == 16 ? 32 : 64;    // O of a pair: the high half of its S columns (2 x 16) or the group's second 64 columns (2 x 32)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ uint64_t x_full, x_empty, w_full[WSTAGES], w_empty[WSTAGES], d_full[NG], d_free, qk_ready[NG], v_ready[NG], s_full[NG][2], s_free[NG], p_full[NG][2], pv_done[NG];
+    __shared__ uint64_t x_full, x_empty, w_full[WSTAGES], w_empty[WSTAGES], d_full[NG], d_free, qk_ready[NG], v_ready[NG], s_full[NG][2], s_free[NG][2], p_full[NG][2], pv_done[NG][2];
     __shared__ uint32_t tmem_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -162,8 +161,8 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         mbar_init(&x_full, 1); mbar_init(&x_empty, 1); mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1); mbar_init(&d_free, SM_WARPS);
         for (int s = 0; s < WSTAGES; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
         for (int g = 0; g < NG; ++g) {
-            mbar_init(&qk_ready[g], SM_WARPS); mbar_init(&v_ready[g], SM_WARPS); mbar_init(&s_free[g], ROWS); mbar_init(&pv_done[g], 1);
-            for (int pr = 0; pr < 2; ++pr) { mbar_init(&s_full[g][pr], 1); mbar_init(&p_full[g][pr], ROWS); }
+            mbar_init(&qk_ready[g], SM_WARPS); mbar_init(&v_ready[g], SM_WARPS);
+            for (int pr = 0; pr < 2; ++pr) { mbar_init(&s_full[g][pr], 1); mbar_init(&p_full[g][pr], ROWS); mbar_init(&s_free[g][pr], ROWS); mbar_init(&pv_done[g][pr], 1); }
         }
         fence_barrier_init();
     }
@@ -254,40 +253,45 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             const int g = warp - MMA_WARP0;
             const uint64_t d0 = tma::desc_sw128(sbase + OFF_QKV);
             const uint32_t tS = tm + TM_S + g * 128;
-            int k = 0;                                              // windows this group has processed
+            // Items of a unit: i = 0..3 = (window i / 2, head pair i % 2); item i lives in the 64 tensor-memory columns of pair i % 2
+            // (S, then P in place, O in the high half).  The scores of item i + 2 are issued as soon as the softmax warps have read
+            // O of item i (in the middle of the softmax of item i + 1), so that they are ready when that softmax ends.
+            auto issue_qk = [&](int w, int pr) {
+                const uint32_t stage = (uint32_t)((g * 2 + w) * STAGE_BYTES);
+                const uint32_t off = (stage + pr * (2 * HD * 2)) >> 4;       // see window_attn_win8.cu: both heads of a pair read the same Q tile
+                const uint64_t qd = d0 + off + (OFF_Q >> 4), kd = d0 + off + (OFF_K >> 4);
+                const uint64_t qd_odd = qd - (WIN_BYTES >> 4) + ((HD * 2) >> 4), kd_odd = kd + ((HD * 2) >> 4);
+                fence_after_sync();
+                mma_ss_masked(tS + pr * 64, qd, kd, idesc_s, false, 0u, 0u, ALL, ALL);
+                mma_ss_masked(tS + pr * 64, qd_odd, kd_odd, idesc_s, false, ALL, ALL, 0u, 0u);
+                mma_commit(&s_full[g][pr]);
+            };
             for (int u = g, j = 0; u < n_units; u += NG, ++j) {
-#pragma unroll 1
-                for (int w = 0; w < 2; ++w, ++k) {                  // the two windows of the unit, one after the other
-                    const uint32_t stage = (uint32_t)((g * 2 + w) * STAGE_BYTES);
-                    if (w == 0) mbar_wait_spin(&qk_ready[g], (uint32_t)(j & 1));      // K and Q tiles of both windows are written (V follows)
-                    if (k > 0) mbar_wait_spin(&s_free[g], (uint32_t)((k - 1) & 1));
-                    ATRACE(1 + g, k, 0);
+                mbar_wait_spin(&qk_ready[g], (uint32_t)(j & 1));                 // K and Q tiles of both windows are written (V follows)
+#pragma unroll
+                for (int pr = 0; pr < 2; ++pr) {                                // items 0, 1: their columns were freed by the previous unit's items 2, 3
+                    if (j > 0) mbar_wait_spin(&s_free[g][pr], (uint32_t)((2 * j - 1) & 1));
+                    issue_qk(0, pr);
+                }
+                ATRACE(1 + g, 2 * j, 1);
+                mbar_wait_spin(&v_ready[g], (uint32_t)(j & 1));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int w = i >> 1, pr = i & 1;
+                    const uint32_t par = (uint32_t)((2 * j + w) & 1);           // phase of the pair's barriers: one per item on its columns
+                    mbar_wait_spin(&p_full[g][pr], par);
+                    if (pr == 0) ATRACE(1 + g, 2 * j + w, 2);
                     fence_after_sync();
+                    const uint64_t vd = d0 + (((uint32_t)((g * 2 + w) * STAGE_BYTES) + OFF_V + pr * (2 * HD * 2)) >> 4);
 #pragma unroll
-                    for (int pr = 0; pr < HPB; ++pr) {          // see window_attn_win8.cu: both heads of a pair read the same Q tile
-                        const uint32_t off = (stage + pr * (2 * HD * 2)) >> 4;
-                        const uint64_t qd = d0 + off + (OFF_Q >> 4), kd = d0 + off + (OFF_K >> 4);
-                        const uint64_t qd_odd = qd - (WIN_BYTES >> 4) + ((HD * 2) >> 4), kd_odd = kd + ((HD * 2) >> 4);
-#pragma unroll
-                        for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd + 2 * ks, kd + 2 * ks, idesc_s, ks > 0, 0u, 0u, ALL, ALL);
-#pragma unroll
-                        for (int ks = 0; ks < HD / 16; ++ks) mma_ss_masked(tS + pr * 64, qd_odd + 2 * ks, kd_odd + 2 * ks, idesc_s, ks > 0, ALL, ALL, 0u, 0u);
-                        mma_commit(&s_full[g][pr]);             // per head pair: the softmax of pair 0 starts while pair 1's scores are computed
+                    for (int ks = 0; ks < NTOK / 16; ++ks)      // O[128 x 2hd] = P [V_even | V_odd]: P in the low 32 columns of the pair's S
+                        mma_ts(tS + pr * 64 + O_OFF, tS + pr * 64 + ks * 8, vd + ks * (2048 >> 4), idesc_o, ks > 0);
+                    mma_commit(&pv_done[g][pr]);
+                    if (pr == 1) ATRACE(1 + g, 2 * j + w, 3);
+                    if (i < 2) {                                                // scores of item i + 2 (window 1, same pair)
+                        mbar_wait_spin(&s_free[g][pr], par);
+                        issue_qk(1, pr);
                     }
-                    ATRACE(1 + g, k, 1);
-                    if (w == 0) mbar_wait_spin(&v_ready[g], (uint32_t)(j & 1));
-#pragma unroll
-                    for (int pr = 0; pr < HPB; ++pr) {          // O[128 x 2hd] = P [V_even | V_odd]: P in the low 32 columns of the pair's S;
-                        mbar_wait_spin(&p_full[g][pr], (uint32_t)(k & 1));      // pair 0's P V runs during the softmax of pair 1
-                        if (pr == 0) ATRACE(1 + g, k, 2);
-                        fence_after_sync();
-                        const uint64_t vd = d0 + ((stage + OFF_V + pr * (2 * HD * 2)) >> 4);
-#pragma unroll
-                        for (int ks = 0; ks < NTOK / 16; ++ks)
-                            mma_ts(tS + pr * 64 + O_OFF, tS + pr * 64 + ks * 8, vd + ks * (2048 >> 4), idesc_o, ks > 0);
-                    }
-                    mma_commit(&pv_done[g]);
-                    ATRACE(1 + g, k, 3);
                 }
             }
         }
@@ -339,7 +343,6 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         };
         float2 mr_cur = make_float2(0.f, 1.f), mr_next = load_mr(0);
         int cur_t = -1, next_t = 0;
-        int k = 0;                                                  // windows this group has processed
 
         for (int u = g; u < n_units; u += NG) {
             const int t = u / KB, cg = u - t * KB;
@@ -355,8 +358,9 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             if (tid == g * 128) ATRACE(3 + g, u >> 1, 1);
             fence_after_sync();
             if (u >= NG) {
-                // buffer g was read by the group's previous unit: its P V (waited for in its epilogues) and its output stores
-                if (storer) tma::store_wait_read<0>();
+                // buffer g was read by the group's previous unit: its MMAs have completed (waited for in its epilogues); window 0's
+                // output tile (staged in its Q tile) must have left; window 1's (staged in window 0's V tile): before V is written
+                if (storer) tma::store_wait_read<1>();
                 asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
             }
             {
@@ -398,6 +402,10 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&qk_ready[g]);
+                        if (u >= NG) {
+                            if (storer) tma::store_wait_read<0>();
+                            asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+                        }
                     }
                     if (ch == 5) {
                         fence_proxy_async();
@@ -407,119 +415,121 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
                 }
                 if (tid == g * 128) ATRACE(3 + g, u >> 1, 2);
             }
-            // ---------------------------------------------------------------- attention of the unit's two windows
-#pragma unroll 1
-            for (int w = 0; w < 2; ++w, ++k) {
-                const WinBox my_box = win_box(geo, 2 * tile + w);
-                uint64_t mbits = 0;
-                if (s_ > 0) {
-                    if (my_box.last_row) mbits |= (ty >= WS - s_) ? ~yhi : yhi;
-                    if (my_box.last_col) mbits |= (tx >= WS - s_) ? ~xhi : xhi;
-                }
-                const bool any_mask = s_ > 0 && (my_box.last_row || my_box.last_col);
-                const uint32_t par = (uint32_t)(k & 1);
-                float row_sum[HPB];
-#pragma unroll
-                for (int pr = 0; pr < HPB; ++pr) {
-                    mbar_wait(&s_full[g][pr], par);
-                    if (pr == 0 && tid == g * 128) ATRACE(3 + g, u >> 1, 3 + 4 * w);
-                    fence_after_sync();
-                    const int h = cg * G + 2 * pr + hp;
-                    uint64_t tt[NTOK / 2];
-                    uint32_t pk[NTOK / 2];
-#pragma unroll
-                    for (int part = 0; part < 2; ++part) {
-                        uint32_t ra[32];
-                        tmem_ld32(tS + pr * 64 + part * 32, ra);
-                        tmem_wait_ld();
-                        const float* tb = tab_row + h * TAB_HEAD - part * 4 * TAB_ROW;
-#pragma unroll
-                        for (int yj = 0; yj < 4; ++yj) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
-                                tt[part * 16 + yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
-                            }
-                        }
-                    }
-                    if (any_mask) {
-#pragma unroll
-                        for (int j = 0; j < NTOK / 2; ++j) {
-                            float lo, hi;
-                            unpack2(tt[j], lo, hi);
-                            if ((mbits >> (2 * j)) & 1ull) lo += mv2;
-                            if ((mbits >> (2 * j + 1)) & 1ull) hi += mv2;
-                            tt[j] = pack2(lo, hi);
-                        }
-                    }
-                    float m4[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float lo, hi;
-                        unpack2(tt[q], lo, hi);
-                        m4[q] = fmaxf(lo, hi);
-                    }
-#pragma unroll
-                    for (int j = 4; j < NTOK / 2; ++j) {
-                        float lo, hi;
-                        unpack2(tt[j], lo, hi);
-                        m4[j & 3] = fmax3(m4[j & 3], lo, hi);
-                    }
-                    const float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
-                    const uint64_t nmx2 = pack2(-mx, -mx);
-                    uint64_t sum2 = 0ull;
-#pragma unroll
-                    for (int j = 0; j < NTOK / 2; ++j) {
-                        float lo, hi;
-                        unpack2(fadd2(tt[j], nmx2), lo, hi);
-                        const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
-                        sum2 = fadd2(sum2, pack2(p0, p1));
-                        pk[j] = pack_bf16(p0, p1);
-                    }
-                    float a, b;
-                    unpack2(sum2, a, b);
-                    row_sum[pr] = a + b;
-                    tmem_st(tS + pr * 64, pk);                  // P in place: this lane's scores of the pair are all in registers
-                    tmem_wait_st();
-                    fence_before_sync();
-                    mbar_arrive(&p_full[g][pr]);                // the pair's P V starts while the next pair's softmax runs
-                }
-                if (tid == g * 128) ATRACE(3 + g, u >> 1, 4 + 4 * w);
-                // -------------------------------------------------------------- epilogue of the window
-                mbar_wait(&pv_done[g], par);
-                if (tid == g * 128) ATRACE(3 + g, u >> 1, 5 + 4 * w);
+            // ---------------------------------------------------------------- attention: items (window, head pair) = (0,0) (0,1) (1,0) (1,1)
+            // The epilogue of item i - 1 (O -> staging tile) runs in the middle of the softmax of item i, when its P V has long
+            // completed; it frees the pair's columns for the scores of item i + 1.
+            const int jj = u >> 1;                                              // own unit index: phases of the per-pair barriers
+            float prev_sum = 0.f;
+            WinBox boxes[2];
+            boxes[0] = win_box(geo, 2 * tile);
+            boxes[1] = win_box(geo, 2 * tile + 1);
+            const uint32_t stage0 = sbase + OFF_QKV + (uint32_t)((g * 2) * STAGE_BYTES);
+            // staging tiles: window 0 -> its own Q tile (dead after its scores); window 1 -> window 0's V tile (dead after its P V)
+            auto epilogue = [&](int i_prev) {
+                const int w = i_prev >> 1, pr = i_prev & 1;
+                mbar_wait(&pv_done[g][pr], (uint32_t)((2 * jj + w) & 1));
                 fence_after_sync();
-                uint32_t o[HPB][HD];
-#pragma unroll
-                for (int pr = 0; pr < HPB; ++pr) {
-                    if constexpr (HD == 16) tmem_ld16(tS + pr * 64 + O_OFF + hp * HD, o[pr]);
-                    else tmem_ld32(tS + pr * 64 + O_OFF + hp * HD, o[pr]);
-                }
+                uint32_t o[HD];
+                tmem_ld16(tS + pr * 64 + O_OFF + hp * HD, o);
                 tmem_wait_ld();
                 fence_before_sync();
-                mbar_arrive(&s_free[g]);                        // S / P / O columns of the group are free: the next scores may be issued
-                const uint32_t tile_s = sbase + OFF_QKV + (uint32_t)((g * 2 + w) * STAGE_BYTES) + OFF_Q;      // the window's Q tile is dead: staging
+                mbar_arrive(&s_free[g][pr]);                    // the pair's columns are free: the next scores on them may be issued
+                const uint32_t tile_s = stage0 + (w == 0 ? OFF_Q : OFF_V);
+                const float inv = fast_rcp(prev_sum);
 #pragma unroll
-                for (int pr = 0; pr < HPB; ++pr) {
-                    const float inv = fast_rcp(row_sum[pr]);
+                for (int j2 = 0; j2 < HD; j2 += 8) {
+                    const uint32_t chunk = (uint32_t)(((2 * pr + hp) * HD + j2) >> 3) ^ sw;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
+                                 "r"(pack_bf16(__uint_as_float(o[j2]) * inv, __uint_as_float(o[j2 + 1]) * inv)),
+                                 "r"(pack_bf16(__uint_as_float(o[j2 + 2]) * inv, __uint_as_float(o[j2 + 3]) * inv)),
+                                 "r"(pack_bf16(__uint_as_float(o[j2 + 4]) * inv, __uint_as_float(o[j2 + 5]) * inv)),
+                                 "r"(pack_bf16(__uint_as_float(o[j2 + 6]) * inv, __uint_as_float(o[j2 + 7]) * inv)) : "memory");
+                }
+                if (pr == 1) {                                  // both pairs of the window are staged: the tile leaves
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+                    if (storer) {
+                        store_tile(out_maps, geo, boxes[w], tile_s, cg * 64, lane);
+                        tma::store_commit();
+                    }
+                    if (tid == g * 128) ATRACE(3 + g, u >> 1, 6 + 4 * w);
+                }
+            };
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {                       // (not unrolled: four copies of the softmax body thrash the instruction cache)
+                const int w = i >> 1, pr = i & 1;
+                uint64_t mbits = 0;
+                if (s_ > 0) {
+                    if (boxes[w].last_row) mbits |= (ty >= WS - s_) ? ~yhi : yhi;
+                    if (boxes[w].last_col) mbits |= (tx >= WS - s_) ? ~xhi : xhi;
+                }
+                const bool any_mask = s_ > 0 && (boxes[w].last_row || boxes[w].last_col);
+                mbar_wait(&s_full[g][pr], (uint32_t)((2 * jj + w) & 1));
+                if (pr == 0 && tid == g * 128) ATRACE(3 + g, u >> 1, 3 + 4 * w);
+                fence_after_sync();
+                const int h = cg * G + 2 * pr + hp;
+                uint64_t tt[NTOK / 2];
+                uint32_t pk[NTOK / 2];
 #pragma unroll
-                    for (int j = 0; j < HD; j += 8) {
-                        const uint32_t chunk = (uint32_t)(((2 * pr + hp) * HD + j) >> 3) ^ sw;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(tile_s + srow + (chunk << 4)),
-                                     "r"(pack_bf16(__uint_as_float(o[pr][j]) * inv, __uint_as_float(o[pr][j + 1]) * inv)),
-                                     "r"(pack_bf16(__uint_as_float(o[pr][j + 2]) * inv, __uint_as_float(o[pr][j + 3]) * inv)),
-                                     "r"(pack_bf16(__uint_as_float(o[pr][j + 4]) * inv, __uint_as_float(o[pr][j + 5]) * inv)),
-                                     "r"(pack_bf16(__uint_as_float(o[pr][j + 6]) * inv, __uint_as_float(o[pr][j + 7]) * inv)) : "memory");
+                for (int part = 0; part < 2; ++part) {
+                    uint32_t ra[32];
+                    tmem_ld32(tS + pr * 64 + part * 32, ra);
+                    tmem_wait_ld();
+                    const float* tb = tab_row + h * TAB_HEAD - part * 4 * TAB_ROW;
+#pragma unroll
+                    for (int yj = 0; yj < 4; ++yj) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 b = *reinterpret_cast<const float2*>(tb - yj * TAB_ROW + 2 * q);
+                            tt[part * 16 + yj * 4 + q] = ffma2(pack2(__uint_as_float(ra[yj * 8 + 2 * q]), __uint_as_float(ra[yj * 8 + 2 * q + 1])), c2, pack2(b.x, b.y));
+                        }
                     }
                 }
-                fence_proxy_async();
-                asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");      // the window's tile is complete
-                if (storer) {
-                    store_tile(out_maps, geo, my_box, tile_s, cg * 64, lane);
-                    tma::store_commit();
+                if (any_mask) {
+#pragma unroll
+                    for (int j2 = 0; j2 < NTOK / 2; ++j2) {
+                        float lo, hi;
+                        unpack2(tt[j2], lo, hi);
+                        if ((mbits >> (2 * j2)) & 1ull) lo += mv2;
+                        if ((mbits >> (2 * j2 + 1)) & 1ull) hi += mv2;
+                        tt[j2] = pack2(lo, hi);
+                    }
                 }
-                if (tid == g * 128) ATRACE(3 + g, u >> 1, 6 + 4 * w);
+                float m4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float lo, hi;
+                    unpack2(tt[q], lo, hi);
+                    m4[q] = fmaxf(lo, hi);
+                }
+#pragma unroll
+                for (int j2 = 4; j2 < NTOK / 2; ++j2) {
+                    float lo, hi;
+                    unpack2(tt[j2], lo, hi);
+                    m4[j2 & 3] = fmax3(m4[j2 & 3], lo, hi);
+                }
+                const float mx = fmaxf(fmax3(m4[0], m4[1], m4[2]), m4[3]);
+                if (i > 0) epilogue(i - 1);                     // the previous item's O: its P V ran during the score phase above
+                const uint64_t nmx2 = pack2(-mx, -mx);
+                uint64_t sum2 = 0ull;
+#pragma unroll
+                for (int j2 = 0; j2 < NTOK / 2; ++j2) {
+                    float lo, hi;
+                    unpack2(fadd2(tt[j2], nmx2), lo, hi);
+                    const float p0 = fast_exp2(lo), p1 = fast_exp2(hi);
+                    sum2 = fadd2(sum2, pack2(p0, p1));
+                    pk[j2] = pack_bf16(p0, p1);
+                }
+                float a, b;
+                unpack2(sum2, a, b);
+                prev_sum = a + b;
+                tmem_st(tS + pr * 64, pk);                      // P in place: this lane's scores of the pair are all in registers
+                tmem_wait_st();
+                fence_before_sync();
+                mbar_arrive(&p_full[g][pr]);                    // the pair's P V starts while the next item's softmax runs
+                if (pr == 1 && tid == g * 128) ATRACE(3 + g, u >> 1, 4 + 4 * w);
             }
+            epilogue(3);                                        // drain: the unit's last item (its P V is exposed here)
         }
         if (storer) tma::store_wait_all();
     }
@@ -556,7 +566,7 @@ extern "C" int sodt_attn_trace(void* host, size_t bytes) {
 bool attn_block_supported(int H, int W, int C, int heads, int ws, int shift) {
     if (ws != WS || C != KB * 64 || heads <= 0 || C % heads || H % WS || W % (2 * WS) || shift < 0 || shift >= WS) return false;
     const int hd = C / heads;
-    return (hd == 16 || hd == 32) && smem_bytes(heads) <= 227 * 1024;
+    return hd == 16 && smem_bytes(heads) <= 227 * 1024;      // (head pairs of 2 x 16 channels: 64 tensor-memory columns hold S, P and O of a pair)
 }
 
 int attn_block(const void* x, const float* ln_stats, int ln_boxes, float ln_eps, const void* w, const float* colsum, const float* bias,
@@ -583,18 +593,10 @@ int attn_block(const void* x, const float* ln_stats, int ln_boxes, float ln_eps,
     int grid = (int)(geo.total_tiles < num_sms ? geo.total_tiles : num_sms);
     if (shift > 0 && geo.total_tiles > num_sms)
         while (grid > 1 && gcd(grid, geo.nW / 2) != 1) --grid;
-    cudaError_t e;
-    if (C / heads == 16) {
-        auto kern = attn_block_kernel<16>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_status(e);
-        e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, in_maps, out_maps, w_map, p, geo);
-    } else {
-        auto kern = attn_block_kernel<32>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_status(e);
-        e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, in_maps, out_maps, w_map, p, geo);
-    }
+    auto kern = attn_block_kernel<16>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, in_maps, out_maps, w_map, p, geo);
     if (e != cudaSuccess) return cuda_status(e);
     return check_launch();
 }

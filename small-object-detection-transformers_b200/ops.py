@@ -8,6 +8,8 @@ shape functions) so that the modules stay traceable.  No CPU path exists.
 import math
 import weakref
 
+import os
+
 import torch
 
 from . import _capi
@@ -582,12 +584,13 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
     return y
 
 
-# norm1 + qkv Linear + window attention of the C = 192 Swin blocks as one kernel (no qkv tensor).  Bit-identical to the two kernels
-# and 8 % faster than them on an idle GPU (1.38 vs 1.50 ms, shift 0), but inside the power-capped step (SM clock ~1.6 GHz) the
-# latency-bound fused kernel slows down with the clock (1.66 ms) while the memory-bound qkv GEMM does not (0.71 + 0.88 ms), so the
-# model keeps the two kernels by default; ``attn_block`` / sodt_attn_block_fwd stay available (and tested) as an op.
-USE_FUSED_ATTN = False
-FUSED_ATTN_SHIFTED = False   # also for the shifted blocks (1.66-1.78 vs 1.51 ms on an idle GPU)
+# norm1 + qkv Linear + window attention of the C = 192 Swin blocks as one kernel (sodt_attn_block_fwd: no qkv tensor).  Bit-identical
+# to the two kernels.  Alone on an idle GPU: 1.31 ms against 0.75 + 0.75 ms (shift 0), 1.65 against 1.51 ms (shift 2: wrapped border
+# windows).  Inside the power-capped step the unshifted blocks gain more than that difference -- 4.8 GB less HBM traffic per block
+# lets the SM clock rise (same box: 825 -> 852 images/s, 1552 -> 1635 MHz) -- so they use it by default; the shifted blocks keep the
+# two kernels (SODT_FUSED_ATTN_SHIFTED=1: 854 images/s, within noise of the default).
+USE_FUSED_ATTN = os.environ.get("SODT_FUSED_ATTN", "1") == "1"
+FUSED_ATTN_SHIFTED = os.environ.get("SODT_FUSED_ATTN_SHIFTED", "0") == "1"
 
 
 def attn_block_supported(x, heads, ws, shift):

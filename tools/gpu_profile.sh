@@ -14,7 +14,7 @@ echo "launch list rc=$?"
 fi
 if [ "$WHAT" = "launches" ]; then exit 0; fi
 python tools/prof_kernels.py 1 > gpurun_out/${R}_plain_kernels.log 2>&1 || { echo "plain prof_kernels failed"; tail -5 gpurun_out/${R}_plain_kernels.log; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:"window_attn|linear_tc|mlp_tc|cattn|frontend|detect_decode|nms_|add_layernorm|row_stats|stats_finalize" -c 76 -o /tmp/${R}_kernels -f python tools/prof_kernels.py 1 > gpurun_out/${R}_ncu_kernels.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"window_attn|attn_block|linear_tc|mlp_tc|cattn|frontend|detect_decode|nms_|add_layernorm|row_stats|stats_finalize" -c 80 -o /tmp/${R}_kernels -f python tools/prof_kernels.py 1 > gpurun_out/${R}_ncu_kernels.log 2>&1
 echo "set full rc=$?"
 ncu -i /tmp/${R}_kernels.ncu-rep --page raw --csv > gpurun_out/${R}_kernels_raw.csv
 ncu -i /tmp/${R}_kernels.ncu-rep --page source --csv --kernel-name regex:window_attn_win8 > gpurun_out/${R}_win8_source.csv

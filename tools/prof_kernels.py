@@ -43,6 +43,9 @@ for _ in range(reps):
     hid = ops.linear(x1, w1, b1, act="gelu", ln=(mr, gam, bet))                               # norm2 + fc1 + GELU
     ops.linear(hid, w(192, 768), bias(192), residual=xt, want_stats=True)                # fc2 + residual
     ops.mlp_ln(x1, (mr, gam, bet, 1e-5), w1, b1, w(192, 768), bias(192), want_stats=True)       # the same MLP half as one kernel
+    tb = 0.02 * torch.randn(225, 12, device=dev, generator=g)
+    for sh in (0, 2):         # norm1 + qkv + window attention as one kernel
+        ops.attn_block(x1.view(B, 256, 256, 192), (mr, gam, bet, 1e-5), wq, bq, tb, 12, 8, sh)
     ops.conv2d_nhwc(xt.view(B, 256, 256, 192), w(192, 4 * 192), bias(192), (2, 2), (0, 0), "gelu")
     ops.patch_merge_linear(xt.view(B, 256, 256, 192), w(384, 768))
     ops.add_layernorm(xt, None, torch.ones(192, device=dev), torch.zeros(192, device=dev), 1e-5)
