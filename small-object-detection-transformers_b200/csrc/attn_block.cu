@@ -75,8 +75,13 @@ __device__ __forceinline__ WinBox win_box(const Geo& g, long long wdx) {
     const int wy = win / g.nww, wx = win - wy * g.nww;
     r.x0 = wx * WS + g.shift;
     r.y0 = wy * WS + g.shift;
+#ifdef ATTN_X_NOWRAP      // timing experiments only (border windows read zeros past the image edge and lose the wrapped part)
+    r.wrap_x = false;
+    r.wrap_y = false;
+#else
     r.wrap_x = r.x0 + WS > g.W;
     r.wrap_y = r.y0 + WS > g.H;
+#endif
     r.last_row = wy == g.nwh - 1;
     r.last_col = wx == g.nww - 1;
     r.yg_base = b * g.H;
@@ -186,7 +191,10 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
 
     if (warp == TMA_WARP) {
         // ======================================================= producer: x tile of every window pair, W ring of every unit
-        if (lane == 0) { tma::prefetch_map(&in_maps.full); tma::prefetch_map(&w_map); }
+        if (lane == 0) {
+            tma::prefetch_map(&in_maps.full); tma::prefetch_map(&w_map);
+            if (geo.shift > 0) { tma::prefetch_map(&in_maps.row8); tma::prefetch_map(&in_maps.row_a); tma::prefetch_map(&in_maps.row_b); }
+        }
         int kbc = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
@@ -311,8 +319,6 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         const int r0 = WS - 1 - tx, cp = r0 & 1;
         const float* tab_row = tab + cp * tab_copy_stride(heads) + (ty + WS - 1) * TAB_ROW + (r0 - cp);
         const int s_ = geo.shift;
-        const uint64_t yhi = s_ > 0 ? (~0ull << (8 * (WS - s_))) : 0ull;
-        const uint64_t xhi = s_ > 0 ? 0x0101010101010101ull * (uint64_t)((0xFFu << (WS - s_)) & 0xFFu) : 0ull;
         const uint32_t srow = (uint32_t)ti * 128, sw = (uint32_t)(ti & 7);
         const bool storer = quarter == 0;                          // warp 0 of the group issues the group's TMA stores
 
@@ -423,6 +429,12 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             WinBox boxes[2];
             boxes[0] = win_box(geo, 2 * tile);
             boxes[1] = win_box(geo, 2 * tile + 1);
+            if (storer && lane == 0) {                          // descriptors of the stores this unit will issue (the row maps are rarely used)
+                tma::prefetch_map(&out_maps.full);
+                if (boxes[1].wrap_x || boxes[1].wrap_y || boxes[0].wrap_y) {
+                    tma::prefetch_map(&out_maps.row8); tma::prefetch_map(&out_maps.row_a); tma::prefetch_map(&out_maps.row_b);
+                }
+            }
             const uint32_t stage0 = sbase + OFF_QKV + (uint32_t)((g * 2) * STAGE_BYTES);
             // staging tiles: window 0 -> its own Q tile (dead after its scores); window 1 -> window 0's V tile (dead after its P V)
             auto epilogue = [&](int i_prev) {
@@ -458,12 +470,23 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
 #pragma unroll 1
             for (int i = 0; i < 4; ++i) {                       // (not unrolled: four copies of the softmax body thrash the instruction cache)
                 const int w = i >> 1, pr = i & 1;
-                uint64_t mbits = 0;
+                // shifted-window mask of a border window: key (yj, xj) is masked for this query if their row regions differ (last window
+                // row) or their column regions differ (last window column) -- one test per key row + four precomputed column pairs
+                uint32_t rowm = 0;                                              // bit yj: the whole key row is masked
+                uint64_t colp[4] = {0ull, 0ull, 0ull, 0ull};                    // addend pairs of key columns (2q, 2q + 1)
                 if (s_ > 0) {
-                    if (boxes[w].last_row) mbits |= (ty >= WS - s_) ? ~yhi : yhi;
-                    if (boxes[w].last_col) mbits |= (tx >= WS - s_) ? ~xhi : xhi;
+                    if (boxes[w].last_row) rowm = (ty >= WS - s_) ? ~(0xFFu << (WS - s_)) & 0xFFu : (0xFFu << (WS - s_)) & 0xFFu;
+                    if (boxes[w].last_col) {
+                        const uint32_t cm = (tx >= WS - s_) ? ~(0xFFu << (WS - s_)) & 0xFFu : (0xFFu << (WS - s_)) & 0xFFu;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) colp[q] = pack2((cm >> (2 * q)) & 1u ? mv2 : 0.f, (cm >> (2 * q + 1)) & 1u ? mv2 : 0.f);
+                    }
                 }
+#ifdef ATTN_X_NOMASK      // timing experiments only (wrong results on border windows)
+                const bool any_mask = false;
+#else
                 const bool any_mask = s_ > 0 && (boxes[w].last_row || boxes[w].last_col);
+#endif
                 mbar_wait(&s_full[g][pr], (uint32_t)((2 * jj + w) & 1));
                 if (pr == 0 && tid == g * 128) ATRACE(3 + g, u >> 1, 3 + 4 * w);
                 fence_after_sync();
@@ -485,14 +508,13 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
                         }
                     }
                 }
-                if (any_mask) {
+                if (any_mask) {                                 // (t + 0 = t: the unmasked keys keep their value)
+                    const uint64_t mv22 = pack2(mv2, mv2);
 #pragma unroll
-                    for (int j2 = 0; j2 < NTOK / 2; ++j2) {
-                        float lo, hi;
-                        unpack2(tt[j2], lo, hi);
-                        if ((mbits >> (2 * j2)) & 1ull) lo += mv2;
-                        if ((mbits >> (2 * j2 + 1)) & 1ull) hi += mv2;
-                        tt[j2] = pack2(lo, hi);
+                    for (int yj = 0; yj < WS; ++yj) {
+                        const bool rm = (rowm >> yj) & 1u;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) tt[yj * 4 + q] = fadd2(tt[yj * 4 + q], rm ? mv22 : colp[q]);
                     }
                 }
                 float m4[4];
