@@ -97,7 +97,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
 }
 
 // The KB channel blocks of one window of x, issued by the whole producer warp: tile kb lands at dst + kb * XKB_BYTES
+template <bool SHIFTED>
 __device__ __forceinline__ void load_window(const Maps& m, const Geo& geo, const WinBox& b, uint32_t dst, uint64_t* bar, int lane) {
+    if constexpr (!SHIFTED) {                                // unshifted frame: no window wraps
+        if (lane < KB) tma::load_3d(dst + lane * XKB_BYTES, &m.full, bar, lane * 64, b.x0, b.yg_base + b.y0);
+        return;
+    }
     const int per_box = !b.wrap_x && !b.wrap_y ? 1 : (b.wrap_x ? 2 * WS : WS);
     for (int item = lane; item < KB * per_box; item += 32) {
         const int bi = item / per_box, sub = item - bi * per_box;
@@ -115,8 +120,9 @@ __device__ __forceinline__ void load_window(const Maps& m, const Geo& geo, const
         }
     }
 }
+template <bool SHIFTED>
 __device__ __forceinline__ void store_tile(const Maps& m, const Geo& geo, const WinBox& b, uint32_t sm, int c0, int lane) {
-    if (!b.wrap_x && !b.wrap_y) {
+    if (!SHIFTED || (!b.wrap_x && !b.wrap_y)) {
         if (lane == 0) tma::store_3d(&m.full, sm, c0, b.x0, b.yg_base + b.y0);
         return;
     }
@@ -143,7 +149,8 @@ struct Params {
     float scale, mask_value;
 };
 
-template <int HD>
+// SHIFTED = false: the un-shifted blocks' instantiation without the wrapped-window and mask code (smaller hot loop)
+template <int HD, bool SHIFTED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ Maps out_maps, const __grid_constant__ CUtensorMap w_map,
                   const Params p, const Geo geo) {
@@ -198,14 +205,15 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         int kbc = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+            const WinBox wb0 = win_box(geo, 2 * tile), wb1 = win_box(geo, 2 * tile + 1);     // (before the wait: the x tile's load is on the critical path of every tile)
             if (lane == 0) {
                 if (t > 0) mbar_wait(&x_empty, (uint32_t)((t - 1) & 1));
                 ATRACE(5, t, 0);
                 tma::expect_tx(&x_full, X_BYTES);
             }
             __syncwarp();
-            load_window(in_maps, geo, win_box(geo, 2 * tile), sbase + OFF_X, &x_full, lane);
-            load_window(in_maps, geo, win_box(geo, 2 * tile + 1), sbase + OFF_X + WIN_BYTES, &x_full, lane);
+            load_window<SHIFTED>(in_maps, geo, wb0, sbase + OFF_X, &x_full, lane);
+            load_window<SHIFTED>(in_maps, geo, wb1, sbase + OFF_X + WIN_BYTES, &x_full, lane);
             if (lane == 0) {
                 ATRACE(5, t, 1);
                 for (int cg = 0; cg < KB; ++cg) {
@@ -318,7 +326,7 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         const uint64_t c2 = pack2(c, c);
         const int r0 = WS - 1 - tx, cp = r0 & 1;
         const float* tab_row = tab + cp * tab_copy_stride(heads) + (ty + WS - 1) * TAB_ROW + (r0 - cp);
-        const int s_ = geo.shift;
+        const int s_ = SHIFTED ? geo.shift : 0;
         const uint32_t srow = (uint32_t)ti * 128, sw = (uint32_t)(ti & 7);
         const bool storer = quarter == 0;                          // warp 0 of the group issues the group's TMA stores
 
@@ -426,12 +434,10 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             // completed; it frees the pair's columns for the scores of item i + 1.
             const int jj = u >> 1;                                              // own unit index: phases of the per-pair barriers
             float prev_sum = 0.f;
-            WinBox boxes[2];
-            boxes[0] = win_box(geo, 2 * tile);
-            boxes[1] = win_box(geo, 2 * tile + 1);
+            const WinBox box0 = win_box(geo, 2 * tile), box1 = win_box(geo, 2 * tile + 1);      // (two named boxes: an indexed array lives in local memory)
             if (storer && lane == 0) {                          // descriptors of the stores this unit will issue (the row maps are rarely used)
                 tma::prefetch_map(&out_maps.full);
-                if (boxes[1].wrap_x || boxes[1].wrap_y || boxes[0].wrap_y) {
+                if (SHIFTED && (box1.wrap_x || box1.wrap_y || box0.wrap_y)) {
                     tma::prefetch_map(&out_maps.row8); tma::prefetch_map(&out_maps.row_a); tma::prefetch_map(&out_maps.row_b);
                 }
             }
@@ -461,7 +467,7 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
                     fence_proxy_async();
                     asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
                     if (storer) {
-                        store_tile(out_maps, geo, boxes[w], tile_s, cg * 64, lane);
+                        store_tile<SHIFTED>(out_maps, geo, w ? box1 : box0, tile_s, cg * 64, lane);
                         tma::store_commit();
                     }
                     if (tid == g * 128) ATRACE(3 + g, u >> 1, 6 + 4 * w);
@@ -474,9 +480,10 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
                 // row) or their column regions differ (last window column) -- one test per key row + four precomputed column pairs
                 uint32_t rowm = 0;                                              // bit yj: the whole key row is masked
                 uint64_t colp[4] = {0ull, 0ull, 0ull, 0ull};                    // addend pairs of key columns (2q, 2q + 1)
-                if (s_ > 0) {
-                    if (boxes[w].last_row) rowm = (ty >= WS - s_) ? ~(0xFFu << (WS - s_)) & 0xFFu : (0xFFu << (WS - s_)) & 0xFFu;
-                    if (boxes[w].last_col) {
+                const bool last_row = w ? box1.last_row : box0.last_row, last_col = w ? box1.last_col : box0.last_col;
+                if (SHIFTED && s_ > 0) {
+                    if (last_row) rowm = (ty >= WS - s_) ? ~(0xFFu << (WS - s_)) & 0xFFu : (0xFFu << (WS - s_)) & 0xFFu;
+                    if (last_col) {
                         const uint32_t cm = (tx >= WS - s_) ? ~(0xFFu << (WS - s_)) & 0xFFu : (0xFFu << (WS - s_)) & 0xFFu;
 #pragma unroll
                         for (int q = 0; q < 4; ++q) colp[q] = pack2((cm >> (2 * q)) & 1u ? mv2 : 0.f, (cm >> (2 * q + 1)) & 1u ? mv2 : 0.f);
@@ -485,7 +492,7 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
 #ifdef ATTN_X_NOMASK      // timing experiments only (wrong results on border windows)
                 const bool any_mask = false;
 #else
-                const bool any_mask = s_ > 0 && (boxes[w].last_row || boxes[w].last_col);
+                const bool any_mask = SHIFTED && s_ > 0 && (last_row || last_col);
 #endif
                 mbar_wait(&s_full[g][pr], (uint32_t)((2 * jj + w) & 1));
                 if (pr == 0 && tid == g * 128) ATRACE(3 + g, u >> 1, 3 + 4 * w);
@@ -615,7 +622,7 @@ int attn_block(const void* x, const float* ln_stats, int ln_boxes, float ln_eps,
     int grid = (int)(geo.total_tiles < num_sms ? geo.total_tiles : num_sms);
     if (shift > 0 && geo.total_tiles > num_sms)
         while (grid > 1 && gcd(grid, geo.nW / 2) != 1) --grid;
-    auto kern = attn_block_kernel<16>;
+    auto kern = shift > 0 ? attn_block_kernel<16, true> : attn_block_kernel<16, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     e = launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem, stream, true, in_maps, out_maps, w_map, p, geo);
