@@ -358,9 +358,12 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
         float2 mr_cur = make_float2(0.f, 1.f), mr_next = load_mr(0);
         int cur_t = -1, next_t = 0;
 
+        // the unit's tile geometry is loop-carried: the next unit's is computed while the last item's P V runs (its 64-bit divisions
+        // are not free, and nothing else is ready then)
+        int t = g / KB, cg = g - t * KB;
+        WinBox box0 = win_box(geo, 2 * ((long long)blockIdx.x + (long long)t * gridDim.x));
+        WinBox box1 = win_box(geo, 2 * ((long long)blockIdx.x + (long long)t * gridDim.x) + 1);
         for (int u = g; u < n_units; u += NG) {
-            const int t = u / KB, cg = u - t * KB;
-            const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
             // ---------------------------------------------------------------- D of unit u -> bf16 K | Q | V tiles of both windows
             if (t != cur_t) { mr_cur = mr_next; cur_t = t; }
             {
@@ -434,7 +437,6 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
             // completed; it frees the pair's columns for the scores of item i + 1.
             const int jj = u >> 1;                                              // own unit index: phases of the per-pair barriers
             float prev_sum = 0.f;
-            const WinBox box0 = win_box(geo, 2 * tile), box1 = win_box(geo, 2 * tile + 1);      // (two named boxes: an indexed array lives in local memory)
             if (storer && lane == 0) {                          // descriptors of the stores this unit will issue (the row maps are rarely used)
                 tma::prefetch_map(&out_maps.full);
                 if (SHIFTED && (box1.wrap_x || box1.wrap_y || box0.wrap_y)) {
@@ -558,7 +560,17 @@ attn_block_kernel(const __grid_constant__ Maps in_maps, const __grid_constant__ 
                 mbar_arrive(&p_full[g][pr]);                    // the pair's P V starts while the next item's softmax runs
                 if (pr == 1 && tid == g * 128) ATRACE(3 + g, u >> 1, 4 + 4 * w);
             }
+            int nt = t, ncg = cg;
+            WinBox nb0 = box0, nb1 = box1;
+            if (u + NG < n_units) {
+                nt = (u + NG) / KB; ncg = u + NG - nt * KB;
+                if (nt != t) {
+                    const long long ntile = (long long)blockIdx.x + (long long)nt * gridDim.x;
+                    nb0 = win_box(geo, 2 * ntile); nb1 = win_box(geo, 2 * ntile + 1);
+                }
+            }
             epilogue(3);                                        // drain: the unit's last item (its P V is exposed here)
+            t = nt; cg = ncg; box0 = nb0; box1 = nb1;
         }
         if (storer) tma::store_wait_all();
     }
