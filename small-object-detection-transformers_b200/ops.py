@@ -585,13 +585,12 @@ def linear(x, weight, bias=None, act=None, residual=None, x2=None, out=None, ln=
 
 
 # norm1 + qkv Linear + window attention of the C = 192 Swin blocks as one kernel (sodt_attn_block_fwd: no qkv tensor).  Bit-identical
-# to the two kernels.  Alone on an idle GPU: 1.29 ms against 0.75 + 0.75 ms (shift 0), 1.57 against 1.51 ms (shift 2: wrapped, masked
+# to the two kernels.  Alone on an idle GPU: 1.13 ms against 0.75 + 0.75 ms (shift 0), 1.41 against 1.51 ms (shift 2: wrapped, masked
 # border windows).  Inside the power-capped step it gains more than that difference -- 4.8 GB less HBM traffic per block lets the SM
-# clock rise (same box, alternating runs: 820 -> 834 images/s) -- so the unshifted blocks use it by default.  Fusing the shifted blocks
-# too (SODT_FUSED_ATTN_SHIFTED=1) is worth another +1.1 %; the default keeps the two kernels there so that the stage-1 window-attention
-# launches bench.py reports its roofline on still run in the measured step.
+# clock rise (same box, alternating runs: 820 -> 834 images/s with the un-shifted blocks fused, another +1.1 % with the shifted ones).
+# SODT_FUSED_ATTN=0 / SODT_FUSED_ATTN_SHIFTED=0 select the two kernels for all / for the shifted blocks.
 USE_FUSED_ATTN = os.environ.get("SODT_FUSED_ATTN", "1") == "1"
-FUSED_ATTN_SHIFTED = os.environ.get("SODT_FUSED_ATTN_SHIFTED", "0") == "1"
+FUSED_ATTN_SHIFTED = os.environ.get("SODT_FUSED_ATTN_SHIFTED", "1") == "1"
 
 
 def attn_block_supported(x, heads, ws, shift):

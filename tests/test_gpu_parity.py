@@ -681,7 +681,7 @@ def test_model_detector_graph_replay_matches_eager_and_stream():
     for b, (d, c) in zip(batches, want):                      # replayed graph (second and third call reuse the capture)
         d2, c2 = graph.detect(*b)
         assert torch.equal(c2, c) and torch.equal(d2, d)
-    assert graph.launches_per_step(batches[0][0].cuda(), batches[0][1].cuda()) > 80       # 86 sodt kernels per step at this size
+    assert graph.launches_per_step(batches[0][0].cuda(), batches[0][1].cuda()) >= 70      # 80 sodt kernels per step at this size (86 with SODT_FUSED_ATTN=0)
     got = [(d.clone(), c.clone()) for d, c in graph.detect_stream(iter(batches))]
     assert len(got) == len(want)
     for (d2, c2), (d, c) in zip(got, want):

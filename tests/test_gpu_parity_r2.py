@@ -81,7 +81,7 @@ def test_detector_1024_bf16_graph_path_vs_oracle():
     # (2) graph replay == eager step, bit for bit, and it produces detections at this threshold
     buf_graph = det.detect_device(rgb8.cuda(), ir8.cuda())
     flat_graph = buf_graph.flat.clone()
-    assert det.launches_per_step(rgb8.cuda(), ir8.cuda()) > 80
+    assert det.launches_per_step(rgb8.cuda(), ir8.cuda()) >= 70      # 80 with the fused attention half, 86 without
     eager = Detector(state_dict=sd, device="cuda", dtype=torch.bfloat16, conf_thres=1e-4, iou_thres=0.45, cuda_graph=False)
     buf_eager = eager.detect_device(rgb8.cuda(), ir8.cuda())
     assert torch.equal(flat_graph, buf_eager.flat)

@@ -60,6 +60,7 @@ lines = [f"# ncu --set full, one launch per kernel ({os.path.basename(rep)}; B =
          "|---|" + "---|" * (len(cols) + 1)]
 traffic = None
 tensor_pct = {}
+traffic_by_kernel = {}
 for r in data:
     name = r[col["Kernel Name"]].replace("void ", "").replace("sodt::<unnamed>::", "").split("(")[0]
     cells = []
@@ -72,7 +73,10 @@ for r in data:
     stalls = ", ".join(f"{n} {100 * v / tot:.0f}%" for v, n in st[:5])
     lines.append(f"| `{name[:60]}` | " + " | ".join(cells) + f" | {stalls} |")
     tp = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
-    if tp in col and ("window_attn" in name or "cattn" in name) and "prep" not in name:
+    if any(kname in name for kname in ("window_attn_win8_kernel<16>", "attn_block_kernel", "mlp_tc_kernel")) and name.split("::")[-1] not in traffic_by_kernel:
+        traffic_by_kernel[name.split("::")[-1]] = (to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) +
+                                                   to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]]))
+    if tp in col and ("window_attn" in name or "cattn" in name or "attn_block" in name) and "prep" not in name:
         tensor_pct.setdefault(name.split("::")[-1], num(r[col[tp]]))
     if traffic is None and "window_attn_win8_kernel<16>" in name:
         rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
@@ -83,11 +87,12 @@ for r in data:
 open(os.path.join(out_dir, f"{rnd}_kernels_ncu.md"), "w").write("\n".join(lines) + "\n")
 if traffic:
     import hashlib
+    traffic["traffic_by_kernel"] = traffic_by_kernel        # DRAM bytes of one launch of the kernels bench.py reports a roofline on
     traffic["attention_tensor_pipe_pct"] = tensor_pct       # BASELINE.json's "attn tensor-pipe %" (sm__pipe_tensor_cycles_active)
     # stamp: bench.py reports these numbers only while the kernel sources are the ones that were profiled
     csrc = os.path.join(ROOT, "small-object-detection-transformers_b200", "csrc")
     traffic["source_sha256"] = {f: hashlib.sha256(open(os.path.join(csrc, f), "rb").read()).hexdigest()
-                                for f in ("window_attn_win8.cu", "window_attn_flash.cu", "cattn.cu", "tc05.cuh", "tma.cuh")}
+                                for f in ("window_attn_win8.cu", "window_attn_flash.cu", "cattn.cu", "attn_block.cu", "mlp_tc.cu", "tc05.cuh", "tma.cuh")}
     json.dump(traffic, open(os.path.join(out_dir, f"{rnd}_roofline_traffic.json"), "w"), indent=1)
 # trim the launch list to whole steps: from the first front-end launch to the last one (exclusive)
 lrows = open(launches).read().splitlines()
