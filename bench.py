@@ -433,6 +433,9 @@ def run_sodt(args):
         else:
             achieved, peak, unit, src = work / (avg_ms * 1e-3) / 1e12, tf_peak, "TFLOP/s", "bf16_tflops_sustained"
             extra = {"alg_flops_per_launch": work}
+        if short == "attn_block":      # the fusion trades roofline fraction for time: 4x fewer DRAM bytes than the two kernels it replaces
+            extra["note"] = ("replaces the norm1 + qkv GEMM (0.71-0.82 ms in step) and the stage-1 window attention (0.88 ms, 0.55 of HBM): "
+                             "bound by the MUFU / per-item softmax chain of its two softmax groups, not by a pipe (DESIGN.md 4.8)")
         roof.append({"kernel": desc, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                      "traffic": traffic, "avg_launch_ms": avg_ms, "launches_per_step": len(durs) / steps,
                      "ms_per_step": sum(durs) / steps, **extra,
